@@ -1,0 +1,184 @@
+"""ctypes binding of the C ABI in include/gvqa_b200.h (graphvqa_b200/lib/libgvqa_b200.so).
+
+This is the only place the package talks to native code.  There is NO fallback: if the shared
+library is missing or a call fails, a RuntimeError is raised.  Device pointers are taken from
+torch tensors (``data_ptr()``) and work is enqueued on torch's current CUDA stream, so calls
+compose with torch ops and are CUDA-graph capturable.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
+ABI_VERSION = 1
+
+EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
+VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED = 0, 1, 2
+
+_c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
+                                        ctypes.c_void_p, ctypes.c_size_t)
+
+
+class GatHopArgs(ctypes.Structure):
+    """Mirror of ``struct gvqa_gat_hop_args`` (field order and types must match the header)."""
+    _fields_ = [
+        ("x_l", _c_vp), ("ldx", _c_i64), ("x_graph", _c_vp), ("a_node", _c_vp), ("a_graph", _c_vp),
+        ("a_edge", _c_vp), ("lde", _c_i64), ("rowptr", _c_vp), ("col_src", _c_vp), ("perm", _c_vp),
+        ("graph_ptr", _c_vp), ("node_graph", _c_vp), ("h_prev", _c_vp), ("bias", _c_vp),
+        ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("alpha_out", _c_vp),
+        ("num_nodes", _c_i64), ("num_edges", _c_i64), ("num_graphs", _c_i64),
+        ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
+        ("max_nodes_per_graph", _c_i32), ("variant", _c_i32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/gvqa_b200.h
+SIGNATURES = {
+    "gvqa_abi_version": (ctypes.c_int, []),
+    "gvqa_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "gvqa_csr_workspace_bytes": (_c_sz, [_c_i64, _c_i64]),
+    "gvqa_build_csr": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                      _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
+    "gvqa_skinny_matmul_f32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, ctypes.c_int,
+                                              ctypes.c_int, _c_vp]),
+    "gvqa_gat_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatHopArgs), _c_vp]),
+    "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
+                                                _c_f32, _c_i32, _c_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise loudly when it is absent or stale."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "graphvqa_b200: CUDA library %s not found. Build it with "
+                "`python -m graphvqa_b200.build` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.gvqa_abi_version() != ABI_VERSION:
+            raise RuntimeError("graphvqa_b200: ABI version mismatch (library %d, binding %d); rebuild"
+                               % (handle.gvqa_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError("graphvqa_b200: %s failed: %s (status %d)"
+                           % (what, lib().gvqa_error_string(status).decode(), status))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("graphvqa_b200 runs on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device)
+
+
+def require_f32c(**tensors):
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if t.dtype != torch.float32:
+            raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+
+
+# ------------------------------------------------------------------------------------------
+# thin tensor-level wrappers
+# ------------------------------------------------------------------------------------------
+def build_csr(edge_index, batch, num_graphs):
+    """Returns dict(rowptr, col_src, perm, graph_ptr, node_graph, stats) of int32 tensors."""
+    require_cuda(edge_index, batch)
+    if edge_index.dtype != torch.int64 or batch.dtype != torch.int64:
+        raise TypeError("edge_index and batch must be int64 (the reference's layout)")
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must be [2, E]")
+    edge_index = edge_index.contiguous()
+    batch = batch.contiguous()
+    dev = edge_index.device
+    n, e = batch.numel(), edge_index.size(1)
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = dict(rowptr=torch.empty(n + 1, **i32), col_src=torch.empty(max(e, 1), **i32),
+               perm=torch.empty(max(e, 1), **i32), graph_ptr=torch.empty(num_graphs + 1, **i32),
+               node_graph=torch.empty(max(n, 1), **i32), stats=torch.empty(8, **i32))
+    ws_bytes = lib().gvqa_csr_workspace_bytes(n, e)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().gvqa_build_csr(ptr(edge_index), e, ptr(batch), n, num_graphs, ptr(out["rowptr"]),
+                                   ptr(out["col_src"]), ptr(out["perm"]), ptr(out["graph_ptr"]),
+                                   ptr(out["node_graph"]), ptr(out["stats"]), ptr(ws), ws_bytes,
+                                   stream_handle(dev)), "gvqa_build_csr")
+    return out
+
+
+def skinny_matmul(x, v, out=None):
+    """out[M,K] = x[M,F] @ v[K,F]^T ; x may be a row-strided view (stride(1) == 1)."""
+    require_cuda(x, v)
+    if x.dtype != torch.float32 or v.dtype != torch.float32:
+        raise TypeError("skinny_matmul expects float32")
+    if x.dim() != 2 or v.dim() != 2 or x.size(1) != v.size(1) or x.stride(1) != 1 or not v.is_contiguous():
+        raise ValueError("skinny_matmul: x [M,F] (unit column stride), v [K,F] contiguous")
+    m, f = x.shape
+    k = v.size(0)
+    if out is None:
+        out = torch.empty(m, k, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_skinny_matmul_f32(ptr(x), x.stride(0) if m > 1 else f, ptr(v), ptr(out), m, f, k,
+                                           stream_handle(x.device)), "gvqa_skinny_matmul_f32")
+    return out
+
+
+def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, x_graph=None,
+            a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
+            negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
+            variant=VARIANT_AUTO):
+    require_cuda(x_l, a_node, a_edge, h_out, x_graph, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
+    require_f32c(a_node=a_node, h_out=h_out, x_graph=x_graph, a_graph=a_graph, h_prev=h_prev, bias=bias,
+                 ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
+    n = h_out.size(0)
+    e = csr["num_edges"]
+    a = GatHopArgs()
+    a.x_l, a.ldx = ptr(x_l), (x_l.stride(0) if ldx is None else ldx)
+    a.x_graph, a.a_node, a.a_graph = ptr(x_graph), ptr(a_node), ptr(a_graph)
+    a.a_edge, a.lde = ptr(a_edge), (a_edge.stride(0) if lde is None else lde)
+    a.rowptr, a.col_src, a.perm = ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"])
+    a.graph_ptr, a.node_graph = ptr(csr["graph_ptr"]), ptr(csr["node_graph"])
+    a.h_prev, a.bias, a.ep_scale, a.ep_shift = ptr(h_prev), ptr(bias), ptr(ep_scale), ptr(ep_shift)
+    a.h_out, a.alpha_out = ptr(h_out), ptr(alpha_out)
+    a.num_nodes, a.num_edges = n, e
+    a.num_graphs = csr["num_graphs"] if num_graphs is None else num_graphs
+    a.heads, a.channels, a.negative_slope, a.epilogue = heads, channels, negative_slope, epilogue
+    a.max_nodes_per_graph, a.variant = max_nodes_per_graph, variant
+    with torch.cuda.device(h_out.device):
+        check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
+    return h_out
+
+
+def graph_layernorm(x, graph_ptr, num_graphs, weight, bias, eps, out=None, max_nodes_per_graph=0):
+    require_cuda(x, graph_ptr, weight, bias)
+    require_f32c(x=x, weight=weight, bias=bias, out=out)
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_graph_layernorm_f32(ptr(x), ptr(graph_ptr), ptr(weight), ptr(bias), ptr(out),
+                                             x.size(0), num_graphs, x.size(1), eps, max_nodes_per_graph,
+                                             stream_handle(x.device)), "gvqa_graph_layernorm_f32")
+    return out

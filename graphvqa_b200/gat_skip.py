@@ -1,0 +1,248 @@
+"""B200 engine behind the reference's ``gat_skip`` operator surface.
+
+Mirrors the constructor / ``forward`` signatures, attribute names and ``state_dict`` keys of the
+reference's ``gat`` (gat_skip.py:16-213) and ``gat_seq`` (gat_skip.py:220-279), so a checkpoint
+trained with the reference loads unchanged, but executes the message passing through the C ABI in
+``include/gvqa_b200.h``:
+
+  per batch   gvqa_build_csr (cached on the SceneGraphBatch), edge-logit skinny projection for all
+              hops at once (edge_attr is hop-invariant), per-graph instruction terms (2 small bmm);
+  per hop     node projection  h @ W_h^T  (cuBLAS fp32, TF32 off),
+              gvqa_skinny_matmul_f32 for the collapsed a_l/a_r node logits,
+              gvqa_gat_hop_f32: gather + logits + segment softmax + aggregate + head mean + bias +
+              skip + BatchNorm(eval) + ReLU in ONE kernel.
+
+The reference's  cat([h, ins[batch]]) @ W^T  is evaluated as  h @ W[:, :F]^T + (ins @ W[:, F:]^T)[batch]
+and  <W x, att_h>  as  x . (W_h^T att_h)   -- same mathematics, fp32 rounding
+differences of order 1e-6.  Inference only: ``forward`` raises in training mode (attention dropout
+and BatchNorm batch statistics, gat_skip.py:190/274, are not part of the engine).  CUDA only: there
+is no CPU fallback.
+"""
+import contextlib
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .graph_batch import GraphCSR
+
+
+def _glorot_(t):
+    """torch_geometric.nn.inits.glorot: U(-a,a), a = sqrt(6/(size(-2)+size(-1)))."""
+    bound = (6.0 / (t.size(-2) + t.size(-1))) ** 0.5
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
+
+
+@contextlib.contextmanager
+def _strict_fp32_matmul():
+    """The 1e-4 parity bar rules out TF32 for the projections (hard part 1)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _collapse(att, weight, heads):
+    """V[h,:] = sum_c att[0,h,c] * W[h*C+c,:]  in float64 -> float32  ([H, in])."""
+    h = heads
+    c = weight.size(0) // h
+    v = torch.einsum("hc,hcf->hf", att.detach().double().view(h, c), weight.detach().double().view(h, c, -1))
+    return v.float()
+
+
+def _param_key(module):
+    return tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+
+
+def _require_inference(module, *tensors):
+    if module.training:
+        raise NotImplementedError(
+            "%s: the B200 engine implements the eval-mode path only (call .eval()); training through "
+            "the fused kernels (autograd, attention dropout, BatchNorm batch statistics) is not built"
+            % type(module).__name__)
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("%s: inputs require grad; run under torch.no_grad()" % type(module).__name__)
+
+
+class gat(nn.Module):
+    """Edge-featured multi-head GAT convolution with the reference signature (gat_skip.py:60-63)."""
+
+    def __init__(self, in_channels, out_channels, edge_in_channels, heads=1, concat=True,
+                 negative_slope=0.2, dropout=0.0, add_self_loops=True, bias=True, **kwargs):
+        super().__init__()
+        if not isinstance(in_channels, int):
+            raise NotImplementedError("bipartite (tuple) in_channels are not used by GraphVQA")
+        if concat:
+            raise NotImplementedError("concat=True is never instantiated by GraphVQA (gat_skip.py:231)")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.add_self_loops = add_self_loops   # stored, never used -- like the reference (:73)
+        self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.lin_r = self.lin_l                 # shared module: both keys appear in the state_dict
+        self.lin_e = nn.Linear(edge_in_channels, heads * out_channels, bias=False)
+        self.att_e = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_l = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_r = nn.Parameter(torch.empty(1, heads, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self._packed = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # same order as gat_skip.py:101-108 so a seeded construction matches the reference
+        _glorot_(self.lin_l.weight)
+        _glorot_(self.lin_r.weight)
+        _glorot_(self.lin_e.weight)
+        _glorot_(self.att_l)
+        _glorot_(self.att_r)
+        _glorot_(self.att_e)
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    # ---- weight prepack (cached until a parameter changes) ---------------------------------
+    def packed(self):
+        key = _param_key(self)
+        if self._packed is None or self._packed["key"] != key:
+            h = self.heads
+            v_l = _collapse(self.att_l, self.lin_l.weight, h)
+            v_r = _collapse(self.att_r, self.lin_l.weight, h)
+            v_e = _collapse(self.att_e, self.lin_e.weight, h)
+            self._packed = dict(key=key, v_node=torch.cat([v_l, v_r]).contiguous(), v_l=v_l, v_r=v_r,
+                                v_edge=v_e.contiguous())
+        return self._packed
+
+    def forward(self, x, edge_index, edge_attr, size=None, return_attention_weights=None, csr=None):
+        """x [N, in], edge_index [2,E] i64, edge_attr [E, edge_in] -> [N, out]
+        (+ (edge_index, alpha[E,H]) when return_attention_weights is a bool, gat_skip.py:170-175)."""
+        _require_inference(self, x, edge_attr)
+        _cabi.require_cuda(x, edge_attr, edge_index)
+        assert x.dim() == 2, "Static graphs not supported in `GATConv`."
+        n, e, h, c = x.size(0), edge_index.size(1), self.heads, self.out_channels
+        if csr is None:  # stand-alone call: the whole input is one graph
+            csr = GraphCSR.build(edge_index, torch.zeros(n, dtype=torch.int64, device=x.device), 1)
+        pk = self.packed()
+        x = x.contiguous().float()
+        edge_attr = edge_attr.contiguous().float()
+        with _strict_fp32_matmul():
+            x_l = torch.mm(x, self.lin_l.weight.t())
+        a_node = _cabi.skinny_matmul(x, pk["v_node"])
+        a_edge = _cabi.skinny_matmul(edge_attr, pk["v_edge"]) if e > 0 else x.new_zeros(1, h)
+        out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+        want_alpha = isinstance(return_attention_weights, bool)
+        alpha = torch.zeros(e, h, dtype=torch.float32, device=x.device) if want_alpha else None
+        _cabi.gat_hop(x_l, a_node, a_edge, csr.as_dict(), h, c, out, bias=self.bias, alpha_out=alpha,
+                      negative_slope=self.negative_slope, max_nodes_per_graph=csr.max_nodes_per_graph)
+        if want_alpha:
+            return out, (edge_index, alpha)
+        return out
+
+    def __repr__(self):
+        return "{}({}, {}, heads={})".format(type(self).__name__, self.in_channels, self.out_channels, self.heads)
+
+
+class gat_seq(nn.Module):
+    """num_ins hops of [cat instruction -> gat -> skip -> BatchNorm1d -> ReLU -> Dropout]
+    (no BN/ReLU after the last hop), reference signature gat_skip.py:224-225, 249."""
+
+    def __init__(self, in_channels, out_channels, edge_attr_dim, ins_dim, num_ins,
+                 dropout=0.0, gat_heads=4, gat_negative_slope=0.2, gat_bias=True):
+        super().__init__()
+        if in_channels != out_channels:
+            raise ValueError("the skip connection (gat_skip.py:270) needs in_channels == out_channels")
+        self.convs = nn.ModuleList([
+            gat(in_channels=in_channels + ins_dim, out_channels=out_channels,
+                edge_in_channels=edge_attr_dim + ins_dim, heads=gat_heads, concat=False,
+                negative_slope=gat_negative_slope, dropout=dropout, bias=gat_bias)
+            for _ in range(num_ins)])
+        self.bns = nn.ModuleList([nn.BatchNorm1d(out_channels) for _ in range(num_ins - 1)])
+        self.dropout = dropout
+        self.in_channels, self.edge_attr_dim, self.ins_dim = in_channels, edge_attr_dim, ins_dim
+        self.kernel_variant = _cabi.VARIANT_AUTO
+        self._packed = None
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+        for bn in self.bns:
+            bn.reset_parameters()
+
+    # ---- weight prepack ---------------------------------------------------------------------
+    def packed(self):
+        key = _param_key(self)
+        if self._packed is not None and self._packed["key"] == key:
+            return self._packed
+        f, fe = self.in_channels, self.edge_attr_dim
+        w_h, w_ins, v_node, v_graph, v_edge, scale, shift = [], [], [], [], [], [], []
+        for i, conv in enumerate(self.convs):
+            pk = conv.packed()
+            w = conv.lin_l.weight.detach()
+            w_h.append(w[:, :f].contiguous())                     # [HC, F]
+            w_ins.append(w[:, f:].t().contiguous())               # [D, HC]
+            v_node.append(torch.cat([pk["v_l"][:, :f], pk["v_r"][:, :f]]).contiguous())        # [2H, F]
+            v_graph.append((pk["v_l"][:, f:].double() + pk["v_r"][:, f:].double()
+                            + pk["v_edge"][:, fe:].double()).float().t().contiguous())          # [D, H]
+            v_edge.append(pk["v_edge"][:, :fe])                   # [H, Fe]
+            if i < len(self.bns):
+                bn = self.bns[i]
+                inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+                g = bn.weight.detach().double() if bn.affine else torch.ones_like(inv)
+                b = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
+                scale.append((g * inv).float().contiguous())
+                shift.append((b - bn.running_mean.detach().double() * g * inv).float().contiguous())
+        self._packed = dict(key=key, w_h=w_h, w_ins=torch.stack(w_ins), v_node=v_node,
+                            v_graph=torch.stack(v_graph), v_edge=torch.cat(v_edge).contiguous(),
+                            scale=scale, shift=shift)
+        return self._packed
+
+    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, csr=None, return_hops=False):
+        """x [N,F], edge_index [2,E] i64, edge_attr [E,Fe], instr_vectors [num_ins,B,D], batch [N] i64
+        -> h [N,F].  ``csr`` (a GraphCSR) may be passed to reuse the per-batch pre-pass."""
+        _require_inference(self, x, edge_attr, instr_vectors)
+        _cabi.require_cuda(x, edge_index, edge_attr, instr_vectors, batch)
+        num_hops = len(self.convs)
+        n, e = x.size(0), edge_index.size(1)
+        b = instr_vectors.size(1)
+        heads, c = self.convs[0].heads, self.convs[0].out_channels
+        if csr is None:
+            csr = GraphCSR.build(edge_index, batch, b)
+        csr_d = csr.as_dict()
+        pk = self.packed()
+        x = x.contiguous().float()
+        edge_attr = edge_attr.contiguous().float()
+        ins = instr_vectors[:num_hops].contiguous().float()
+
+        # hop-invariant pre-pass: all hops' edge logits in one sweep over edge_attr, and the
+        # per-graph instruction terms of x_l and of the logits
+        a_edge_all = (_cabi.skinny_matmul(edge_attr, pk["v_edge"]) if e > 0
+                      else x.new_zeros(1, num_hops * heads))                    # [E, hops*H]
+        with _strict_fp32_matmul():
+            x_graph_all = torch.bmm(ins, pk["w_ins"])                           # [hops, B, H*C]
+            a_graph_all = torch.bmm(ins, pk["v_graph"])                         # [hops, B, H]
+
+        h = x
+        hops = []
+        x_l = torch.empty(n, heads * c, dtype=torch.float32, device=x.device)
+        a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        for i in range(num_hops):
+            with _strict_fp32_matmul():
+                torch.mm(h, pk["w_h"][i].t(), out=x_l)
+            _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
+            last = i == num_hops - 1
+            h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+            _cabi.gat_hop(x_l, a_node, a_edge_all[:, i * heads:], csr_d, heads, c, h_out,
+                          lde=a_edge_all.stride(0), x_graph=x_graph_all[i], a_graph=a_graph_all[i],
+                          h_prev=h, bias=self.convs[i].bias,
+                          ep_scale=None if last else pk["scale"][i], ep_shift=None if last else pk["shift"][i],
+                          negative_slope=self.convs[i].negative_slope,
+                          epilogue=_cabi.EPI_NONE if last else _cabi.EPI_AFFINE_RELU,
+                          max_nodes_per_graph=csr.max_nodes_per_graph, variant=self.kernel_variant)
+            h = h_out
+            if return_hops:
+                hops.append(h)
+        return (h, hops) if return_hops else h

@@ -1,0 +1,113 @@
+"""Batched disjoint scene graphs: the input object of the engine.
+
+``SceneGraphBatch`` is a duck-typed stand-in for ``torch_geometric.data.Batch`` with exactly the
+attributes the reference reads (produced by
+``gqa_dataset_entry.GQATorchDataset_collate_fn``, gqa_dataset_entry.py:631-675 of the reference):
+``x[N,12]`` i64 token ids, ``edge_index[2,E]`` i64 ([0]=source, [1]=target), ``edge_attr[E,1]`` i64,
+``added_sym_edge[K]`` i64, ``batch[N]`` i64 (non-decreasing), ``y[N,5]`` f32, ``num_graphs``, and
+``.to(device=, non_blocking=)`` as called by mainExplain_gat.py:424-428.
+
+``GraphCSR`` is the engine-side int32 destination-CSR view (built once per batch on the GPU by
+``gvqa_build_csr``) that every hop kernel consumes.
+"""
+import torch
+
+from . import _cabi
+
+
+class GraphCSR:
+    """int32 destination-CSR of a batch (device tensors) + loader hints."""
+
+    def __init__(self, parts, num_nodes, num_edges, num_graphs, max_nodes_per_graph=0):
+        self.rowptr, self.col_src, self.perm = parts["rowptr"], parts["col_src"], parts["perm"]
+        self.graph_ptr, self.node_graph, self.stats = parts["graph_ptr"], parts["node_graph"], parts["stats"]
+        self.num_nodes, self.num_edges, self.num_graphs = num_nodes, num_edges, num_graphs
+        self.max_nodes_per_graph = max_nodes_per_graph
+
+    def as_dict(self):
+        return dict(rowptr=self.rowptr, col_src=self.col_src, perm=self.perm, graph_ptr=self.graph_ptr,
+                    node_graph=self.node_graph, num_edges=self.num_edges, num_graphs=self.num_graphs)
+
+    def read_stats(self):
+        """Host copy (synchronises!) of {max_nodes, max_in_edges, max_in_degree, bad_edges}."""
+        s = self.stats.cpu().tolist()
+        return dict(max_nodes=s[0], max_in_edges=s[1], max_in_degree=s[2], bad_edges=s[3])
+
+    @staticmethod
+    def build(edge_index, batch, num_graphs, max_nodes_per_graph=0):
+        parts = _cabi.build_csr(edge_index, batch, num_graphs)
+        return GraphCSR(parts, batch.numel(), edge_index.size(1), num_graphs, max_nodes_per_graph)
+
+
+class SceneGraphBatch:
+    """Attribute bag with the reference Batch surface.  Extra: ``max_nodes_per_graph`` hint and a
+    lazily built, cached ``csr`` (dropped by ``.to`` to another device)."""
+
+    _TENSOR_FIELDS = ("x", "edge_index", "edge_attr", "added_sym_edge", "batch", "y")
+
+    def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, added_sym_edge=None, y=None,
+                 num_graphs=None, max_nodes_per_graph=0):
+        self.x, self.edge_index, self.edge_attr, self.batch = x, edge_index, edge_attr, batch
+        self.added_sym_edge, self.y = added_sym_edge, y
+        self.num_graphs = num_graphs
+        self.max_nodes_per_graph = max_nodes_per_graph
+        self._csr = None
+
+    @property
+    def num_nodes(self):
+        return self.batch.numel()
+
+    @property
+    def num_edges(self):
+        return self.edge_index.size(1)
+
+    def to(self, device=None, non_blocking=False):
+        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph)
+        for name in self._TENSOR_FIELDS:
+            t = getattr(self, name)
+            setattr(out, name, None if t is None else t.to(device=device, non_blocking=non_blocking))
+        return out
+
+    def pin_memory(self):
+        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph)
+        for name in self._TENSOR_FIELDS:
+            t = getattr(self, name)
+            setattr(out, name, None if t is None else t.pin_memory())
+        return out
+
+    def csr(self):
+        if self._csr is None:
+            if self.num_graphs is None:
+                raise ValueError("SceneGraphBatch.num_graphs must be set (avoids a device sync on batch.max())")
+            self._csr = GraphCSR.build(self.edge_index, self.batch, self.num_graphs, self.max_nodes_per_graph)
+        return self._csr
+
+
+def get_csr(graph_or_none, edge_index, batch, num_graphs):
+    """CSR for (edge_index, batch): reuse the batch object's cache when the tensors are its own."""
+    if isinstance(graph_or_none, SceneGraphBatch) and graph_or_none.edge_index is edge_index:
+        return graph_or_none.csr()
+    return GraphCSR.build(edge_index, batch, num_graphs)
+
+
+def synthetic_topology(num_graphs, nodes_per_graph, edges_per_graph, seed=1234, jitter=0):
+    """GQA-shaped synthetic topology: per graph, one self-loop per
+    node listed first (the dataset emits an explicit <self> edge per node,
+    gqa_dataset_entry.py:292-297) followed by ``edges_per_graph - nodes`` random intra-graph
+    directed edges (duplicates allowed).  ``jitter`` > 0 varies the node count per graph by
+    +-jitter.  Returns CPU tensors (edge_index[2,E] i64, batch[N] i64, max_nodes)."""
+    g = torch.Generator().manual_seed(seed)
+    srcs, dsts, batch, off, max_nodes = [], [], [], 0, 0
+    for b in range(num_graphs):
+        n = nodes_per_graph
+        if jitter:
+            n = max(1, n + int(torch.randint(-jitter, jitter + 1, (1,), generator=g)))
+        extra = max(0, int(round(edges_per_graph * n / nodes_per_graph)) - n)
+        loops = torch.arange(n)
+        s = torch.cat([loops, torch.randint(0, n, (extra,), generator=g)]) + off
+        d = torch.cat([loops, torch.randint(0, n, (extra,), generator=g)]) + off
+        srcs.append(s); dsts.append(d)
+        batch.append(torch.full((n,), b, dtype=torch.long))
+        off += n
+        max_nodes = max(max_nodes, n)
+    return torch.stack([torch.cat(srcs), torch.cat(dsts)]), torch.cat(batch), max_nodes

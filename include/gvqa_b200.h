@@ -1,0 +1,152 @@
+/*
+ * gvqa_b200.h -- C ABI of the B200-native GraphVQA scene-graph message-passing engine.
+ *
+ * The reference (codexxxl/GraphVQA) is pure Python and has no FFI of its own; each entry point
+ * below therefore cites the reference *Python interface* whose device work it replaces
+ * (paths relative to the reference root).  The Python host mirror in graphvqa_b200/ binds these
+ * with ctypes (see INTEGRATION.md for the stub a maintainer would add to the reference).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer (cudaMalloc'ed or a torch tensor's data_ptr) unless the
+ *    name ends in _host.  The caller owns every buffer; nothing here allocates, frees,
+ *    synchronises or touches a stream other than the one passed in.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *    enqueued asynchronously and is CUDA-graph capturable.
+ *  - Matrices are row-major fp32.  Graph topology is int32 destination-CSR produced by
+ *    gvqa_build_csr from the reference's int64 COO `edge_index` ([0]=source j, [1]=target i).
+ *  - Return value: GVQA_OK (0) or a negative gvqa_status; gvqa_error_string() describes it.
+ *    Argument errors are detected on the host before anything is enqueued.
+ *  - Thread-safe: no global mutable state (a one-time cudaFuncSetAttribute per kernel aside).
+ */
+#ifndef GVQA_B200_H_
+#define GVQA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVQA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GVQA_API __attribute__((visibility("default")))
+#else
+#define GVQA_API
+#endif
+
+typedef enum gvqa_status {
+  GVQA_OK = 0,
+  GVQA_ERR_NULL_POINTER = -1,   /* a required pointer is NULL */
+  GVQA_ERR_BAD_SHAPE = -2,      /* negative / inconsistent sizes */
+  GVQA_ERR_UNSUPPORTED = -3,    /* channel count not a multiple of 4, > 1024, heads > 8, ... */
+  GVQA_ERR_MISALIGNED = -4,     /* pointer or leading dimension not 16-byte aligned */
+  GVQA_ERR_WORKSPACE = -5,      /* workspace too small */
+  GVQA_ERR_CUDA = -6            /* a CUDA runtime call failed (launch error) */
+} gvqa_status;
+
+/* Epilogue applied by the hop kernels after  out = conv + skip. */
+typedef enum gvqa_epilogue {
+  GVQA_EPI_NONE = 0,         /* last hop of gat_seq (gat_skip.py:273: no BN after the final conv) */
+  GVQA_EPI_AFFINE = 1,       /* y = out*scale[c] + shift[c]            (BatchNorm1d in eval mode)  */
+  GVQA_EPI_AFFINE_RELU = 2   /* y = relu(out*scale[c] + shift[c])      (gat_skip.py:274-275)       */
+} gvqa_epilogue;
+
+GVQA_API int gvqa_abi_version(void);
+GVQA_API const char* gvqa_error_string(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * Destination-CSR build.  Replaces what torch_geometric's MessagePassing.propagate derives
+ * from `edge_index` on every call (gat_skip.py:155) and the
+ * `int(batch.max())` / `batch[-1].item()` host syncs (my_graph_layernorm.py:59,
+ * pipeline_model_gat.py:152).
+ *
+ *   edge_index [2,E] int64 (row 0 = source, row 1 = target), batch [N] int64 non-decreasing.
+ * Outputs (int32):
+ *   rowptr[N+1]      in-edge range of node i is [rowptr[i], rowptr[i+1])
+ *   col_src[E]       source node of CSR slot k
+ *   perm[E]          original edge id of CSR slot k; slots of one node keep the original
+ *                    edge order (stable), so sums run in the order of a sequential index_add
+ *   graph_ptr[B+1]   node range of graph g is [graph_ptr[g], graph_ptr[g+1])
+ *   node_graph[N]    int32 copy of batch
+ *   stats[8]         {max nodes/graph, max in-edges/graph, max in-degree, #edges whose
+ *                    endpoints lie in different graphs or out of range, 0...}
+ * workspace: gvqa_csr_workspace_bytes(N, E) bytes of scratch.
+ */
+GVQA_API size_t gvqa_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+GVQA_API int gvqa_build_csr(const int64_t* edge_index, int64_t num_edges, const int64_t* batch,
+                   int64_t num_nodes, int64_t num_graphs, int32_t* rowptr, int32_t* col_src,
+                   int32_t* perm, int32_t* graph_ptr, int32_t* node_graph, int32_t* stats,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Skinny projection  out[M,K] = x[M,F] @ v[K,F]^T,  K <= 32, F % 4 == 0  (v laid out like an
+ * nn.Linear weight, [out, in]).  Computes the attention-logit terms of gat.forward
+ * (gat_skip.py:134-135 a_l/a_r, :150-151 a_e) after the algebraic collapse
+ * <W x, att_h>  =  x . (W_h^T att_h)  (SURVEY.md section 8a).  x rows have stride ldx floats.
+ */
+GVQA_API int gvqa_skinny_matmul_f32(const float* x, int64_t ldx, const float* v, float* out, int64_t m,
+                           int f, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused GAT hop.  One launch replaces, for one hop of gat_seq.forward (gat_skip.py:254-276):
+ * index_select x3, add, leaky_relu, torch_geometric.utils.softmax (scatter_max, exp,
+ * scatter_add, div), mul, scatter-add aggregate, head mean, +bias, +skip, BatchNorm1d(eval),
+ * ReLU  (gat_skip.py:155-168, 183-208, 270-275).
+ *
+ *   xl_full[n,h,:] = x_l[n*ldx + h*C + :] + (x_graph ? x_graph[g(n), h*C + :] : 0)
+ *   logit[k,h]     = a_node[src_k, h] + a_node[i, H+h] + (a_graph ? a_graph[g(i), h] : 0)
+ *                    + a_edge[e_k*lde + h],   e_k = perm ? perm[k] : k        (k in CSR order)
+ *   alpha          = softmax over the in-edges of i of leaky_relu(logit, negative_slope),
+ *                    with PyG's  exp(l - max) / (sum + 1e-16)
+ *   out[i,:]       = (1/H) sum_h sum_k alpha[k,h] * xl_full[src_k, h, :] + bias + h_prev[i,:]
+ *   h_out[i,:]     = epilogue(out[i,:])
+ * alpha_out (optional) receives alpha[E,H] in ORIGINAL edge order (return_attention_weights,
+ * gat_skip.py:170-175).  Nodes without in-edges get out = bias + h_prev (empty softmax).
+ */
+typedef struct gvqa_gat_hop_args {
+  const float* x_l;        /* [N, ldx] projected node features, head-major columns h*C+c     */
+  int64_t ldx;             /* row stride of x_l in floats (>= H*C, multiple of 4)            */
+  const float* x_graph;    /* [B, H*C] per-graph additive term of x_l, or NULL               */
+  const float* a_node;     /* [N, 2H]: columns 0..H-1 = source term a_l, H..2H-1 = target a_r */
+  const float* a_graph;    /* [B, H] per-graph additive logit term, or NULL                  */
+  const float* a_edge;     /* [E, lde] per-edge logit term                                    */
+  int64_t lde;             /* row stride of a_edge in floats (>= H)                           */
+  const int32_t* rowptr;   /* [N+1] */
+  const int32_t* col_src;  /* [E]   */
+  const int32_t* perm;     /* [E] or NULL when a_edge is already in CSR order                 */
+  const int32_t* graph_ptr;  /* [B+1] */
+  const int32_t* node_graph; /* [N]   */
+  const float* h_prev;     /* [N, C] skip input, or NULL                                      */
+  const float* bias;       /* [C] or NULL                                                     */
+  const float* ep_scale;   /* [C] (epilogue != NONE)                                          */
+  const float* ep_shift;   /* [C] (epilogue != NONE)                                          */
+  float* h_out;            /* [N, C]                                                          */
+  float* alpha_out;        /* [E, H] original edge order, or NULL                             */
+  int64_t num_nodes, num_edges, num_graphs;
+  int32_t heads, channels; /* H <= 8; C multiple of 4, <= 1024                                */
+  float negative_slope;
+  int32_t epilogue;        /* gvqa_epilogue                                                   */
+  int32_t max_nodes_per_graph; /* hint from the loader (0 = unknown): selects the staged kernel */
+  int32_t variant;         /* 0 = auto, 1 = force gather-from-L2 kernel, 2 = force smem-staged */
+} gvqa_gat_hop_args;
+
+GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-graph LayerNorm (graph_utils/my_graph_layernorm.py:52-78): statistics over all
+ * nodes x channels of each graph, two-pass variance, eps added to the std, scalar affine.
+ * weight/bias point to ONE float each on the device (the reference's parameters have shape
+ * [1], my_graph_layernorm.py:40-41) or are NULL.  In-place (out == x) is allowed.
+ * max_nodes_per_graph is a loader hint (0 = unknown) that sizes the shared-memory staging.
+ */
+GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, const float* weight,
+                             const float* bias, float* out, int64_t num_nodes,
+                             int64_t num_graphs, int32_t channels, float eps,
+                             int32_t max_nodes_per_graph, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVQA_B200_H_ */

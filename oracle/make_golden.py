@@ -1,0 +1,148 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (over oracle/pyg_shim).
+
+TEST INFRASTRUCTURE, build-container only:   python -m oracle.make_golden
+
+Each fixture holds the inputs, the module ``state_dict`` and the outputs the reference's own code
+produced on CPU (fp32).  Topologies come from the reference's ``debug_sceneGraphs.json`` (4 graphs:
+21/12/20/6 nodes), converted with the edge rules of gqa_dataset_entry.py:255-332 (self-loop first,
+then each relation, each followed by a synthesized reverse edge when the reverse is absent).
+Feature values are seeded random numbers (the GloVe vocabulary needs network access).
+"""
+import hashlib
+import json
+import os
+
+import torch
+
+from . import run_reference as rr
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def debug_topology():
+    """(edge_index[2,E], batch[N], added_sym_edge list per graph) for the 4 debug scene graphs."""
+    with open(os.path.join(rr.REFERENCE_ROOT, "debug_sceneGraphs.json")) as f:
+        sgs = json.load(f)
+    src, dst, batch, off = [], [], [], 0
+    for gi, key in enumerate(sgs):
+        objs = sgs[key]["objects"]
+        ids = sorted(objs.keys())
+        idx = {o: i for i, o in enumerate(ids)}
+        present = {(idx[o], idx[r["object"]]) for o in ids for r in objs[o]["relations"]}
+        for o in ids:
+            i = idx[o]
+            src.append(off + i); dst.append(off + i)
+            for r in objs[o]["relations"]:
+                j = idx[r["object"]]
+                src.append(off + i); dst.append(off + j)
+                if (j, i) not in present:
+                    src.append(off + j); dst.append(off + i)
+        batch += [gi] * len(ids)
+        off += len(ids)
+    return torch.tensor([src, dst], dtype=torch.long), torch.tensor(batch, dtype=torch.long)
+
+
+def _randomise_bn(module, gen):
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.1, generator=gen)
+            m.running_var.uniform_(0.5, 1.5, generator=gen)
+            with torch.no_grad():
+                m.weight.uniform_(0.5, 1.5, generator=gen)
+                m.bias.normal_(0, 0.1, generator=gen)
+
+
+def _state_hash(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode()); h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ei, batch = debug_topology()
+    n, e, b = batch.numel(), ei.size(1), int(batch.max()) + 1
+    gat_skip = rr.load("gat_skip")
+    lnmod = rr.load("graph_utils.my_graph_layernorm")
+    lcgn = rr.load("lcgn")
+    gine = rr.load("pipeline_model_gine")
+    gcn = rr.load("pipeline_model_gcn")
+    meta = dict(generator="oracle/make_golden.py", reference=rr.REFERENCE_ROOT, torch=torch.__version__)
+
+    with torch.no_grad():
+        # 1. gat_seq, small dims, weights stored
+        gen = torch.Generator().manual_seed(101)
+        torch.manual_seed(101)
+        f, d, hops = 32, 16, 3
+        m = gat_skip.gat_seq(f, f, f, d, hops, dropout=0.1, gat_heads=4).eval()
+        _randomise_bn(m, gen)
+        for c in m.convs:
+            c.bias.normal_(0, 0.1, generator=gen)
+        x = torch.randn(n, f, generator=gen); ea = torch.randn(e, f, generator=gen)
+        ins = torch.randn(hops, b, d, generator=gen)
+        out = m(x, ei, ea, ins, batch)
+        conv0 = m.convs[0]
+        x_cat = torch.cat((x, ins[0][batch]), -1); e_cat = torch.cat((ea, ins[0][batch[ei[0]]]), -1)
+        c_out, (_, alpha) = conv0(x_cat, ei, e_cat, return_attention_weights=True)
+        torch.save(dict(meta=meta, config=dict(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d,
+                                               num_ins=hops, dropout=0.1, gat_heads=4),
+                        state=m.state_dict(), x=x, edge_index=ei, edge_attr=ea, instr_vectors=ins, batch=batch,
+                        out=out, conv0_out=c_out, conv0_alpha=alpha), os.path.join(OUT, "gat_seq_small.pt"))
+
+        # 2. gat_seq at the reference dims (F=300, D=512, H=4, 5 hops); weights by seed + hash
+        gen = torch.Generator().manual_seed(202)
+        torch.manual_seed(202)
+        m = gat_skip.gat_seq(300, 300, 300, 512, 5, dropout=0.1, gat_heads=4).eval()
+        sd_hash = _state_hash(m.state_dict())
+        x = torch.randn(n, 300, generator=gen); ea = torch.randn(e, 300, generator=gen)
+        ins = torch.randn(5, b, 512, generator=gen)
+        out = m(x, ei, ea, ins, batch)
+        torch.save(dict(meta=meta, seed=202, state_sha256=sd_hash, x=x, edge_index=ei, edge_attr=ea,
+                        instr_vectors=ins, batch=batch, out=out), os.path.join(OUT, "gat_seq_refdims.pt"))
+
+        # 3. graph LayerNorm
+        gen = torch.Generator().manual_seed(303)
+        ln = lnmod.LayerNorm(300)
+        ln.weight.fill_(1.3); ln.bias.fill_(-0.2)
+        x = torch.randn(n, 300, generator=gen) * 2 + 0.5
+        torch.save(dict(meta=meta, state=ln.state_dict(), x=x, batch=batch, out=ln(x, batch)),
+                   os.path.join(OUT, "graph_layernorm.pt"))
+
+        # 4. lcgn_seq small (x_ctx = the torch.randn the reference draws at lcgn.py:306)
+        gen = torch.Generator().manual_seed(404)
+        torch.manual_seed(404)
+        m = lcgn.lcgn_seq(in_channels=24, out_channels=32, edge_attr_dim=24, num_ins=5, gat_cmd_dim=32,
+                          question_dim=32, dropout=0.1).eval()
+        m.lcgn.bias.normal_(0, 0.1, generator=gen)
+        x = torch.randn(n, 24, generator=gen); q = torch.randn(b, 32, generator=gen)
+        lo = torch.randn(7, b, 32, generator=gen)
+        torch.manual_seed(405); x_ctx = torch.randn(n, 32)
+        torch.manual_seed(405); out = m(x, ei, batch, q, lo)
+        torch.save(dict(meta=meta, config=dict(in_channels=24, out_channels=32, edge_attr_dim=24, num_ins=5,
+                                               gat_cmd_dim=32, question_dim=32, dropout=0.1),
+                        state=m.state_dict(), x=x, edge_index=ei, batch=batch, q_encoding=q, lstm_outputs=lo,
+                        x_ctx=x_ctx, out=out), os.path.join(OUT, "lcgn_seq_small.pt"))
+
+        # 5/6. gine_seq / gcn_seq small: bug-faithful output + the (discarded) conv results
+        for name, mod, cls in (("gine", gine, "gine_seq"), ("gcn", gcn, "gcn_seq")):
+            gen = torch.Generator().manual_seed(505)
+            torch.manual_seed(505)
+            m = getattr(mod, cls)(32, 32, 16, dropout=0.1).eval()
+            _randomise_bn(m, gen)
+            x = torch.randn(n, 32, generator=gen); ea = torch.randn(e, 32, generator=gen)
+            ins = torch.randn(5, b, 16, generator=gen)
+            conv_out = []
+            hooks = [c.register_forward_hook(lambda _m, _i, o: conv_out.append(o.clone())) for c in m.convs]
+            out = m(x, ei, ea, ins, batch) if name == "gine" else m(x, ei, ins, batch)
+            for hk in hooks:
+                hk.remove()
+            torch.save(dict(meta=meta, config=dict(in_channels=32, out_channels=32, ins_dim=16, dropout=0.1),
+                            state=m.state_dict(), x=x, edge_index=ei, edge_attr=ea, instr_vectors=ins,
+                            batch=batch, out=out, conv_out=conv_out), os.path.join(OUT, "%s_seq_small.pt" % name))
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    main()
