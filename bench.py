@@ -43,7 +43,8 @@ def make_inputs(cfg, seed):
     x = torch.randn(batch.numel(), cfg["feat"], generator=g)
     ea = torch.randn(ei.size(1), cfg["feat"], generator=g)
     ins = torch.randn(cfg["hops"], cfg["graphs"], cfg["ins"], generator=g)
-    return dict(x=x, edge_index=ei, edge_attr=ea, instr_vectors=ins, batch=batch, max_nodes=max_nodes)
+    return dict(x=x, edge_index=ei, edge_attr=ea, instr_vectors=ins, batch=batch, max_nodes=max_nodes,
+                max_edges=synthetic_topology.last_max_edges)
 
 
 def randomise_bn(model, seed):
@@ -177,6 +178,7 @@ def run_engine(args, rank, local_rank, world):
     model = eng.gat_seq(**model_kwargs(cfg)).eval()
     randomise_bn(model, 7)
     model = model.to(dev)
+    model.kernel_variant = args.variant
 
     # R input sets (> L2 in total: 4 x ~50 MB) rotated step to step so no step finds its inputs in L2
     R = 4
@@ -184,11 +186,13 @@ def run_engine(args, rank, local_rank, world):
     keys = ("x", "edge_index", "edge_attr", "instr_vectors", "batch")
     pinned = [{k: s[k].pin_memory() for k in keys} for s in host_sets]
     dev_sets = [{k: s[k].to(dev) for k in keys} for s in host_sets]
-    max_nodes = host_sets[0]["max_nodes"]
+    max_nodes = max(s["max_nodes"] for s in host_sets)
+    max_edges = max(s["max_edges"] for s in host_sets)
     in_bytes = sum(host_sets[0][k].numel() * host_sets[0][k].element_size() for k in keys)
 
     def step(s):
-        csr = GraphCSR.build(s["edge_index"], s["batch"], b, max_nodes_per_graph=max_nodes)
+        csr = GraphCSR.build(s["edge_index"], s["batch"], b, max_nodes_per_graph=max_nodes,
+                             max_in_edges_per_graph=max_edges)
         return model(s["x"], s["edge_index"], s["edge_attr"], s["instr_vectors"], s["batch"], csr=csr)
 
     def barrier():
@@ -312,6 +316,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -30,7 +30,7 @@ class GatHopArgs(ctypes.Structure):
         ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("alpha_out", _c_vp),
         ("num_nodes", _c_i64), ("num_edges", _c_i64), ("num_graphs", _c_i64),
         ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
-        ("max_nodes_per_graph", _c_i32), ("variant", _c_i32),
+        ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
     ]
 
 
@@ -149,7 +149,7 @@ def skinny_matmul(x, v, out=None):
 def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, x_graph=None,
             a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
-            variant=VARIANT_AUTO):
+            max_in_edges_per_graph=0, variant=VARIANT_AUTO):
     require_cuda(x_l, a_node, a_edge, h_out, x_graph, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
     require_f32c(a_node=a_node, h_out=h_out, x_graph=x_graph, a_graph=a_graph, h_prev=h_prev, bias=bias,
                  ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
@@ -166,7 +166,8 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.num_nodes, a.num_edges = n, e
     a.num_graphs = csr["num_graphs"] if num_graphs is None else num_graphs
     a.heads, a.channels, a.negative_slope, a.epilogue = heads, channels, negative_slope, epilogue
-    a.max_nodes_per_graph, a.variant = max_nodes_per_graph, variant
+    a.max_nodes_per_graph, a.max_in_edges_per_graph = max_nodes_per_graph, max_in_edges_per_graph
+    a.variant = variant
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
     return h_out

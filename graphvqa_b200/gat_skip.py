@@ -137,7 +137,7 @@ class gat(nn.Module):
         want_alpha = isinstance(return_attention_weights, bool)
         alpha = torch.zeros(e, h, dtype=torch.float32, device=x.device) if want_alpha else None
         _cabi.gat_hop(x_l, a_node, a_edge, csr.as_dict(), h, c, out, bias=self.bias, alpha_out=alpha,
-                      negative_slope=self.negative_slope, max_nodes_per_graph=csr.max_nodes_per_graph)
+                      negative_slope=self.negative_slope, **csr.hints())
         if want_alpha:
             return out, (edge_index, alpha)
         return out
@@ -164,6 +164,7 @@ class gat_seq(nn.Module):
         self.dropout = dropout
         self.in_channels, self.edge_attr_dim, self.ins_dim = in_channels, edge_attr_dim, ins_dim
         self.kernel_variant = _cabi.VARIANT_AUTO
+        self.hop_events = None      # set to a list to collect (start, end) CUDA events per fused-hop launch
         self._packed = None
 
     def reset_parameters(self):
@@ -235,13 +236,19 @@ class gat_seq(nn.Module):
             _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
             last = i == num_hops - 1
             h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+            if self.hop_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             _cabi.gat_hop(x_l, a_node, a_edge_all[:, i * heads:], csr_d, heads, c, h_out,
                           lde=a_edge_all.stride(0), x_graph=x_graph_all[i], a_graph=a_graph_all[i],
                           h_prev=h, bias=self.convs[i].bias,
                           ep_scale=None if last else pk["scale"][i], ep_shift=None if last else pk["shift"][i],
                           negative_slope=self.convs[i].negative_slope,
                           epilogue=_cabi.EPI_NONE if last else _cabi.EPI_AFFINE_RELU,
-                          max_nodes_per_graph=csr.max_nodes_per_graph, variant=self.kernel_variant)
+                          variant=self.kernel_variant, **csr.hints())
+            if self.hop_events is not None:
+                ev[1].record()
+                self.hop_events.append(ev)
             h = h_out
             if return_hops:
                 hops.append(h)

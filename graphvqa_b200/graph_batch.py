@@ -18,11 +18,18 @@ from . import _cabi
 class GraphCSR:
     """int32 destination-CSR of a batch (device tensors) + loader hints."""
 
-    def __init__(self, parts, num_nodes, num_edges, num_graphs, max_nodes_per_graph=0):
+    def __init__(self, parts, num_nodes, num_edges, num_graphs, max_nodes_per_graph=0,
+                 max_in_edges_per_graph=0):
         self.rowptr, self.col_src, self.perm = parts["rowptr"], parts["col_src"], parts["perm"]
         self.graph_ptr, self.node_graph, self.stats = parts["graph_ptr"], parts["node_graph"], parts["stats"]
         self.num_nodes, self.num_edges, self.num_graphs = num_nodes, num_edges, num_graphs
+        # loader hints (0 = unknown): they size the shared-memory staged kernels, never correctness
         self.max_nodes_per_graph = max_nodes_per_graph
+        self.max_in_edges_per_graph = max_in_edges_per_graph
+
+    def hints(self):
+        return dict(max_nodes_per_graph=self.max_nodes_per_graph,
+                    max_in_edges_per_graph=self.max_in_edges_per_graph)
 
     def as_dict(self):
         return dict(rowptr=self.rowptr, col_src=self.col_src, perm=self.perm, graph_ptr=self.graph_ptr,
@@ -34,9 +41,16 @@ class GraphCSR:
         return dict(max_nodes=s[0], max_in_edges=s[1], max_in_degree=s[2], bad_edges=s[3])
 
     @staticmethod
-    def build(edge_index, batch, num_graphs, max_nodes_per_graph=0):
+    def build(edge_index, batch, num_graphs, max_nodes_per_graph=0, max_in_edges_per_graph=0,
+              read_hints=False):
+        """read_hints=True fills missing hints from the device stats (one host sync)."""
         parts = _cabi.build_csr(edge_index, batch, num_graphs)
-        return GraphCSR(parts, batch.numel(), edge_index.size(1), num_graphs, max_nodes_per_graph)
+        csr = GraphCSR(parts, batch.numel(), edge_index.size(1), num_graphs, max_nodes_per_graph,
+                       max_in_edges_per_graph)
+        if read_hints and (not max_nodes_per_graph or not max_in_edges_per_graph):
+            st = csr.read_stats()
+            csr.max_nodes_per_graph, csr.max_in_edges_per_graph = st["max_nodes"], st["max_in_edges"]
+        return csr
 
 
 class SceneGraphBatch:
@@ -46,11 +60,12 @@ class SceneGraphBatch:
     _TENSOR_FIELDS = ("x", "edge_index", "edge_attr", "added_sym_edge", "batch", "y")
 
     def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, added_sym_edge=None, y=None,
-                 num_graphs=None, max_nodes_per_graph=0):
+                 num_graphs=None, max_nodes_per_graph=0, max_in_edges_per_graph=0):
         self.x, self.edge_index, self.edge_attr, self.batch = x, edge_index, edge_attr, batch
         self.added_sym_edge, self.y = added_sym_edge, y
         self.num_graphs = num_graphs
         self.max_nodes_per_graph = max_nodes_per_graph
+        self.max_in_edges_per_graph = max_in_edges_per_graph
         self._csr = None
 
     @property
@@ -62,14 +77,16 @@ class SceneGraphBatch:
         return self.edge_index.size(1)
 
     def to(self, device=None, non_blocking=False):
-        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph)
+        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph,
+                              max_in_edges_per_graph=self.max_in_edges_per_graph)
         for name in self._TENSOR_FIELDS:
             t = getattr(self, name)
             setattr(out, name, None if t is None else t.to(device=device, non_blocking=non_blocking))
         return out
 
     def pin_memory(self):
-        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph)
+        out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph,
+                              max_in_edges_per_graph=self.max_in_edges_per_graph)
         for name in self._TENSOR_FIELDS:
             t = getattr(self, name)
             setattr(out, name, None if t is None else t.pin_memory())
@@ -79,7 +96,8 @@ class SceneGraphBatch:
         if self._csr is None:
             if self.num_graphs is None:
                 raise ValueError("SceneGraphBatch.num_graphs must be set (avoids a device sync on batch.max())")
-            self._csr = GraphCSR.build(self.edge_index, self.batch, self.num_graphs, self.max_nodes_per_graph)
+            self._csr = GraphCSR.build(self.edge_index, self.batch, self.num_graphs, self.max_nodes_per_graph,
+                                       self.max_in_edges_per_graph)
         return self._csr
 
 
@@ -95,9 +113,10 @@ def synthetic_topology(num_graphs, nodes_per_graph, edges_per_graph, seed=1234, 
     node listed first (the dataset emits an explicit <self> edge per node,
     gqa_dataset_entry.py:292-297) followed by ``edges_per_graph - nodes`` random intra-graph
     directed edges (duplicates allowed).  ``jitter`` > 0 varies the node count per graph by
-    +-jitter.  Returns CPU tensors (edge_index[2,E] i64, batch[N] i64, max_nodes)."""
+    +-jitter.  Returns CPU tensors (edge_index[2,E] i64, batch[N] i64, max_nodes); the largest
+    per-graph edge count is ``synthetic_topology.last_max_edges``."""
     g = torch.Generator().manual_seed(seed)
-    srcs, dsts, batch, off, max_nodes = [], [], [], 0, 0
+    srcs, dsts, batch, off, max_nodes, max_edges = [], [], [], 0, 0, 0
     for b in range(num_graphs):
         n = nodes_per_graph
         if jitter:
@@ -110,4 +129,6 @@ def synthetic_topology(num_graphs, nodes_per_graph, edges_per_graph, seed=1234, 
         batch.append(torch.full((n,), b, dtype=torch.long))
         off += n
         max_nodes = max(max_nodes, n)
+        max_edges = max(max_edges, n + extra)
+    synthetic_topology.last_max_edges = max_edges
     return torch.stack([torch.cat(srcs), torch.cat(dsts)]), torch.cat(batch), max_nodes

@@ -128,7 +128,8 @@ typedef struct gvqa_gat_hop_args {
   int32_t heads, channels; /* H <= 8; C multiple of 4, <= 1024                                */
   float negative_slope;
   int32_t epilogue;        /* gvqa_epilogue                                                   */
-  int32_t max_nodes_per_graph; /* hint from the loader (0 = unknown): selects the staged kernel */
+  int32_t max_nodes_per_graph;    /* loader hints (0 = unknown) that size the shared-memory staged  */
+  int32_t max_in_edges_per_graph; /* kernel; never a correctness input (oversize graphs fall back)   */
   int32_t variant;         /* 0 = auto, 1 = force gather-from-L2 kernel, 2 = force smem-staged */
 } gvqa_gat_hop_args;
 

@@ -84,15 +84,21 @@ def _inputs(ei, batch, b, f, fe, d, hops, seed):
             torch.randn(hops, b, d, generator=g), batch)
 
 
-def _run_both(o, e, args, variant=0):
+def _run_both(o, e, args, variant=0, hints=None):
+    """variant 1 = gather-from-L2 kernel, 2 = shared-memory staged kernel (needs loader hints;
+    ``hints`` overrides the true maxima to force the in-kernel oversize fallback)."""
     e.kernel_variant = variant
     with torch.no_grad():
         want, want_hops = o(*args, return_hops=True)
-        got, got_hops = e(*[a.to(DEV) for a in args], return_hops=True)
+        dargs = [a.to(DEV) for a in args]
+        csr = GraphCSR.build(dargs[1], dargs[4], args[3].size(1), read_hints=True)
+        if hints is not None:
+            csr.max_nodes_per_graph, csr.max_in_edges_per_graph = hints
+        got, got_hops = e(*dargs, csr=csr, return_hops=True)
     return want, want_hops, got.cpu(), [h.cpu() for h in got_hops]
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("f,d,heads,hops", [(300, 512, 4, 5), (512, 512, 4, 5), (64, 32, 1, 2), (128, 64, 8, 3),
                                             (36, 20, 2, 2)])
 def test_gat_seq_matches_oracle_random_graphs(f, d, heads, hops, variant):
@@ -108,7 +114,18 @@ def test_gat_seq_matches_oracle_random_graphs(f, d, heads, hops, variant):
     assert (want - got).abs().max() <= TOL
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("hints", [(2, 3), (8, 1000), (1000, 16)])
+def test_gat_seq_staged_oversize_units_fall_back(hints):
+    """Loader hints smaller than the real graphs must only cost speed, never correctness."""
+    cfg = dict(in_channels=128, out_channels=128, edge_attr_dim=128, ins_dim=32, num_ins=2, gat_heads=4)
+    o, e = _pair(cfg, seed=13)
+    ei, batch = random_graphs(9, 1, 20, 2.5, seed=8, isolated=True)
+    args = _inputs(ei, batch, 9, 128, 128, 32, 2, seed=14)
+    want, _, got, _ = _run_both(o, e, args, variant=2, hints=hints)
+    assert (want - got).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("variant", [1, 2])
 def test_gat_seq_high_degree_hub(variant):
     # one hub node with in-degree > 32 exercises the chunked softmax path
     n = 90
@@ -122,7 +139,7 @@ def test_gat_seq_high_degree_hub(variant):
     assert (want - got).abs().max() <= TOL
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("variant", [1, 2])
 def test_gat_seq_golden_small(golden, variant):
     fx = golden("gat_seq_small")
     e = eng.gat_seq(**fx["config"]).eval()
@@ -130,7 +147,9 @@ def test_gat_seq_golden_small(golden, variant):
     e = e.to(DEV)
     e.kernel_variant = variant
     with torch.no_grad():
-        out = e(*[fx[k].to(DEV) for k in ("x", "edge_index", "edge_attr", "instr_vectors", "batch")]).cpu()
+        dargs = [fx[k].to(DEV) for k in ("x", "edge_index", "edge_attr", "instr_vectors", "batch")]
+        csr = GraphCSR.build(dargs[1], dargs[4], fx["instr_vectors"].size(1), read_hints=True)
+        out = e(*dargs, csr=csr).cpu()
         x_cat = torch.cat((fx["x"], fx["instr_vectors"][0][fx["batch"]]), -1).to(DEV)
         e_cat = torch.cat((fx["edge_attr"], fx["instr_vectors"][0][fx["batch"][fx["edge_index"][0]]]), -1).to(DEV)
         c_out, (_, alpha) = e.convs[0](x_cat, fx["edge_index"].to(DEV), e_cat, return_attention_weights=True)
@@ -152,23 +171,28 @@ def test_gat_seq_golden_refdims(golden):
     assert (out - fx["out"]).abs().max() <= TOL
 
 
-def test_gat_seq_cfg2_shape_and_determinism():
+@pytest.mark.parametrize("variant", [1, 2])
+def test_gat_seq_cfg2_shape_and_determinism(variant):
     """BASELINE cfg2 (B=256, 30 nodes / 60 edges, F=512, 5 hops): parity vs oracle on a 16-graph
     slice, bitwise run-to-run determinism and shard invariance on the full batch."""
     cfg = dict(in_channels=512, out_channels=512, edge_attr_dim=512, ins_dim=512, num_ins=5, gat_heads=4)
     o, e = _pair(cfg, seed=21)
     ei, batch, max_nodes = synthetic_topology(256, 30, 60, seed=1234)
     args = _inputs(ei, batch, 256, 512, 512, 512, 5, seed=22)
+    e.kernel_variant = variant
     with torch.no_grad():
         dev_args = [a.to(DEV) for a in args]
-        full1 = e(*dev_args)
-        full2 = e(*dev_args)
+        csr = GraphCSR.build(dev_args[1], dev_args[4], 256, read_hints=True)
+        assert csr.max_nodes_per_graph == max_nodes == 30
+        full1 = e(*dev_args, csr=csr)
+        full2 = e(*dev_args, csr=csr)
         assert torch.equal(full1, full2)
         # first 16 graphs alone == the corresponding rows of the full batch (graphs are independent)
         nn, ne = 16 * 30, 16 * 60
         keep_e = (ei[1] < nn)
         sub = (args[0][:nn], ei[:, keep_e], args[2][keep_e], args[3][:, :16], batch[:nn])
-        part = e(*[a.to(DEV) for a in sub])
+        dsub = [a.to(DEV) for a in sub]
+        part = e(*dsub, csr=GraphCSR.build(dsub[1], dsub[4], 16, read_hints=True))
         assert torch.equal(part, full1[:nn])
         want = o(*sub)
     assert (want - part.cpu()).abs().max() <= TOL
