@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
 ABI_VERSION = 1
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
-VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED = 0, 1, 2
+VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK = 0, 1, 2, 3
 
 _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
                                         ctypes.c_void_p, ctypes.c_size_t)
@@ -24,7 +24,7 @@ _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c
 class GatHopArgs(ctypes.Structure):
     """Mirror of ``struct gvqa_gat_hop_args`` (field order and types must match the header)."""
     _fields_ = [
-        ("x_l", _c_vp), ("ldx", _c_i64), ("x_graph", _c_vp), ("a_node", _c_vp), ("a_graph", _c_vp),
+        ("x_l", _c_vp), ("ldx", _c_i64), ("graph_bias", _c_vp), ("a_node", _c_vp), ("a_graph", _c_vp),
         ("a_edge", _c_vp), ("lde", _c_i64), ("rowptr", _c_vp), ("col_src", _c_vp), ("perm", _c_vp),
         ("graph_ptr", _c_vp), ("node_graph", _c_vp), ("h_prev", _c_vp), ("bias", _c_vp),
         ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("alpha_out", _c_vp),
@@ -146,18 +146,18 @@ def skinny_matmul(x, v, out=None):
     return out
 
 
-def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, x_graph=None,
+def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, graph_bias=None,
             a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
             max_in_edges_per_graph=0, variant=VARIANT_AUTO):
-    require_cuda(x_l, a_node, a_edge, h_out, x_graph, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
-    require_f32c(a_node=a_node, h_out=h_out, x_graph=x_graph, a_graph=a_graph, h_prev=h_prev, bias=bias,
+    require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
+    require_f32c(a_node=a_node, h_out=h_out, graph_bias=graph_bias, a_graph=a_graph, h_prev=h_prev, bias=bias,
                  ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
     n = h_out.size(0)
     e = csr["num_edges"]
     a = GatHopArgs()
     a.x_l, a.ldx = ptr(x_l), (x_l.stride(0) if ldx is None else ldx)
-    a.x_graph, a.a_node, a.a_graph = ptr(x_graph), ptr(a_node), ptr(a_graph)
+    a.graph_bias, a.a_node, a.a_graph = ptr(graph_bias), ptr(a_node), ptr(a_graph)
     a.a_edge, a.lde = ptr(a_edge), (a_edge.stride(0) if lde is None else lde)
     a.rowptr, a.col_src, a.perm = ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"])
     a.graph_ptr, a.node_graph = ptr(csr["graph_ptr"]), ptr(csr["node_graph"])

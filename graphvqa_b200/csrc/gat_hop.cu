@@ -6,13 +6,19 @@
 // BatchNorm(eval)+ReLU epilogue.  No atomics: destination-CSR, one warp owns one output row,
 // in-edges are summed in the caller's edge order -> bitwise deterministic.
 //
-// Two kernels:
-//  * gat_hop_gather_kernel  -- source rows are gathered straight from global memory (L2);
-//    works for any graph size.
-//  * gat_hop_staged_kernel  -- one CTA owns a (graph, channel-slice) work unit: the slice of
-//    every node row of the graph (all heads) is staged ONCE into shared memory by the TMA engine
-//    (cp.async.bulk + mbarrier, double buffered across units), so each x_l byte crosses
-//    L2->SM exactly once; the gathers then hit shared memory.
+// Three kernels (gvqa_gat_hop_args.variant; 0 = auto):
+//  1 gat_hop_gather_kernel -- one warp per destination node, everything from global/L2.
+//  3 gat_hop_block_kernel  -- one 128-thread CTA per 16 consecutive destination nodes: the CTA
+//    loads its CSR slice and logit terms edge-parallel (3 dependent round trips for the whole
+//    CTA instead of 5 per node), runs the softmax with one thread per (node, head) in shared
+//    memory, then every warp streams its nodes' source rows with 32 independent 128-bit loads in
+//    flight per lane.  The whole grid is resident in ONE wave (no tail), so the kernel behaves
+//    like a streaming copy.  Default.
+//  2 gat_hop_staged_kernel -- one CTA per (graph, channel-window): softmax once for all heads,
+//    then one stage per head (the window of every node row of the graph) streamed by the TMA
+//    engine (cp.async.bulk + mbarrier) through a 3-deep shared-memory ring, accumulators in
+//    registers across heads; each x_l byte crosses L2->SM exactly once.  Measured slower than 3 on
+//    B200 for GQA-sized graphs (per-copy TMA issue cost, profiles/microbench), kept selectable.
 #include "common.cuh"
 
 namespace gvqa {
@@ -21,7 +27,7 @@ constexpr int kEdgeChunk = 32;  // in-edges whose alpha are staged per warp at a
 
 struct HopParams {
   const float* __restrict__ x_l;
-  const float* __restrict__ x_graph;
+  const float* __restrict__ graph_bias;
   const float* __restrict__ a_node;
   const float* __restrict__ a_graph;
   const float* __restrict__ a_edge;
@@ -44,10 +50,10 @@ struct HopParams {
 
 // Softmax weights of the in-edges [e0,e1) of node `i` for all H heads, computed by one warp.
 // Lane l serves head (l % H); the 32/H lanes of a head stride over the edges.  On return the
-// per-head (max, 1/(sum+1e-16), sum/(sum+1e-16)) live in every lane of that head.
+// per-head (max, 1/(sum+1e-16)) live in every lane of that head.
 template <int H>
 struct WarpSoftmax {
-  float m, inv, total;
+  float m, inv;
   const HopParams& p;
   int i, g, e0, e1, lane, head, slot;
   float target_term;
@@ -67,17 +73,6 @@ struct WarpSoftmax {
     return leaky_relu(v, p.slope);
   }
 
-  __device__ __forceinline__ float reduce_max(float v) const {
-#pragma unroll
-    for (int o = 16; o >= H; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
-    return v;
-  }
-  __device__ __forceinline__ float reduce_sum(float v) const {
-#pragma unroll
-    for (int o = 16; o >= H; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-  }
-
   // first_logit: logit of edge e0+slot if it exists (kept by the caller for reuse)
   __device__ __forceinline__ void run(float& first_logit) {
     constexpr int per = 32 / H;
@@ -88,21 +83,26 @@ struct WarpSoftmax {
       mx = first_logit;
     }
     for (int k = e0 + slot + per; k < e1; k += per) mx = fmaxf(mx, logit(k));
-    m = reduce_max(mx);
+#pragma unroll
+    for (int o = 16; o >= H; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    m = mx;
     float s = 0.f;
     if (e0 + slot < e1) s = expf(first_logit - m);
     for (int k = e0 + slot + per; k < e1; k += per) s += expf(logit(k) - m);
-    s = reduce_sum(s);
+#pragma unroll
+    for (int o = 16; o >= H; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
     inv = 1.0f / (s + 1e-16f);
-    total = s * inv;
   }
 };
 
-// Epilogue for one float4 column (absolute float4 index c4) of output row i:
-// head mean, +bias, +skip, BatchNorm(eval) affine, ReLU; 128-bit streaming store.
+// Epilogue for one float4 column (absolute float4 index c4) of output row i: head mean,
+// + per-graph instruction term (rows with in-edges only), +bias, +skip, BatchNorm(eval) affine,
+// ReLU; 128-bit streaming store.
 __device__ __forceinline__ void epilogue_store4(const HopParams& p, int i, int c4, float4 o, float inv_heads,
-                                                bool have_skip, const float4& skip) {
+                                                bool add_gb, const float4& gb, bool have_skip,
+                                                const float4& skip) {
   o.x *= inv_heads; o.y *= inv_heads; o.z *= inv_heads; o.w *= inv_heads;
+  if (add_gb) { o.x += gb.x; o.y += gb.y; o.z += gb.z; o.w += gb.w; }
   if (p.bias) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + c4);
     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -129,13 +129,17 @@ __device__ __forceinline__ void gather_node(const HopParams& p, int i, int lane,
   const int g = p.node_graph[i];
   constexpr int per = 32 / H;
 
-  float4 acc[J], skip[J];
+  float4 acc[J], skip[J], gb[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     skip[j] = acc[j];
+    gb[j] = acc[j];
     const int c4 = lane + 32 * j;
-    if (p.h_prev && c4 < c4_n) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * (c4_lo + c4));
+    if (c4 < c4_n) {
+      if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * (c4_lo + c4));
+      if (p.graph_bias && e1 > e0) gb[j] = ldg_cached(p.graph_bias + (int64_t)g * p.C + 4 * (c4_lo + c4));
+    }
   }
 
   if (e1 > e0) {
@@ -172,24 +176,13 @@ __device__ __forceinline__ void gather_node(const HopParams& p, int i, int lane,
       }
       __syncwarp();
     }
-    if (p.x_graph) {
-      // sum_k alpha[k,h] * x_graph[g,h,:] = (sum_k alpha[k,h]) * x_graph[g,h,:]
-      const float* row = p.x_graph + (int64_t)g * H * p.C + 4 * c4_lo;
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float t = __shfl_sync(kFull, sm.total, h);  // lane h serves head h
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const int c4 = lane + 32 * j;
-          if (c4 < c4_n) fma4(acc[j], t, ldg_cached(row + h * p.C + 4 * c4));
-        }
-      }
-    }
   }
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int c4 = lane + 32 * j;
-    if (c4 < c4_n) epilogue_store4(p, i, c4_lo + c4, acc[j], 1.0f / H, p.h_prev != nullptr, skip[j]);
+    if (c4 < c4_n)
+      epilogue_store4(p, i, c4_lo + c4, acc[j], 1.0f / H, p.graph_bias != nullptr && e1 > e0, gb[j],
+                      p.h_prev != nullptr, skip[j]);
   }
 }
 
@@ -207,123 +200,250 @@ __global__ void __launch_bounds__(256) gat_hop_gather_kernel(const HopParams p) 
   gather_node<J, H>(p, i, lane, 0, p.C >> 2, alpha_s[wid], src_s[wid], true);
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 3: block-phase gather.  CTA = 4 warps = 16 consecutive destination nodes.
+// ------------------------------------------------------------------------------------------
+constexpr int kBlkNodes = 16;     // max destination nodes per CTA (the launch picks npc <= 16 so that the
+                                  // grid is one balanced wave: npc = ceil(N / (148 SMs x 4 resident CTAs)))
+constexpr int kBlkThreads = 128;  // 4 warps; warp w owns nodes w, w+4, w+8, w+12 of the CTA
+constexpr int kBlkEdgeCap = 256;  // in-edges of the CTA's nodes staged in shared memory
+
 template <int J, int H>
-static int launch_gather(const HopParams& p, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((p.N + 7) / 8);
-  gat_hop_gather_kernel<J, H><<<grid, 256, 0, stream>>>(p);
+__global__ void __launch_bounds__(kBlkThreads, 4) gat_hop_block_kernel(const HopParams p, const int npc) {
+  __shared__ int32_t rp_s[kBlkNodes + 1];
+  __shared__ int32_t gid_s[kBlkNodes];
+  __shared__ float tgt_s[kBlkNodes * H];
+  __shared__ int32_t src_s[kBlkEdgeCap];
+  __shared__ __align__(16) float alpha_s[kBlkEdgeCap * H];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i0 = blockIdx.x * npc;
+  const int nn = min(npc, p.N - i0);
+  const int C4 = p.C >> 2;
+
+  // ---- round trip 1: row pointers, graph ids, target-side logit terms ----------------------
+  if (tid <= nn) rp_s[tid] = p.rowptr[i0 + tid];
+  if (tid < nn * H) {
+    const int node = tid / H, h = tid - node * H;
+    const int g = p.node_graph[i0 + node];
+    if (h == 0) gid_s[node] = g;
+    float v = p.a_node[(int64_t)(i0 + node) * 2 * H + H + h];
+    if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
+    tgt_s[tid] = v;
+  }
+  __syncthreads();
+  const int eA = rp_s[0], eC = rp_s[nn] - eA;
+
+  if (eC > kBlkEdgeCap) {
+    // hub-heavy block: per-warp chunked path (scratch carved from alpha_s / src_s)
+    for (int node = wid; node < nn; node += 4)
+      gather_node<J, H>(p, i0 + node, lane, 0, C4, alpha_s + wid * kEdgeChunk * H, src_s + wid * kEdgeChunk, true);
+    return;
+  }
+
+  // ---- round trips 2+3: sources, then source/edge logit terms, edge-parallel ----------------
+  for (int k = tid; k < eC; k += kBlkThreads) {
+    const int src = p.col_src[eA + k];
+    const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+    src_s[k] = src;
+#pragma unroll
+    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_node[(int64_t)src * 2 * H + h] + p.a_edge[e * p.lde + h];
+  }
+  __syncthreads();
+
+  // ---- softmax: one thread per (node, head), sequential over that node's in-edges -----------
+  if (tid < nn * H) {
+    const int node = tid / H, h = tid - node * H;
+    const int r0 = rp_s[node] - eA, r1 = rp_s[node + 1] - eA;
+    const float tg = tgt_s[tid];
+    float mx = -INFINITY;
+    for (int k = r0; k < r1; ++k) {
+      const float l = leaky_relu(alpha_s[k * H + h] + tg, p.slope);
+      alpha_s[k * H + h] = l;
+      mx = fmaxf(mx, l);
+    }
+    float sum = 0.f;
+    for (int k = r0; k < r1; ++k) {
+      const float ex = expf(alpha_s[k * H + h] - mx);
+      alpha_s[k * H + h] = ex;
+      sum += ex;
+    }
+    const float inv = 1.0f / (sum + 1e-16f);
+    for (int k = r0; k < r1; ++k) {
+      const float a = alpha_s[k * H + h] * inv;
+      alpha_s[k * H + h] = a;
+      if (p.alpha_out) {
+        const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+        p.alpha_out[e * H + h] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- weighted gather: warp w owns nodes w, w+4, ...; 2 edges x H x J 128-bit loads in flight
+#pragma unroll 1
+  for (int node = wid; node < nn; node += 4) {
+    const int i = i0 + node;
+    const int r0 = rp_s[node] - eA, r1 = rp_s[node + 1] - eA;
+    float4 acc[J], skip[J], gb[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      skip[j] = acc[j];
+      gb[j] = acc[j];
+      const int c4 = lane + 32 * j;
+      if (c4 < C4) {
+        if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * c4);
+        if (p.graph_bias && r1 > r0) gb[j] = ldg_cached(p.graph_bias + (int64_t)gid_s[node] * p.C + 4 * c4);
+      }
+    }
+#pragma unroll 2
+    for (int k = r0; k < r1; ++k) {
+      const float* row = p.x_l + (int64_t)src_s[k] * p.ldx;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float a = alpha_s[k * H + h];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int c4 = lane + 32 * j;
+          if (c4 < C4) fma4(acc[j], a, ldg_cached(row + h * p.C + 4 * c4));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < C4)
+        epilogue_store4(p, i, c4, acc[j], 1.0f / H, p.graph_bias != nullptr && r1 > r0, gb[j],
+                        p.h_prev != nullptr, skip[j]);
+    }
+  }
+}
+
+template <int J, int H>
+static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
+  if (variant == 1) {
+    gat_hop_gather_kernel<J, H><<<(unsigned)((p.N + 7) / 8), 256, 0, stream>>>(p);
+  } else {
+    int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
+    npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
+    gat_hop_block_kernel<J, H><<<(unsigned)((p.N + npc - 1) / npc), kBlkThreads, 0, stream>>>(p, npc);
+  }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
 
 template <int H>
-static int dispatch_gather(const HopParams& p, cudaStream_t stream) {
+static int dispatch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   const int j = (p.C / 4 + 31) / 32;
   switch (j) {
-    case 1: return launch_gather<1, H>(p, stream);
-    case 2: return launch_gather<2, H>(p, stream);
-    case 3: return launch_gather<3, H>(p, stream);
-    case 4: return launch_gather<4, H>(p, stream);
-    case 5: case 6: return launch_gather<6, H>(p, stream);
-    case 7: case 8: return launch_gather<8, H>(p, stream);
+    case 1: return launch_flat<1, H>(p, variant, stream);
+    case 2: return launch_flat<2, H>(p, variant, stream);
+    case 3: return launch_flat<3, H>(p, variant, stream);
+    case 4: return launch_flat<4, H>(p, variant, stream);
+    case 5: case 6: return launch_flat<6, H>(p, variant, stream);
+    case 7: case 8: return launch_flat<8, H>(p, variant, stream);
     default: return GVQA_ERR_UNSUPPORTED;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 2: shared-memory staged.  One CTA = one work unit (graph g, channel slice s of CW4
-// float4 columns).  The slice of every node row of the graph, all H heads, is copied ONCE into
-// shared memory by the TMA engine (cp.async.bulk, one 16*cw4-byte row segment per (node, head),
-// mbarrier completion) while the CTA loads the graph's CSR slice and logit terms and runs the
-// per-destination softmax; the weighted gathers then read shared memory only.  ~63 KB per CTA at
-// n=30, H=4, CW4=32 -> 3 CTAs per SM overlap each other's loads.
-// Units that do not fit the compiled capacity (n > n_cap or in-edges > e_cap) fall back to the
-// global gather path inside the same kernel, so the loader hints are never a correctness input.
+// Kernel 2: shared-memory staged (TMA).  One CTA = one work unit (graph g, channel window w of
+// W4 float4 columns).  The CTA loads the graph's CSR slice + logit terms and runs the
+// per-destination softmax ONCE for all heads, while the TMA engine (cp.async.bulk + mbarrier)
+// streams one stage per head -- the window of every node row of the graph for that head -- through
+// a 3-deep ring of shared-memory buffers.  Each warp keeps the output accumulators of its
+// destination nodes in registers across the H stages.  Units that do not fit the compiled
+// capacity (n > n_cap or in-edges > e_cap) fall back to the global gather path inside the same
+// kernel, so the loader hints are never a correctness input.
 // ------------------------------------------------------------------------------------------
+constexpr int kStagedBufs = 3;
+
 struct StagedCfg {
-  int S, CW4, n_cap, e_cap;
+  int nwin, W4, n_cap, e_cap, nbuf;
 };
 
 __host__ __device__ inline size_t staged_smem_bytes(const StagedCfg& c, int H) {
-  size_t b = (size_t)c.n_cap * H * c.CW4 * 16;        // slab
+  size_t b = (size_t)c.nbuf * c.n_cap * c.W4 * 16;    // stage ring
   b += (size_t)c.e_cap * H * 4;                       // alpha
-  b += (size_t)c.n_cap * H * 4;                       // target term / alpha row sums
-  b += (size_t)c.e_cap * 4;                           // sources
+  b += (size_t)c.n_cap * H * 4;                       // target term
+  b += (size_t)c.e_cap * 4;                           // sources (graph-local)
   b += (size_t)(c.n_cap + 1) * 4;                     // rowptr
   b = (b + 15) & ~(size_t)15;
-  return b + 16;                                      // mbarrier
+  return b + 8 * kStagedBufs;                         // mbarriers
 }
 
-template <int H>
-__global__ void __launch_bounds__(256) gat_hop_staged_kernel(const HopParams p, const StagedCfg cfg) {
+template <int H, int J, int NPW>
+__global__ void __launch_bounds__(512) gat_hop_staged_kernel(const HopParams p, const StagedCfg cfg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* slab = reinterpret_cast<float*>(smem_raw);
-  float* alpha_s = slab + (size_t)cfg.n_cap * H * cfg.CW4 * 4;
+  const size_t stage_floats = (size_t)cfg.n_cap * cfg.W4 * 4;
+  float* stage0 = reinterpret_cast<float*>(smem_raw);
+  float* alpha_s = stage0 + cfg.nbuf * stage_floats;
   float* tgt_s = alpha_s + (size_t)cfg.e_cap * H;
   int32_t* src_s = reinterpret_cast<int32_t*>(tgt_s + (size_t)cfg.n_cap * H);
   int32_t* rp_s = src_s + cfg.e_cap;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(
+  uint64_t* full = reinterpret_cast<uint64_t*>(
       (reinterpret_cast<uintptr_t>(rp_s + cfg.n_cap + 1) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int g = blockIdx.x / cfg.S, s = blockIdx.x - g * cfg.S;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int g = blockIdx.x / cfg.nwin, w = blockIdx.x - g * cfg.nwin;
   const int n0 = p.graph_ptr[g], n1 = p.graph_ptr[g + 1], n = n1 - n0;
   const int C4 = p.C >> 2;
-  const int c4_lo = s * cfg.CW4;
-  const int cw4 = min(cfg.CW4, C4 - c4_lo);
-  if (n <= 0 || cw4 <= 0) return;
+  const int c4_lo = w * cfg.W4;
+  const int w4 = min(cfg.W4, C4 - c4_lo);
+  if (n <= 0 || w4 <= 0) return;
   const int e0 = p.rowptr[n0], e1 = p.rowptr[n1], eg = e1 - e0;
 
-  if (n > cfg.n_cap || eg > cfg.e_cap) {
-    // oversize unit: global gather path, scratch carved from the (unused) slab
-    float* alpha_w = slab + wid * (kEdgeChunk * H + kEdgeChunk);
+  if (n > cfg.n_cap || eg > cfg.e_cap || n > nwarps * NPW) {
+    // oversize unit: global gather path, scratch carved from the (unused) stage ring
+    float* alpha_w = stage0 + wid * (kEdgeChunk * H + kEdgeChunk);
     int32_t* src_w = reinterpret_cast<int32_t*>(alpha_w + kEdgeChunk * H);
-    for (int i = n0 + wid; i < n1; i += 8) gather_node<1, H>(p, i, lane, c4_lo, cw4, alpha_w, src_w, s == 0);
+    for (int i = n0 + wid; i < n1; i += nwarps) gather_node<J, H>(p, i, lane, c4_lo, w4, alpha_w, src_w, w == 0);
     return;
   }
 
-  // ---- 1. kick off the slab copy (TMA engine) ----------------------------------------------
+  // ---- 1. barriers, then kick off the first stages (one stage = one head) -------------------
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int b = 0; b < cfg.nbuf; ++b) mbar_init(&full[b], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(n * H * cw4 * 16));
-  for (int r = tid; r < n * H; r += 256) {
-    const int node = r / H, h = r - node * H;
-    bulk_g2s(slab + (size_t)r * cfg.CW4 * 4, p.x_l + (int64_t)(n0 + node) * p.ldx + h * p.C + 4 * c4_lo,
-             (uint32_t)(cw4 * 16), bar);
-  }
+  const float* win_base = p.x_l + (int64_t)n0 * p.ldx + 4 * c4_lo;
+  auto issue_stage = [&](int q) {  // called by warp 0 only
+    const int b = q % cfg.nbuf;
+    if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)(n * w4 * 16));
+    __syncwarp();
+    float* dst = stage0 + b * stage_floats;
+    for (int r = lane; r < n; r += 32)
+      bulk_g2s(dst + (size_t)r * cfg.W4 * 4, win_base + (int64_t)r * p.ldx + q * p.C, (uint32_t)(w4 * 16), &full[b]);
+  };
+  if (wid == 0)
+    for (int q = 0; q < cfg.nbuf && q < H; ++q) issue_stage(q);
 
   // ---- 2. CSR slice + per-node target terms (one round trip) --------------------------------
-  for (int i = tid; i <= n; i += 256) rp_s[i] = p.rowptr[n0 + i] - e0;
-  for (int t = tid; t < n * H; t += 256) {
+  for (int i = tid; i <= n; i += nthreads) rp_s[i] = p.rowptr[n0 + i] - e0;
+  for (int t = tid; t < n * H; t += nthreads) {
     const int node = t / H, h = t - node * H;
     float v = p.a_node[(int64_t)(n0 + node) * 2 * H + H + h];
     if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
     tgt_s[t] = v;
   }
-  for (int k = tid; k < eg; k += 256) src_s[k] = p.col_src[e0 + k];
-  // per-lane constants of this slice
-  float4 xg[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    xg[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.x_graph && lane < cw4) xg[h] = ldg_cached(p.x_graph + ((int64_t)g * H + h) * p.C + 4 * (c4_lo + lane));
-  }
+  for (int k = tid; k < eg; k += nthreads) src_s[k] = p.col_src[e0 + k] - n0;
   __syncthreads();
 
   // ---- 3. source + edge logit terms, edge-parallel (second round trip) ----------------------
-  for (int t = tid; t < eg * H; t += 256) {
+  for (int t = tid; t < eg * H; t += nthreads) {
     const int k = t / H, h = t - k * H;
     const int64_t e = p.perm ? p.perm[e0 + k] : (e0 + k);
-    alpha_s[t] = p.a_node[(int64_t)src_s[k] * 2 * H + h] + p.a_edge[e * p.lde + h];
+    alpha_s[t] = p.a_node[(int64_t)(src_s[k] + n0) * 2 * H + h] + p.a_edge[e * p.lde + h];
   }
   __syncthreads();
 
-  // ---- 4. per-destination softmax in shared memory (warp per node) --------------------------
+  // ---- 4. per-destination softmax in shared memory (warp per node, all heads at once) -------
   constexpr int per = 32 / H;
   const int head = lane % H, slot = lane / H;
-  for (int node = wid; node < n; node += 8) {
+  for (int node = wid; node < n; node += nwarps) {
     const int r0 = rp_s[node], r1 = rp_s[node + 1];
     const float tg = tgt_s[node * H + head];
     float mx = -INFINITY;
@@ -346,77 +466,139 @@ __global__ void __launch_bounds__(256) gat_hop_staged_kernel(const HopParams p, 
     for (int k = r0 + slot; k < r1; k += per) {
       const float a = alpha_s[k * H + head] * inv;
       alpha_s[k * H + head] = a;
-      if (p.alpha_out && s == 0) {
+      if (p.alpha_out && w == 0) {
         const int64_t e = p.perm ? p.perm[e0 + k] : (e0 + k);
         p.alpha_out[e * H + head] = a;
       }
     }
-    __syncwarp();
-    if (slot == 0) tgt_s[node * H + head] = r1 > r0 ? sum * inv : 0.f;  // row sum of alpha (x_graph term)
   }
-  __syncwarp();
+  __syncwarp();  // a warp consumes only the alpha rows it produced (same node -> warp mapping below)
 
-  // ---- 5. weighted gather from the staged slab + epilogue -----------------------------------
-  mbar_wait(bar, 0);
-  const bool active = lane < cw4;
-  for (int node = wid; node < n; node += 8) {
-    const int i = n0 + node;
-    const int r0 = rp_s[node], r1 = rp_s[node + 1];
-    float4 skip = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.h_prev && active) skip = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * (c4_lo + lane));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
+  // ---- 5. stream the H stages; accumulators of this warp's nodes stay in registers ----------
+  float4 acc[NPW][J];
+#pragma unroll
+  for (int t = 0; t < NPW; ++t)
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[t][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+  for (int q = 0; q < H; ++q) {
+    const int b = q % cfg.nbuf;
+    mbar_wait(&full[b], (uint32_t)((q / cfg.nbuf) & 1));
+    const float* st = stage0 + b * stage_floats;
+#pragma unroll
+    for (int t = 0; t < NPW; ++t) {
+      const int node = wid + t * nwarps;
+      if (node < n) {
+        const int r0 = rp_s[node], r1 = rp_s[node + 1];
 #pragma unroll 2
-      for (int k = r0; k < r1; ++k) {
-        const int src = src_s[k] - n0;
-        if (src >= 0 && src < n) {
-          const float* row = slab + ((size_t)src * H * cfg.CW4 + lane) * 4;
+        for (int k = r0; k < r1; ++k) {
+          const int src = src_s[k];
+          const float a = alpha_s[k * H + q];
+          if (src >= 0 && src < n) {
+            const float* row = st + (size_t)src * cfg.W4 * 4;
 #pragma unroll
-          for (int h = 0; h < H; ++h)
-            fma4(acc, alpha_s[k * H + h], *reinterpret_cast<const float4*>(row + (size_t)h * cfg.CW4 * 4));
-        } else {  // source outside this graph (flagged by gvqa_build_csr): read it from global
-          const float* row = p.x_l + (int64_t)src_s[k] * p.ldx + 4 * (c4_lo + lane);
+            for (int j = 0; j < J; ++j) {
+              const int c4 = lane + 32 * j;
+              if (c4 < w4) fma4(acc[t][j], a, *reinterpret_cast<const float4*>(row + 4 * c4));
+            }
+          } else {  // source outside this graph (flagged by gvqa_build_csr): read it from global
+            const float* row = p.x_l + (int64_t)(src + n0) * p.ldx + q * p.C + 4 * c4_lo;
 #pragma unroll
-          for (int h = 0; h < H; ++h) fma4(acc, alpha_s[k * H + h], ldg_cached(row + h * p.C));
+            for (int j = 0; j < J; ++j) {
+              const int c4 = lane + 32 * j;
+              if (c4 < w4) fma4(acc[t][j], a, ldg_cached(row + 4 * c4));
+            }
+          }
         }
       }
-      if (p.x_graph) {
-#pragma unroll
-        for (int h = 0; h < H; ++h) fma4(acc, tgt_s[node * H + h], xg[h]);
+    }
+    if (q + cfg.nbuf < H) {      // refill this buffer with stage q + nbuf once every warp is done with it
+      __syncthreads();
+      if (wid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_stage(q + cfg.nbuf);
       }
-      epilogue_store4(p, i, c4_lo + lane, acc, 1.0f / H, p.h_prev != nullptr, skip);
+    }
+  }
+
+  // ---- 6. epilogue: head mean, +graph term, +bias, +skip, BatchNorm(eval)+ReLU ---------------
+#pragma unroll
+  for (int t = 0; t < NPW; ++t) {
+    const int node = wid + t * nwarps;
+    if (node < n) {
+      const bool has_in = rp_s[node + 1] > rp_s[node];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < w4) {
+          float4 skip = make_float4(0.f, 0.f, 0.f, 0.f), gb = skip;
+          if (p.h_prev) skip = ldg_stream(p.h_prev + (int64_t)(n0 + node) * p.C + 4 * (c4_lo + c4));
+          if (p.graph_bias && has_in) gb = ldg_cached(p.graph_bias + (int64_t)g * p.C + 4 * (c4_lo + c4));
+          epilogue_store4(p, n0 + node, c4_lo + c4, acc[t][j], 1.0f / H, p.graph_bias != nullptr && has_in, gb,
+                          p.h_prev != nullptr, skip);
+        }
+      }
     }
   }
 }
 
-// Slice geometry for the staged kernel; returns false when the graph slab cannot be staged.
-static bool plan_staged(int C, int H, int max_nodes, int max_in_edges, StagedCfg* out, size_t* smem) {
+struct StagedPlan {
+  StagedCfg cfg;
+  size_t smem;
+  int J, NPW, threads;
+};
+
+// Window geometry for the staged kernel; returns false when the graph slab cannot be staged
+// (the caller then uses the block kernel).
+static bool plan_staged(int C, int H, int max_nodes, int max_in_edges, StagedPlan* out) {
   if (max_nodes <= 0) return false;
   const int C4 = C / 4;
-  StagedCfg c;
-  c.S = (C4 + 31) / 32;
-  c.CW4 = (C4 + c.S - 1) / c.S;
+  StagedPlan pl;
+  StagedCfg& c = pl.cfg;
   c.n_cap = max_nodes;
   c.e_cap = max_in_edges > 0 ? max_in_edges : 8 * max_nodes;
   if (c.e_cap < 64) c.e_cap = 64;
-  // the gather fallback needs 8 x (32*H floats + 32 ints) of scratch inside the slab
-  while ((size_t)c.n_cap * H * c.CW4 * 16 < (size_t)8 * (kEdgeChunk * H + kEdgeChunk) * 4) ++c.n_cap;
-  const size_t b = staged_smem_bytes(c, H);
-  if (b > 112 * 1024) return false;  // keep >= 2 CTAs per SM so units overlap each other's loads
-  *out = c;
-  *smem = b;
-  return true;
+  c.nbuf = H < kStagedBufs ? H : kStagedBufs;
+  pl.threads = 512;  // node capacity: 16 warps x NPW nodes
+  if (c.n_cap <= 32) pl.NPW = 2;
+  else if (c.n_cap <= 64) pl.NPW = 4;
+  else return false;
+  const size_t budget = 112 * 1024;  // >= 2 CTAs per SM so units overlap each other's set-up
+  for (c.nwin = 1; c.nwin <= C4; ++c.nwin) {
+    c.W4 = (C4 + c.nwin - 1) / c.nwin;
+    pl.J = (c.W4 + 31) / 32;
+    if (pl.J > 2) continue;
+    if (c.W4 < 32 && c.nwin > 1) return false;  // narrow windows: tiny TMA segments
+    // the gather fallback needs nwarps x (32*H floats + 32 ints) of scratch inside the ring
+    if ((size_t)c.nbuf * c.n_cap * c.W4 * 16 < (size_t)16 * (kEdgeChunk * H + kEdgeChunk) * 4) return false;
+    pl.smem = staged_smem_bytes(c, H);
+    if (pl.smem <= budget) {
+      *out = pl;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int H, int J, int NPW>
+static int launch_staged3(const HopParams& p, const StagedPlan& pl, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(gat_hop_staged_kernel<H, J, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)pl.smem) != cudaSuccess)
+    return GVQA_ERR_CUDA;
+  const unsigned grid = (unsigned)((int64_t)p.B * pl.cfg.nwin);
+  gat_hop_staged_kernel<H, J, NPW><<<grid, pl.threads, pl.smem, stream>>>(p, pl.cfg);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
 }
 
 template <int H>
-static int launch_staged(const HopParams& p, const StagedCfg& cfg, size_t smem, cudaStream_t stream) {
-  if (cudaFuncSetAttribute(gat_hop_staged_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return GVQA_ERR_CUDA;
-  const unsigned grid = (unsigned)((int64_t)p.B * cfg.S);
-  gat_hop_staged_kernel<H><<<grid, 256, smem, stream>>>(p, cfg);
-  GVQA_LAUNCH_CHECK();
-  return GVQA_OK;
+static int launch_staged(const HopParams& p, const StagedPlan& pl, cudaStream_t stream) {
+  if (pl.J == 1 && pl.NPW == 2) return launch_staged3<H, 1, 2>(p, pl, stream);
+  if (pl.J == 1 && pl.NPW == 4) return launch_staged3<H, 1, 4>(p, pl, stream);
+  if (pl.J == 2 && pl.NPW == 2) return launch_staged3<H, 2, 2>(p, pl, stream);
+  if (pl.J == 2 && pl.NPW == 4) return launch_staged3<H, 2, 4>(p, pl, stream);
+  return GVQA_ERR_UNSUPPORTED;
 }
 
 }  // namespace gvqa
@@ -434,13 +616,14 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->epilogue != GVQA_EPI_NONE && (!a->ep_scale || !a->ep_shift)) return GVQA_ERR_NULL_POINTER;
   if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || a->variant > 3) return GVQA_ERR_UNSUPPORTED;
   if ((a->ldx & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
-      (a->x_graph && !aligned16(a->x_graph)) || (a->bias && !aligned16(a->bias)) ||
+      (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
     return GVQA_ERR_MISALIGNED;
 
   HopParams p;
-  p.x_l = a->x_l; p.x_graph = a->x_graph; p.a_node = a->a_node; p.a_graph = a->a_graph; p.a_edge = a->a_edge;
+  p.x_l = a->x_l; p.graph_bias = a->graph_bias; p.a_node = a->a_node; p.a_graph = a->a_graph; p.a_edge = a->a_edge;
   p.rowptr = a->rowptr; p.col_src = a->col_src; p.perm = a->perm; p.graph_ptr = a->graph_ptr;
   p.node_graph = a->node_graph; p.h_prev = a->h_prev; p.bias = a->bias; p.ep_scale = a->ep_scale;
   p.ep_shift = a->ep_shift; p.h_out = a->h_out; p.alpha_out = a->alpha_out;
@@ -449,25 +632,24 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-  StagedCfg cfg;
-  size_t smem = 0;
-  bool staged = false;
-  if (a->variant != 1 && a->graph_ptr && a->num_graphs > 0)
-    staged = plan_staged(C, H, a->max_nodes_per_graph, a->max_in_edges_per_graph, &cfg, &smem);
-  if (a->variant == 2 && !staged) return GVQA_ERR_UNSUPPORTED;
-  if (staged) {
+  if (a->variant == 2) {
+    StagedPlan plan;
+    if (!a->graph_ptr || a->num_graphs <= 0 ||
+        !plan_staged(C, H, a->max_nodes_per_graph, a->max_in_edges_per_graph, &plan))
+      return GVQA_ERR_UNSUPPORTED;
     switch (H) {
-      case 1: return launch_staged<1>(p, cfg, smem, stream);
-      case 2: return launch_staged<2>(p, cfg, smem, stream);
-      case 4: return launch_staged<4>(p, cfg, smem, stream);
-      case 8: return launch_staged<8>(p, cfg, smem, stream);
+      case 1: return launch_staged<1>(p, plan, stream);
+      case 2: return launch_staged<2>(p, plan, stream);
+      case 4: return launch_staged<4>(p, plan, stream);
+      case 8: return launch_staged<8>(p, plan, stream);
     }
   }
+  const int variant = a->variant == 1 ? 1 : 3;
   switch (H) {
-    case 1: return dispatch_gather<1>(p, stream);
-    case 2: return dispatch_gather<2>(p, stream);
-    case 4: return dispatch_gather<4>(p, stream);
-    case 8: return dispatch_gather<8>(p, stream);
+    case 1: return dispatch_flat<1>(p, variant, stream);
+    case 2: return dispatch_flat<2>(p, variant, stream);
+    case 4: return dispatch_flat<4>(p, variant, stream);
+    case 8: return dispatch_flat<8>(p, variant, stream);
   }
   return GVQA_ERR_UNSUPPORTED;
 }

@@ -12,9 +12,11 @@ trained with the reference loads unchanged, but executes the message passing thr
               gvqa_gat_hop_f32: gather + logits + segment softmax + aggregate + head mean + bias +
               skip + BatchNorm(eval) + ReLU in ONE kernel.
 
-The reference's  cat([h, ins[batch]]) @ W^T  is evaluated as  h @ W[:, :F]^T + (ins @ W[:, F:]^T)[batch]
-and  <W x, att_h>  as  x . (W_h^T att_h)   -- same mathematics, fp32 rounding
-differences of order 1e-6.  Inference only: ``forward`` raises in training mode (attention dropout
+The reference's  cat([h, ins[batch]]) @ W^T  is evaluated as  h @ W[:, :F]^T + (ins @ W[:, F:]^T)[batch];
+the second, per-graph term is identical for every source row of a graph and the softmax weights
+of a destination sum to one, so it is added once per destination as ``graph_bias`` (head mean of
+ins @ W[:, F:]^T).  <W x, att_h> is evaluated as x . (W_h^T att_h)  (SURVEY.md section 8a).  Same
+mathematics, fp32 rounding differences of order 1e-6.  Inference only: ``forward`` raises in training mode (attention dropout
 and BatchNorm batch statistics, gat_skip.py:190/274, are not part of the engine).  CUDA only: there
 is no CPU fallback.
 """
@@ -184,7 +186,8 @@ class gat_seq(nn.Module):
             pk = conv.packed()
             w = conv.lin_l.weight.detach()
             w_h.append(w[:, :f].contiguous())                     # [HC, F]
-            w_ins.append(w[:, f:].t().contiguous())               # [D, HC]
+            heads, c = conv.heads, conv.out_channels
+            w_ins.append(w[:, f:].double().view(heads, c, -1).mean(0).float().t().contiguous())   # [D, C]
             v_node.append(torch.cat([pk["v_l"][:, :f], pk["v_r"][:, :f]]).contiguous())        # [2H, F]
             v_graph.append((pk["v_l"][:, f:].double() + pk["v_r"][:, f:].double()
                             + pk["v_edge"][:, fe:].double()).float().t().contiguous())          # [D, H]
@@ -223,7 +226,7 @@ class gat_seq(nn.Module):
         a_edge_all = (_cabi.skinny_matmul(edge_attr, pk["v_edge"]) if e > 0
                       else x.new_zeros(1, num_hops * heads))                    # [E, hops*H]
         with _strict_fp32_matmul():
-            x_graph_all = torch.bmm(ins, pk["w_ins"])                           # [hops, B, H*C]
+            graph_bias_all = torch.bmm(ins, pk["w_ins"])                        # [hops, B, C]
             a_graph_all = torch.bmm(ins, pk["v_graph"])                         # [hops, B, H]
 
         h = x
@@ -240,7 +243,7 @@ class gat_seq(nn.Module):
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             _cabi.gat_hop(x_l, a_node, a_edge_all[:, i * heads:], csr_d, heads, c, h_out,
-                          lde=a_edge_all.stride(0), x_graph=x_graph_all[i], a_graph=a_graph_all[i],
+                          lde=a_edge_all.stride(0), graph_bias=graph_bias_all[i], a_graph=a_graph_all[i],
                           h_prev=h, bias=self.convs[i].bias,
                           ep_scale=None if last else pk["scale"][i], ep_shift=None if last else pk["shift"][i],
                           negative_slope=self.convs[i].negative_slope,

@@ -95,20 +95,25 @@ GVQA_API int gvqa_skinny_matmul_f32(const float* x, int64_t ldx, const float* v,
  * scatter_add, div), mul, scatter-add aggregate, head mean, +bias, +skip, BatchNorm1d(eval),
  * ReLU  (gat_skip.py:155-168, 183-208, 270-275).
  *
- *   xl_full[n,h,:] = x_l[n*ldx + h*C + :] + (x_graph ? x_graph[g(n), h*C + :] : 0)
+ *   xl[n,h,:]      = x_l[n*ldx + h*C + :]
  *   logit[k,h]     = a_node[src_k, h] + a_node[i, H+h] + (a_graph ? a_graph[g(i), h] : 0)
  *                    + a_edge[e_k*lde + h],   e_k = perm ? perm[k] : k        (k in CSR order)
  *   alpha          = softmax over the in-edges of i of leaky_relu(logit, negative_slope),
  *                    with PyG's  exp(l - max) / (sum + 1e-16)
- *   out[i,:]       = (1/H) sum_h sum_k alpha[k,h] * xl_full[src_k, h, :] + bias + h_prev[i,:]
+ *   out[i,:]       = (1/H) sum_h sum_k alpha[k,h] * xl[src_k, h, :]
+ *                    + (deg(i) > 0 ? graph_bias[g(i), :] : 0) + bias + h_prev[i,:]
  *   h_out[i,:]     = epilogue(out[i,:])
+ * graph_bias carries the instruction half of the reference's concatenated input: every source
+ * row of graph g contains the same term P[g,h,:] = ins[g] @ W_l[h, :, F:]^T, and the softmax
+ * weights of a destination sum to 1, so  sum_k alpha[k,h] P[g,h,:] = P[g,h,:]  and the head mean
+ * of P is added once per destination that has in-edges (graph_bias = mean_h P).
  * alpha_out (optional) receives alpha[E,H] in ORIGINAL edge order (return_attention_weights,
  * gat_skip.py:170-175).  Nodes without in-edges get out = bias + h_prev (empty softmax).
  */
 typedef struct gvqa_gat_hop_args {
   const float* x_l;        /* [N, ldx] projected node features, head-major columns h*C+c     */
   int64_t ldx;             /* row stride of x_l in floats (>= H*C, multiple of 4)            */
-  const float* x_graph;    /* [B, H*C] per-graph additive term of x_l, or NULL               */
+  const float* graph_bias; /* [B, C] per-graph additive output term (see above), or NULL     */
   const float* a_node;     /* [N, 2H]: columns 0..H-1 = source term a_l, H..2H-1 = target a_r */
   const float* a_graph;    /* [B, H] per-graph additive logit term, or NULL                  */
   const float* a_edge;     /* [E, lde] per-edge logit term                                    */
@@ -130,7 +135,7 @@ typedef struct gvqa_gat_hop_args {
   int32_t epilogue;        /* gvqa_epilogue                                                   */
   int32_t max_nodes_per_graph;    /* loader hints (0 = unknown) that size the shared-memory staged  */
   int32_t max_in_edges_per_graph; /* kernel; never a correctness input (oversize graphs fall back)   */
-  int32_t variant;         /* 0 = auto, 1 = force gather-from-L2 kernel, 2 = force smem-staged */
+  int32_t variant;         /* 0 = auto, 1 = warp-per-node gather, 2 = TMA smem-staged, 3 = block-phase gather */
 } gvqa_gat_hop_args;
 
 GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* args, void* stream);
