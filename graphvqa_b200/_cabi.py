@@ -46,6 +46,13 @@ SIGNATURES = {
     "gvqa_gat_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatHopArgs), _c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
+    "gvqa_gine_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                               _c_i32, _c_i32, _c_f32, _c_vp]),
+    "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "gvqa_gcn_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                              _c_i32, _c_vp]),
+    "gvqa_lcgn_hop_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
+                                         _c_vp, _c_i64, _c_i32, _c_f32, _c_vp]),
 }
 
 _lib = None
@@ -182,4 +189,59 @@ def graph_layernorm(x, graph_ptr, num_graphs, weight, bias, eps, out=None, max_n
         check(lib().gvqa_graph_layernorm_f32(ptr(x), ptr(graph_ptr), ptr(weight), ptr(bias), ptr(out),
                                              x.size(0), num_graphs, x.size(1), eps, max_nodes_per_graph,
                                              stream_handle(x.device)), "gvqa_graph_layernorm_f32")
+    return out
+
+
+def gine_aggregate(h, edge_attr, ins, csr, eps, out=None):
+    """z[N, F+D] of GINEConv's propagate + self term on the split inputs (see the header)."""
+    require_cuda(h, edge_attr, ins)
+    require_f32c(h=h, edge_attr=edge_attr, ins=ins, out=out)
+    n, f = h.shape
+    d = 0 if ins is None else ins.size(1)
+    if out is None:
+        out = torch.empty(n, f + d, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        check(lib().gvqa_gine_aggregate_f32(ptr(h), ptr(edge_attr), ptr(ins), ptr(csr["rowptr"]),
+                                            ptr(csr["col_src"]), ptr(csr["perm"]), ptr(csr["node_graph"]),
+                                            ptr(out), n, f, d, eps, stream_handle(h.device)),
+              "gvqa_gine_aggregate_f32")
+    return out
+
+
+def gcn_degree(csr, num_nodes, device):
+    dinv = torch.empty(max(num_nodes, 1), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib().gvqa_gcn_degree_f32(ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(dinv), num_nodes,
+                                        stream_handle(device)), "gvqa_gcn_degree_f32")
+    return dinv
+
+
+def gcn_aggregate(xw, graph_term, dinv, bias, csr, out=None):
+    require_cuda(xw, graph_term, dinv, bias)
+    require_f32c(xw=xw, graph_term=graph_term, dinv=dinv, bias=bias, out=out)
+    n, c = xw.shape
+    if out is None:
+        out = torch.empty(n, c, dtype=torch.float32, device=xw.device)
+    with torch.cuda.device(xw.device):
+        check(lib().gvqa_gcn_aggregate_f32(ptr(xw), ptr(graph_term), ptr(dinv), ptr(bias), ptr(csr["rowptr"]),
+                                           ptr(csr["col_src"]), ptr(csr["node_graph"]), ptr(out), n, c,
+                                           stream_handle(xw.device)), "gvqa_gcn_aggregate_f32")
+    return out
+
+
+def lcgn_hop(xl, xr, xv, proj_cmd, cal_cmd, bias, csr, negative_slope, out=None):
+    """xl/xr/xv: [N,C] views sharing one row stride (unit column stride)."""
+    require_cuda(xl, xr, xv, proj_cmd, cal_cmd, bias)
+    require_f32c(proj_cmd=proj_cmd, cal_cmd=cal_cmd, bias=bias, out=out)
+    n, c = xl.shape
+    ld = xl.stride(0) if n > 1 else c
+    for t in (xl, xr, xv):
+        if t.dtype != torch.float32 or t.stride(1) != 1 or (n > 1 and t.stride(0) != ld):
+            raise ValueError("lcgn_hop: xl/xr/xv must be float32 [N,C] views with a common row stride")
+    if out is None:
+        out = torch.empty(n, c, dtype=torch.float32, device=xl.device)
+    with torch.cuda.device(xl.device):
+        check(lib().gvqa_lcgn_hop_f32(ptr(xl), ptr(xr), ptr(xv), ld, ptr(proj_cmd), ptr(cal_cmd), ptr(bias),
+                                      ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["node_graph"]), ptr(out),
+                                      n, c, negative_slope, stream_handle(xl.device)), "gvqa_lcgn_hop_f32")
     return out

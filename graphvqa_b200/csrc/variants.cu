@@ -1,0 +1,264 @@
+// Message-passing kernels of the GCN / GINE / LCGN variants (see include/gvqa_b200.h).
+//
+// Same skeleton as the GAT hop: int32 destination-CSR, one warp per destination node, lanes own
+// 128-bit column slices, in-edges summed in the caller's edge order, no atomics.
+//   gvqa_gine_aggregate_f32 : torch_geometric GINEConv's propagate + (1+eps)*x_i
+//                             (baseline_and_test_models/pipeline_model_gine.py:665)
+//   gvqa_gcn_degree_f32 / gvqa_gcn_aggregate_f32 : GCNConv's gcn_norm + propagate + bias
+//                             (baseline_and_test_models/pipeline_model_gcn.py:660)
+//   gvqa_lcgn_hop_f32       : gat_lcgn.forward/message (baseline_and_test_models/lcgn.py:120-238)
+#include "common.cuh"
+
+namespace gvqa {
+
+constexpr int kVarThreads = 128;  // 4 warps, one destination node per warp at a time
+
+// ------------------------------------------------------------------------------------------
+// GINE:  z[i, :F]     = (1+eps) h[i] + sum_k relu(h[src_k] + edge_attr[e_k])
+//        z[i, F:F+D]  = (1+eps) ins[g] + deg(i) * relu(2 ins[g])      (instruction halves of
+//        x_cat / edge_cat are the same per-graph vector, pipeline_model_gine.py:652-661)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVarThreads) gine_aggregate_kernel(
+    const float* __restrict__ h, const float* __restrict__ edge_attr, const float* __restrict__ ins,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ node_graph, float* __restrict__ z, int N, int F, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kVarThreads / 32) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  const int F4 = F >> 2, D4 = D >> 2;
+  const int64_t ldz = (int64_t)F + D;
+  const float self_scale = 1.0f + eps;
+  for (int c4 = lane; c4 < F4; c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = e0; k < e1; ++k) {
+      const int src = col_src[k];
+      const int64_t e = perm ? perm[k] : k;
+      const float4 a = ldg_cached(h + (int64_t)src * F + 4 * c4);
+      const float4 b = ldg_stream(edge_attr + e * F + 4 * c4);
+      acc.x += fmaxf(a.x + b.x, 0.f); acc.y += fmaxf(a.y + b.y, 0.f);
+      acc.z += fmaxf(a.z + b.z, 0.f); acc.w += fmaxf(a.w + b.w, 0.f);
+    }
+    const float4 s = ldg_cached(h + (int64_t)i * F + 4 * c4);
+    // PyG adds (1+eps)*x_i AFTER the aggregation (out += (1 + eps) * x_r)
+    acc.x += self_scale * s.x; acc.y += self_scale * s.y; acc.z += self_scale * s.z; acc.w += self_scale * s.w;
+    stg_stream(z + (int64_t)i * ldz + 4 * c4, acc);
+  }
+  if (D4 > 0) {
+    const float deg = (float)(e1 - e0);
+    const float* iv = ins + (int64_t)node_graph[i] * D;
+    for (int c4 = lane; c4 < D4; c4 += 32) {
+      const float4 v = ldg_cached(iv + 4 * c4);
+      float4 o;
+      // sum of deg identical terms relu(v+v), accumulated like the reference (repeated addition
+      // of equal values == deg * value up to rounding), then the self term
+      o.x = deg * fmaxf(v.x + v.x, 0.f) + self_scale * v.x; o.y = deg * fmaxf(v.y + v.y, 0.f) + self_scale * v.y;
+      o.z = deg * fmaxf(v.z + v.z, 0.f) + self_scale * v.z; o.w = deg * fmaxf(v.w + v.w, 0.f) + self_scale * v.w;
+      stg_stream(z + (int64_t)i * ldz + F + 4 * c4, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GCN.  add_remaining_self_loops: existing self-loop edges are dropped, one loop per node is
+// appended; deg(i) = 1 + #non-loop in-edges (duplicates counted); norm_k = dinv[src] dinv[dst].
+// ------------------------------------------------------------------------------------------
+__global__ void gcn_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src,
+                                  float* __restrict__ dinv, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int deg = 1;
+  for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) deg += col_src[k] != i;
+  dinv[i] = 1.0f / sqrtf((float)deg);
+}
+
+//   out[i] = sum_{k: src_k != i} dinv[src_k] dinv[i] (xw[src_k] + P[g]) + dinv[i]^2 (xw[i] + P[g]) + b
+// with xw = h @ W[:F] and P = ins @ W[F:] (x_cat @ W split by rows of W).
+__global__ void __launch_bounds__(kVarThreads) gcn_aggregate_kernel(
+    const float* __restrict__ xw, const float* __restrict__ graph_term, const float* __restrict__ dinv,
+    const float* __restrict__ bias, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src,
+    const int32_t* __restrict__ node_graph, float* __restrict__ out, int N, int C) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kVarThreads / 32) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  const int C4 = C >> 2;
+  const float di = dinv[i];
+  const float* gt = graph_term ? graph_term + (int64_t)node_graph[i] * C : nullptr;
+  for (int c4 = lane; c4 < C4; c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gt) p4 = ldg_cached(gt + 4 * c4);
+#pragma unroll 4
+    for (int k = e0; k < e1; ++k) {
+      const int src = col_src[k];
+      if (src == i) continue;                 // pre-existing self-loops are removed by gcn_norm
+      const float w = dinv[src] * di;
+      const float4 v = ldg_cached(xw + (int64_t)src * C + 4 * c4);
+      acc.x += w * (v.x + p4.x); acc.y += w * (v.y + p4.y); acc.z += w * (v.z + p4.z); acc.w += w * (v.w + p4.w);
+    }
+    const float ws = di * di;                 // the appended loop comes last in PyG's edge list
+    const float4 v = ldg_cached(xw + (int64_t)i * C + 4 * c4);
+    acc.x += ws * (v.x + p4.x); acc.y += ws * (v.y + p4.y); acc.z += ws * (v.z + p4.z); acc.w += ws * (v.w + p4.w);
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    stg_stream(out + (int64_t)i * C + 4 * c4, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LCGN (heads = 1):
+//   logit_k = sum_c xl[src_k,c] * (proj_cmd[g,c] * xr[i,c])          (lcgn.py:154, :209)
+//   alpha   = segment softmax of leaky_relu(logit)                    (:211-212)
+//   out[i]  = cal_cmd[g] * sum_k alpha_k xv[src_k] + bias             (:229-238, :183-186)
+// One pass with a running (max, sum) so each source row is read once per in-edge.
+// ------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(kVarThreads) lcgn_hop_kernel(
+    const float* __restrict__ xl, const float* __restrict__ xr, const float* __restrict__ xv, int64_t ld,
+    const float* __restrict__ proj_cmd, const float* __restrict__ cal_cmd, const float* __restrict__ bias,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src, const int32_t* __restrict__ node_graph,
+    float* __restrict__ out, int N, int C, float slope) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kVarThreads / 32) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  const int C4 = C >> 2;
+  const int g = node_graph[i];
+  float4 q[J], acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[j] = q[j];
+    if (c4 < C4) {
+      const float4 a = ldg_cached(proj_cmd + (int64_t)g * C + 4 * c4);
+      const float4 b = ldg_stream(xr + (int64_t)i * ld + 4 * c4);
+      q[j] = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+    }
+  }
+  float m = -INFINITY, s = 0.f;
+  for (int k = e0; k < e1; ++k) {
+    const int src = col_src[k];
+    float4 lv[J], vv[J];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c4 = lane + 32 * j;
+      lv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[j] = lv[j];
+      if (c4 < C4) {
+        lv[j] = ldg_cached(xl + (int64_t)src * ld + 4 * c4);
+        vv[j] = ldg_cached(xv + (int64_t)src * ld + 4 * c4);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      dot += (lv[j].x * q[j].x + lv[j].y * q[j].y) + (lv[j].z * q[j].z + lv[j].w * q[j].w);
+    const float l = leaky_relu(warp_sum(dot), slope);
+    const float m_new = fmaxf(m, l);
+    const float rescale = expf(m - m_new);     // exp(-inf) = 0 on the first edge
+    const float w = expf(l - m_new);
+    s = s * rescale + w;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      acc[j].x = acc[j].x * rescale + w * vv[j].x; acc[j].y = acc[j].y * rescale + w * vv[j].y;
+      acc[j].z = acc[j].z * rescale + w * vv[j].z; acc[j].w = acc[j].w * rescale + w * vv[j].w;
+    }
+    m = m_new;
+  }
+  const float inv = 1.0f / (s + 1e-16f);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < C4) {
+      const float4 cc = ldg_cached(cal_cmd + (int64_t)g * C + 4 * c4);
+      float4 o = make_float4(acc[j].x * inv * cc.x, acc[j].y * inv * cc.y, acc[j].z * inv * cc.z, acc[j].w * inv * cc.w);
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      stg_stream(out + (int64_t)i * C + 4 * c4, o);
+    }
+  }
+}
+
+}  // namespace gvqa
+
+using namespace gvqa;
+
+extern "C" GVQA_API int gvqa_gine_aggregate_f32(const float* h, const float* edge_attr, const float* ins,
+                                                const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
+                                                const int32_t* node_graph, float* z, int64_t num_nodes,
+                                                int32_t feat, int32_t ins_dim, float eps, void* stream_) {
+  if (num_nodes < 0 || feat <= 0 || ins_dim < 0 || num_nodes >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!h || !edge_attr || !rowptr || !col_src || !z || (ins_dim > 0 && (!ins || !node_graph)))
+    return GVQA_ERR_NULL_POINTER;
+  if ((feat & 3) || (ins_dim & 3)) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(h) || !aligned16(edge_attr) || !aligned16(z) || (ins && !aligned16(ins))) return GVQA_ERR_MISALIGNED;
+  const unsigned grid = (unsigned)((num_nodes + 3) / 4);
+  gine_aggregate_kernel<<<grid, kVarThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      h, edge_attr, ins, rowptr, col_src, perm, node_graph, z, (int)num_nodes, feat, ins_dim, eps);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_gcn_degree_f32(const int32_t* rowptr, const int32_t* col_src, float* dinv,
+                                            int64_t num_nodes, void* stream_) {
+  if (num_nodes < 0 || num_nodes >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!rowptr || !col_src || !dinv) return GVQA_ERR_NULL_POINTER;
+  gcn_degree_kernel<<<(unsigned)((num_nodes + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      rowptr, col_src, dinv, (int)num_nodes);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_gcn_aggregate_f32(const float* xw, const float* graph_term, const float* dinv,
+                                               const float* bias, const int32_t* rowptr, const int32_t* col_src,
+                                               const int32_t* node_graph, float* out, int64_t num_nodes,
+                                               int32_t channels, void* stream_) {
+  if (num_nodes < 0 || channels <= 0 || num_nodes >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!xw || !dinv || !rowptr || !col_src || !out || (graph_term && !node_graph)) return GVQA_ERR_NULL_POINTER;
+  if (channels & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(xw) || !aligned16(out) || (graph_term && !aligned16(graph_term)) || (bias && !aligned16(bias)))
+    return GVQA_ERR_MISALIGNED;
+  const unsigned grid = (unsigned)((num_nodes + 3) / 4);
+  gcn_aggregate_kernel<<<grid, kVarThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      xw, graph_term, dinv, bias, rowptr, col_src, node_graph, out, (int)num_nodes, channels);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_lcgn_hop_f32(const float* xl, const float* xr, const float* xv, int64_t ld,
+                                          const float* proj_cmd, const float* cal_cmd, const float* bias,
+                                          const int32_t* rowptr, const int32_t* col_src, const int32_t* node_graph,
+                                          float* out, int64_t num_nodes, int32_t channels, float negative_slope,
+                                          void* stream_) {
+  if (num_nodes < 0 || channels <= 0 || ld < channels || num_nodes >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!xl || !xr || !xv || !proj_cmd || !cal_cmd || !rowptr || !col_src || !node_graph || !out)
+    return GVQA_ERR_NULL_POINTER;
+  if ((channels & 3) || channels > 1024) return GVQA_ERR_UNSUPPORTED;
+  if ((ld & 3) || !aligned16(xl) || !aligned16(xr) || !aligned16(xv) || !aligned16(proj_cmd) || !aligned16(cal_cmd) ||
+      !aligned16(out) || (bias && !aligned16(bias)))
+    return GVQA_ERR_MISALIGNED;
+  const unsigned grid = (unsigned)((num_nodes + 3) / 4);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int j = (channels / 4 + 31) / 32;
+#define GVQA_LCGN(JJ)                                                                                         \
+  lcgn_hop_kernel<JJ><<<grid, kVarThreads, 0, stream>>>(xl, xr, xv, ld, proj_cmd, cal_cmd, bias, rowptr, col_src, \
+                                                        node_graph, out, (int)num_nodes, channels, negative_slope)
+  if (j <= 1) GVQA_LCGN(1);
+  else if (j == 2) GVQA_LCGN(2);
+  else if (j <= 4) GVQA_LCGN(4);
+  else GVQA_LCGN(8);
+#undef GVQA_LCGN
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}

@@ -152,6 +152,49 @@ GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, 
                              int64_t num_graphs, int32_t channels, float eps,
                              int32_t max_nodes_per_graph, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GINE message passing: the propagate + self term of torch_geometric's GINEConv as called by
+ * gine_seq.forward (baseline_and_test_models/pipeline_model_gine.py:652-665) on the concatenated
+ * inputs x_cat = [h | ins[batch]], edge_cat = [edge_attr | ins[batch[src]]]:
+ *   z[i, :F]    = (1+eps) h[i] + sum_k relu(h[src_k] + edge_attr[e_k]),  e_k = perm ? perm[k] : k
+ *   z[i, F:F+D] = (1+eps) ins[g(i)] + deg(i) relu(2 ins[g(i)])
+ * z [N, F+D] then feeds the conv's MLP (two library GEMMs on the host side).
+ */
+GVQA_API int gvqa_gine_aggregate_f32(const float* h, const float* edge_attr, const float* ins,
+                                     const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
+                                     const int32_t* node_graph, float* z, int64_t num_nodes,
+                                     int32_t feat, int32_t ins_dim, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GCN message passing: gcn_norm + propagate + bias of torch_geometric's GCNConv
+ * (pipeline_model_gcn.py:660): existing self-loops dropped, one loop per
+ * node appended, deg over targets, norm = deg^-1/2[src] deg^-1/2[dst].
+ *   gvqa_gcn_degree_f32:    dinv[i] = (1 + #non-loop in-edges of i)^-1/2
+ *   gvqa_gcn_aggregate_f32: out[i] = sum_{k: src_k != i} dinv[src_k] dinv[i] (xw[src_k] + P[g])
+ *                                    + dinv[i]^2 (xw[i] + P[g]) + bias
+ * with xw = h @ W[:F] [N,C] and the optional per-graph term P = ins @ W[F:] [B,C].
+ */
+GVQA_API int gvqa_gcn_degree_f32(const int32_t* rowptr, const int32_t* col_src, float* dinv,
+                                 int64_t num_nodes, void* stream);
+GVQA_API int gvqa_gcn_aggregate_f32(const float* xw, const float* graph_term, const float* dinv,
+                                    const float* bias, const int32_t* rowptr, const int32_t* col_src,
+                                    const int32_t* node_graph, float* out, int64_t num_nodes,
+                                    int32_t channels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LCGN hop, heads = 1: gat_lcgn.forward + message (baseline_and_test_models/lcgn.py:120-238)
+ * after the node projections, with the per-edge Linear cal_x(x_j) hoisted to node level
+ * (xv = cal_x(x)) and the one-hot matmuls replaced by a gather on node_graph:
+ *   logit_k = sum_c xl[src_k,c] * proj_cmd[g,c] * xr[i,c];   alpha = segment_softmax(leaky_relu)
+ *   out[i]  = cal_cmd[g] * sum_k alpha_k xv[src_k] + bias
+ * xl / xr / xv are [N, C] views with a common row stride ld (e.g. slices of one [N, 3C] GEMM).
+ */
+GVQA_API int gvqa_lcgn_hop_f32(const float* xl, const float* xr, const float* xv, int64_t ld,
+                               const float* proj_cmd, const float* cal_cmd, const float* bias,
+                               const int32_t* rowptr, const int32_t* col_src, const int32_t* node_graph,
+                               float* out, int64_t num_nodes, int32_t channels, float negative_slope,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
