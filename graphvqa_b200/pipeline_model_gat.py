@@ -1,0 +1,396 @@
+"""``PipelineModel`` with the reference's forward/API surface (pipeline_model_gat.py:615-836).
+
+    from graphvqa_b200.pipeline_model_gat import PipelineModel      # instead of: from pipeline_model_gat import ...
+    model = PipelineModel()                                         # mainExplain_gat.py:251
+    programs_output, short_answer_logits = model(questions, gt_scene_graphs, programs_input,
+                                                 full_answers_input, SAMPLE_FLAG=True)   # :758-764
+
+Sub-module names, parameter shapes and ``state_dict`` keys equal the reference's, so a reference
+checkpoint loads through the same size-tolerant ``load_state_dict`` (:823-836).  What runs where:
+
+* scene-graph message passing (``gat_seq`` -- or ``gcn_seq`` / ``gine_seq`` / ``lcgn_seq`` in the sibling
+  modules) and the per-graph LayerNorm: hand-written sm_100a kernels through the C ABI;
+* Transformer question encoder, program decoders, answer head: ordinary PyTorch (``torch.nn``), as in
+  the reference;
+* scene-graph encoder MLPs and the question-conditioned pooling: PyTorch GEMMs around
+  segment reductions that use the batch's destination-CSR (no torch_geometric / torch_scatter).
+
+The reference reads its vocabularies from class attributes of ``gqa_dataset_entry`` at construction
+(pipeline_model_gat.py:556-562, 628-634).  ``PipelineModel()`` does the same when that module is
+importable (true drop-in inside the reference tree); otherwise pass a ``VocabSpec``.
+"""
+import logging
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .gat_skip import gat_seq
+from .graph_batch import GraphCSR, SceneGraphBatch
+from .my_graph_layernorm import LayerNorm
+
+MAX_EXECUTION_STEP = 5          # GQATorchDataset.MAX_EXECUTION_STEP (gqa_dataset_entry.py:387)
+
+
+@dataclass
+class VocabSpec:
+    """What the model needs to know about the two torchtext vocabularies."""
+    text_vocab_size: int
+    sg_vocab_size: int
+    text_pad_idx: int = 1
+    sg_pad_idx: int = 1
+    text_init_idx: int = 2                       # TEXT.vocab.stoi[TEXT.init_token]  ('<start>')
+    text_vectors: Optional[torch.Tensor] = None  # GloVe rows [text_vocab_size, 300] or None
+    num_queries: int = MAX_EXECUTION_STEP
+
+    @staticmethod
+    def from_reference_dataset():
+        try:
+            from gqa_dataset_entry import GQA_gt_sg_feature_lookup, GQATorchDataset   # the reference's module
+        except Exception as exc:  # pragma: no cover - depends on the caller's environment
+            raise RuntimeError("PipelineModel() needs the reference's gqa_dataset_entry vocabularies or an "
+                               "explicit VocabSpec(text_vocab_size=..., sg_vocab_size=...)") from exc
+        text, sg = GQATorchDataset.TEXT, GQA_gt_sg_feature_lookup.SG_ENCODING_TEXT
+        return VocabSpec(text_vocab_size=len(text.vocab), sg_vocab_size=len(sg.vocab),
+                         text_pad_idx=text.vocab.stoi[text.pad_token], sg_pad_idx=sg.vocab.stoi[sg.pad_token],
+                         text_init_idx=text.vocab.stoi[text.init_token],
+                         text_vectors=getattr(text.vocab, "vectors", None),
+                         num_queries=getattr(GQATorchDataset, "MAX_EXECUTION_STEP", MAX_EXECUTION_STEP))
+
+
+def _batch_csr(graphs, num_graphs):
+    """The batch's destination-CSR: cached on a SceneGraphBatch, built ad hoc for foreign objects."""
+    if isinstance(graphs, SceneGraphBatch):
+        if graphs.num_graphs is None:
+            graphs.num_graphs = num_graphs
+        return graphs.csr()
+    csr = getattr(graphs, "_gvqa_csr", None)
+    if csr is None or csr.num_graphs != num_graphs or csr.rowptr.device != graphs.edge_index.device:
+        csr = GraphCSR.build(graphs.edge_index, graphs.batch, num_graphs)
+        try:
+            graphs._gvqa_csr = csr
+        except Exception:
+            pass
+    return csr
+
+
+def _segment_sum_by_dst(values, csr):
+    """sum of per-edge rows over the in-edges of every node, in CSR (= original edge) order."""
+    n = csr.num_nodes
+    out = values.new_zeros((n,) + tuple(values.shape[1:]))
+    if values.size(0) == 0:
+        return out
+    ordered = values.index_select(0, csr.perm[:values.size(0)].long())
+    return torch.segment_reduce(ordered, "sum", offsets=csr.rowptr.long(), axis=0, initial=0) if n else out
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table added to [Len, Batch, Dim] inputs (pipeline_model_gat.py:296-313)."""
+
+    def __init__(self, d_model, dropout=0.1, max_len=5000):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        freq = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, d_model)
+        pe[:, 0::2] = torch.sin(pos * freq)
+        pe[:, 1::2] = torch.cos(pos * freq)
+        self.register_buffer("pe", pe.unsqueeze(0).transpose(0, 1))
+
+    def forward(self, x):
+        return self.dropout(x + self.pe[:x.size(0), :])
+
+
+def _causal_mask(sz, device):
+    return torch.triu(torch.full((sz, sz), float("-inf"), device=device), diagonal=1)
+
+
+class _TextDecoderBase(nn.Module):
+    def __init__(self, text_vocab_embedding, vocab_size, text_emb_dim, ninp, nhead, nhid, nlayers, dropout):
+        super().__init__()
+        self.text_vocab_embedding = text_vocab_embedding
+        self.model_type = "Transformer"
+        self.emb_proj = nn.Linear(text_emb_dim, ninp)
+        self.pos_encoder = PositionalEncoding(ninp, dropout)
+        self.ninp = ninp
+
+    def generate_square_subsequent_mask(self, sz):
+        return _causal_mask(sz, torch.device("cpu"))
+
+    def _embed(self, tokens):
+        return self.pos_encoder(self.emb_proj(self.text_vocab_embedding(tokens)) * math.sqrt(self.ninp))
+
+
+class TransformerProgramDecoder(_TextDecoderBase):
+    """Hierarchical program decoder (pipeline_model_gat.py:317-445): a non-autoregressive coarse
+    decoder over ``num_queries`` learned queries yields the instruction vectors [M, B, D]; a second
+    decoder spells out each instruction's tokens (teacher-forced ``forward`` / greedy ``sample``)."""
+
+    def __init__(self, text_vocab_embedding, vocab_size, text_emb_dim, ninp, nhead, nhid, nlayers, dropout=0.1,
+                 num_queries=MAX_EXECUTION_STEP, init_token_idx=2):
+        super().__init__(text_vocab_embedding, vocab_size, text_emb_dim, ninp, nhead, nhid, nlayers, dropout)
+        self.num_queries = num_queries
+        self.init_token_idx = init_token_idx
+        self.query_embed = nn.Embedding(self.num_queries, ninp)
+        layer = nn.TransformerDecoderLayer(ninp, nhead, nhid, dropout)
+        self.coarse_decoder = nn.TransformerDecoder(layer, nlayers, norm=nn.LayerNorm(ninp))
+        layer = nn.TransformerDecoderLayer(ninp, nhead, nhid, dropout)
+        self.transformer_decoder = nn.TransformerDecoder(layer, nlayers, norm=nn.LayerNorm(ninp))
+        self.vocab_decoder = nn.Linear(ninp, vocab_size)
+
+    def instruction_vectors(self, memory):
+        b = memory.size(1)
+        queries = self.query_embed.weight.unsqueeze(1).repeat(1, b, 1)
+        instr = self.coarse_decoder(tgt=queries, memory=memory, tgt_mask=None)          # [M, B, D]
+        flat = instr.permute(1, 0, 2).reshape(b * self.num_queries, -1).unsqueeze(0)    # [1, B*M, D]
+        return instr, flat, memory.repeat_interleave(self.num_queries, dim=1)
+
+    def forward(self, memory, tgt):
+        instr, flat, memory_rep = self.instruction_vectors(memory)
+        mask = _causal_mask(tgt.shape[0], memory.device)
+        seq = torch.cat((flat, self._embed(tgt)[1:]), dim=0)       # the <start> slot carries the instruction
+        out = self.transformer_decoder(tgt=seq, memory=memory_rep, tgt_mask=mask)
+        return self.vocab_decoder(out), instr
+
+    def sample(self, memory, tgt=None, max_output_len=16):
+        instr, flat, memory_rep = self.instruction_vectors(memory)
+        rows = memory.size(1) * self.num_queries
+        output = torch.full((max_output_len, rows), self.init_token_idx, dtype=torch.long, device=memory.device)
+        for t in range(1, max_output_len):
+            seq = torch.cat((flat, self._embed(output[:t, :])[1:]), dim=0)
+            out = self.transformer_decoder(seq, memory_rep, tgt_mask=_causal_mask(t, memory.device))
+            output[t, :] = self.vocab_decoder(out)[-1].argmax(dim=-1)
+        return output, instr
+
+
+class TransformerFullAnswerDecoder(_TextDecoderBase):
+    """Constructed (its weights are part of every checkpoint) but never called by ``forward``
+    (pipeline_model_gat.py:449-526)."""
+
+    def __init__(self, text_vocab_embedding, vocab_size, text_emb_dim, ninp, nhead, nhid, nlayers, dropout=0.5,
+                 init_token_idx=2):
+        super().__init__(text_vocab_embedding, vocab_size, text_emb_dim, ninp, nhead, nhid, nlayers, dropout)
+        self.init_token_idx = init_token_idx
+        layer = nn.TransformerDecoderLayer(ninp, nhead, nhid, dropout)
+        self.transformer_decoder = nn.TransformerDecoder(layer, nlayers, norm=nn.LayerNorm(ninp))
+        self.vocab_decoder = nn.Linear(ninp, vocab_size)
+
+    def forward(self, memory, tgt):
+        out = self.transformer_decoder(tgt=self._embed(tgt), memory=memory,
+                                       tgt_mask=_causal_mask(tgt.shape[0], memory.device))
+        return self.vocab_decoder(out)
+
+    def sample(self, memory, tgt=None, max_output_len=20):
+        output = torch.full((max_output_len, memory.size(1)), self.init_token_idx, dtype=torch.long,
+                            device=memory.device)
+        for t in range(1, max_output_len):
+            out = self.transformer_decoder(self._embed(output[:t, :]), memory, tgt_mask=_causal_mask(t, memory.device))
+            output[t, :] = self.vocab_decoder(out)[-1].argmax(dim=-1)
+        return output
+
+
+class TransformerQuestionEncoder(nn.Module):
+    """pipeline_model_gat.py:530-550."""
+
+    def __init__(self, text_vocab_embedding, text_emb_dim, ninp, nhead, nhid, nlayers, dropout=0.5):
+        super().__init__()
+        self.text_vocab_embedding = text_vocab_embedding
+        self.model_type = "Transformer"
+        self.emb_proj = nn.Linear(text_emb_dim, ninp)
+        self.pos_encoder = PositionalEncoding(ninp, dropout)
+        layer = nn.TransformerEncoderLayer(ninp, nhead, nhid, dropout)
+        self.transformer_encoder = nn.TransformerEncoder(layer, nlayers, norm=nn.LayerNorm(ninp),
+                                                         enable_nested_tensor=False)
+        self.ninp = ninp
+
+    def forward(self, src):
+        x = self.emb_proj(self.text_vocab_embedding(src)) * math.sqrt(self.ninp)
+        return self.transformer_encoder(self.pos_encoder(x))
+
+
+class _EdgeModel(nn.Module):
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.edge_mlp = nn.Sequential(nn.Linear(2 * nf + ef, ef), nn.ReLU(), nn.Linear(ef, ef))
+
+
+class _NodeModel(nn.Module):
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.node_mlp_1 = nn.Sequential(nn.Linear(nf + ef, nf), nn.ReLU(), nn.Linear(nf, nf))
+        self.node_mlp_2 = nn.Sequential(nn.Linear(2 * nf, nf), nn.ReLU(), nn.Linear(nf, nf))
+
+
+class _MetaLayer(nn.Module):
+    """torch_geometric.nn.MetaLayer(EdgeModel, NodeModel) as instantiated by
+    get_gt_scene_graph_encoding_layer (pipeline_model_gat.py:63-101):
+    edges first -- e' = edge_mlp([x_src | x_dst | e]) -- then nodes on the UPDATED edges:
+    x' = node_mlp_2([x | mean_{in-edges} node_mlp_1([x_src | e'])])."""
+
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.edge_model = _EdgeModel(nf, ef)
+        self.node_model = _NodeModel(nf, ef)
+
+    def forward(self, x, edge_index, edge_attr, csr):
+        row, col = edge_index[0], edge_index[1]
+        e_new = self.edge_model.edge_mlp(torch.cat([x[row], x[col], edge_attr], dim=1))
+        msg = self.node_model.node_mlp_1(torch.cat([x[row], e_new], dim=1))
+        deg = (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).to(msg.dtype).unsqueeze(1)
+        agg = _segment_sum_by_dst(msg, csr) / deg                      # scatter_mean (count clamped to 1)
+        return self.node_model.node_mlp_2(torch.cat([x, agg], dim=1)), e_new
+
+
+class GroundTruth_SceneGraph_Encoder(nn.Module):
+    """Token-embedding sum -> MetaLayer -> per-graph LayerNorm (pipeline_model_gat.py:553-610)."""
+
+    def __init__(self, sg_vocab_size, sg_pad_idx):
+        super().__init__()
+        self.sg_emb_dim = 300
+        self.sg_vocab_embedding = nn.Embedding(sg_vocab_size, self.sg_emb_dim, padding_idx=sg_pad_idx)
+        self.scene_graph_encoding_layer = _MetaLayer(self.sg_emb_dim, self.sg_emb_dim)
+        self.graph_layer_norm = LayerNorm(self.sg_emb_dim)
+
+    def forward(self, gt_scene_graphs, csr=None):
+        g = gt_scene_graphs
+        x_sum = self.sg_vocab_embedding(g.x).sum(dim=-2)
+        e_emb = self.sg_vocab_embedding(g.edge_attr)
+        sym = getattr(g, "added_sym_edge", None)
+        if sym is not None and sym.numel() > 0:
+            # the reference negates rows `added_sym_edge` of the BATCHED edge array although the indices
+            # are graph-local (Batch.from_data_list does not offset them; pipeline_model_gat.py:590)
+            e_emb = e_emb.clone()
+            e_emb[sym, :, :] *= -1
+        e_sum = e_emb.sum(dim=-2)
+        if csr is None:
+            csr = _batch_csr(g, int(g.batch.max()) + 1 if getattr(g, "num_graphs", None) is None else g.num_graphs)
+        x_enc, e_enc = self.scene_graph_encoding_layer(x_sum, g.edge_index, e_sum, csr)
+        return self.graph_layer_norm(x_enc, g.batch, csr=csr), e_enc, None
+
+
+class MyConditionalGlobalAttention(nn.Module):
+    """Question-conditioned soft attention pooling over the nodes of each graph
+    (pipeline_model_gat.py:108-185): gate = gate_nn(ques_nn(u)[batch] * node_nn(x)), per-graph
+    softmax (PyG semantics, +1e-16), weighted sum."""
+
+    def __init__(self, num_node_features, num_out_features):
+        super().__init__()
+        c = num_out_features
+        self.gate_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, 1))
+        self.node_nn = nn.Sequential(nn.Linear(num_node_features, c), nn.ReLU(), nn.Linear(c, c))
+        self.ques_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c))
+
+    def forward(self, x, u, batch, size=None, graph_ptr=None):
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        size = u.size(0) if size is None else size        # the reference syncs on batch[-1].item() (:152)
+        x = self.node_nn(x)
+        gate = self.gate_nn(self.ques_nn(u)[batch] * x)
+        if graph_ptr is None:
+            counts = torch.bincount(batch, minlength=size)
+            graph_ptr = torch.zeros(size + 1, dtype=torch.long, device=x.device)
+            graph_ptr[1:] = counts.cumsum(0)
+        offsets = graph_ptr.long()
+        lengths = offsets[1:] - offsets[:-1]
+        seg_max = torch.segment_reduce(gate, "max", lengths=lengths, axis=0, initial=float("-inf"))
+        seg_max = torch.where(torch.isinf(seg_max), torch.zeros_like(seg_max), seg_max)
+        ex = (gate - seg_max[batch]).exp()
+        seg_sum = torch.segment_reduce(ex, "sum", lengths=lengths, axis=0, initial=0)
+        gate = ex / (seg_sum[batch] + 1e-16)
+        return torch.segment_reduce(gate * x, "sum", lengths=lengths, axis=0, initial=0)
+
+
+class PipelineModel(nn.Module):
+    """Reference surface: ``forward(questions, gt_scene_graphs, programs_input, full_answers_input,
+    SAMPLE_FLAG=False) -> (programs_output, short_answer_logits)``."""
+
+    variant = "gat"
+
+    def __init__(self, vocab: Optional[VocabSpec] = None):
+        super().__init__()
+        vocab = vocab or VocabSpec.from_reference_dataset()
+        self.vocab = vocab
+        self.scene_graph_encoder = GroundTruth_SceneGraph_Encoder(vocab.sg_vocab_size, vocab.sg_pad_idx)
+
+        text_emb_dim = 300
+        self.text_vocab_embedding = nn.Embedding(vocab.text_vocab_size, text_emb_dim, padding_idx=vocab.text_pad_idx)
+        if vocab.text_vectors is not None:
+            self.text_vocab_embedding.weight.data.copy_(vocab.text_vectors)
+
+        self.question_hidden_dim = 512
+        d = self.question_hidden_dim
+        self.question_encoder = TransformerQuestionEncoder(self.text_vocab_embedding, text_emb_dim, ninp=d, nhead=8,
+                                                           nhid=4 * d, nlayers=3, dropout=0.1)
+        self.program_decoder = TransformerProgramDecoder(self.text_vocab_embedding, vocab.text_vocab_size,
+                                                         text_emb_dim, ninp=d, nhead=8, nhid=4 * d, nlayers=3,
+                                                         dropout=0.1, num_queries=vocab.num_queries,
+                                                         init_token_idx=vocab.text_init_idx)
+        self._build_graph_engine()
+        self.full_answer_decoder = TransformerFullAnswerDecoder(self.text_vocab_embedding, vocab.text_vocab_size,
+                                                                text_emb_dim, ninp=d, nhead=8, nhid=4 * d,
+                                                                nlayers=3, dropout=0.1,
+                                                                init_token_idx=vocab.text_init_idx)
+        self.logit_fc = nn.Sequential(nn.Dropout(p=0.2), nn.Linear(3 * d, 512), nn.ELU(), nn.Dropout(p=0.2),
+                                      nn.Linear(512, 1842))
+
+    # -- variant hooks (overridden in pipeline_model_{gcn,gine,lcgn}.py) ------------------------
+    def _build_graph_engine(self):
+        f, d = self.scene_graph_encoder.sg_emb_dim, self.question_hidden_dim
+        self.gat_seq = gat_seq(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d, num_ins=5, dropout=0.1,
+                               gat_heads=4, gat_negative_slope=0.2, gat_bias=True)
+        self.graph_global_attention_pooling = MyConditionalGlobalAttention(num_node_features=f, num_out_features=d)
+
+    def _execute(self, x_encoded, edge_attr_encoded, graphs, instr_vectors, questions_encoded, csr):
+        return self.gat_seq(x=x_encoded, edge_index=graphs.edge_index, edge_attr=edge_attr_encoded,
+                            instr_vectors=instr_vectors, batch=graphs.batch, csr=csr)
+
+    # -------------------------------------------------------------------------------------------
+    def forward(self, questions, gt_scene_graphs, programs_input, full_answers_input, SAMPLE_FLAG=False):
+        _cabi.require_cuda(questions, gt_scene_graphs.edge_index)
+        if self.training or torch.is_grad_enabled():
+            raise NotImplementedError("PipelineModel (B200 engine) is inference-only: call .eval() and run under "
+                                      "torch.no_grad(); training stays on the reference path")
+        num_graphs = questions.size(1)
+        csr = _batch_csr(gt_scene_graphs, num_graphs)
+        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+        questions_encoded = self.question_encoder(questions)
+        if not SAMPLE_FLAG:
+            programs_output, instr_vectors = self.program_decoder(memory=questions_encoded, tgt=programs_input)
+        else:
+            programs_output, instr_vectors = self.program_decoder.sample(memory=questions_encoded, tgt=programs_input)
+        x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
+        q0 = questions_encoded[0]
+        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch,
+                                                     size=num_graphs, graph_ptr=csr.graph_ptr)
+        short_answer_logits = self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
+        return programs_output, short_answer_logits
+
+    def answer_logits(self, questions, gt_scene_graphs):
+        """Inference fast path: the short-answer logits do not depend on the fine program decoder
+        (SURVEY.md section 0, fact 10), so only the coarse decoder runs."""
+        num_graphs = questions.size(1)
+        csr = _batch_csr(gt_scene_graphs, num_graphs)
+        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+        questions_encoded = self.question_encoder(questions)
+        instr_vectors = self.program_decoder.instruction_vectors(questions_encoded)[0]
+        x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
+        q0 = questions_encoded[0]
+        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch,
+                                                     size=num_graphs, graph_ptr=csr.graph_ptr)
+        return self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
+
+    def load_state_dict(self, state_dict, strict=True):
+        """Size-tolerant load (pipeline_model_gat.py:823-836): keys that are missing here or whose
+        shapes differ are skipped and reported through ``logging``."""
+        own = self.state_dict()
+        usable = {k: v for k, v in state_dict.items() if k in own and own[k].size() == v.size()}
+        name = type(self).__name__
+        if len(usable) == len(state_dict):
+            logging.info("%s: All params loaded" % name)
+        else:
+            logging.info("%s: Some params were not loaded:" % name)
+            logging.info(", ".join(k for k in state_dict if k not in usable))
+        own.update(usable)
+        return super().load_state_dict(own)

@@ -19,27 +19,54 @@ from . import run_reference as rr
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def debug_topology():
-    """(edge_index[2,E], batch[N], added_sym_edge list per graph) for the 4 debug scene graphs."""
+def debug_graph_list():
+    """Per-graph (edge_index[2,e] local ids, num_nodes, added_sym_edge positions) of the 4 debug graphs."""
     with open(os.path.join(rr.REFERENCE_ROOT, "debug_sceneGraphs.json")) as f:
         sgs = json.load(f)
-    src, dst, batch, off = [], [], [], 0
-    for gi, key in enumerate(sgs):
+    out = []
+    for key in sgs:
         objs = sgs[key]["objects"]
         ids = sorted(objs.keys())
         idx = {o: i for i, o in enumerate(ids)}
         present = {(idx[o], idx[r["object"]]) for o in ids for r in objs[o]["relations"]}
+        src, dst, sym = [], [], []
         for o in ids:
             i = idx[o]
-            src.append(off + i); dst.append(off + i)
+            src.append(i); dst.append(i)
             for r in objs[o]["relations"]:
                 j = idx[r["object"]]
-                src.append(off + i); dst.append(off + j)
+                src.append(i); dst.append(j)
                 if (j, i) not in present:
-                    src.append(off + j); dst.append(off + i)
-        batch += [gi] * len(ids)
-        off += len(ids)
-    return torch.tensor([src, dst], dtype=torch.long), torch.tensor(batch, dtype=torch.long)
+                    src.append(j); dst.append(i)
+                    sym.append(len(src) - 1)
+        out.append((torch.tensor([src, dst], dtype=torch.long), len(ids), torch.tensor(sym, dtype=torch.long)))
+    return out
+
+
+def debug_topology():
+    """(edge_index[2,E], batch[N]) of the 4 debug scene graphs batched as disjoint components."""
+    eis, batch, off = [], [], 0
+    for gi, (ei, n, _) in enumerate(debug_graph_list()):
+        eis.append(ei + off); batch += [gi] * n; off += n
+    return torch.cat(eis, dim=1), torch.tensor(batch, dtype=torch.long)
+
+
+def debug_token_batch(seed):
+    """The debug graphs as the reference's collate would deliver them (torch_geometric Batch via the
+    shim: node offsets on edge_index only, added_sym_edge left graph-local), with seeded random
+    token ids in place of the GloVe vocabulary lookups (pad id 1 in unused attribute slots)."""
+    import torch_geometric
+    g = torch.Generator().manual_seed(seed)
+    data = []
+    for ei, n, sym in debug_graph_list():
+        x = torch.randint(4, rr.SG_VOCAB_SIZE, (n, 12), generator=g)
+        x[torch.rand(n, 12, generator=g) < 0.6] = 1
+        x[:, 0] = torch.randint(4, rr.SG_VOCAB_SIZE, (n,), generator=g)
+        ea = torch.randint(4, rr.SG_VOCAB_SIZE, (ei.size(1), 1), generator=g)
+        d = torch_geometric.data.Data(x=x, edge_index=ei, edge_attr=ea)
+        d.added_sym_edge = sym
+        data.append(d)
+    return torch_geometric.data.Batch.from_data_list(data)
 
 
 def _randomise_bn(module, gen):
@@ -140,6 +167,36 @@ def main():
             torch.save(dict(meta=meta, config=dict(in_channels=32, out_channels=32, ins_dim=16, dropout=0.1),
                             state=m.state_dict(), x=x, edge_index=ei, edge_attr=ea, instr_vectors=ins,
                             batch=batch, out=out, conv_out=conv_out), os.path.join(OUT, "%s_seq_small.pt" % name))
+        # 7. the whole PipelineModel of every variant (67M parameters: weights reproduced from a seed by
+        #    oracle/golden_utils.deterministic_fill, identified by a hash)
+        from .golden_utils import deterministic_fill, state_hash
+        batch_obj = debug_token_batch(seed=606)
+        gen = torch.Generator().manual_seed(607)
+        nb = 4
+        questions = torch.randint(4, rr.TEXT_VOCAB_SIZE, (9, nb), generator=gen)
+        programs = torch.randint(4, rr.TEXT_VOCAB_SIZE, (6, nb * 5), generator=gen)
+        programs[0] = 2
+        for variant in ("gat", "gcn", "gine", "lcgn"):
+            mod = rr.load("pipeline_model_" + variant)
+            torch.manual_seed(0)
+            model = deterministic_fill(mod.PipelineModel().eval(), seed=700)
+            fx = dict(meta=meta, variant=variant, fill_seed=700, state_sha256=state_hash(model.state_dict()),
+                      questions=questions, programs_input=programs, x=batch_obj.x, edge_index=batch_obj.edge_index,
+                      edge_attr=batch_obj.edge_attr, added_sym_edge=batch_obj.added_sym_edge, batch=batch_obj.batch)
+            if variant == "lcgn":
+                torch.manual_seed(708); fx["x_ctx"] = torch.randn(batch_obj.batch.numel(), 512)
+                torch.manual_seed(708)
+            prog_out, logits = model(questions, batch_obj, programs, None, SAMPLE_FLAG=False)
+            fx["short_answer_logits"] = logits
+            fx["programs_output_slice"] = prog_out[:, :, :48].clone()
+            fx["programs_argmax"] = prog_out.argmax(-1)
+            x_enc, e_enc, _ = model.scene_graph_encoder(batch_obj)
+            fx["x_encoded"], fx["edge_attr_encoded"] = x_enc, e_enc
+            if variant == "gat":
+                torch.manual_seed(1)
+                sampled, _ = model.program_decoder.sample(model.question_encoder(questions), None)
+                fx["sampled_programs"] = sampled
+            torch.save(fx, os.path.join(OUT, "pipeline_%s.pt" % variant))
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

@@ -178,3 +178,13 @@ def test_live_reference_seeded_init_is_identical():
     torch.manual_seed(5); a = ref.gat_seq(16, 16, 16, 8, 2).state_dict()
     torch.manual_seed(5); b = orc.gat_seq(16, 16, 16, 8, 2).state_dict()
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_deterministic_fill_is_reproducible_and_aliases_hold():
+    from graphvqa_b200.gat_skip import gat_seq
+    from oracle.golden_utils import deterministic_fill, state_hash
+    a = deterministic_fill(gat_seq(8, 8, 8, 4, 2), 5)
+    b = deterministic_fill(gat_seq(8, 8, 8, 4, 2), 5)
+    assert state_hash(a.state_dict()) == state_hash(b.state_dict())
+    assert a.convs[0].lin_l.weight is a.convs[0].lin_r.weight
+    assert float(a.bns[0].running_var.min()) >= 0.5
