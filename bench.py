@@ -179,6 +179,7 @@ def run_engine(args, rank, local_rank, world):
     randomise_bn(model, 7)
     model = model.to(dev)
     model.kernel_variant = args.variant
+    model.projection = args.projection
 
     # R input sets (> L2 in total: 4 x ~50 MB) rotated step to step so no step finds its inputs in L2
     R = 4
@@ -262,18 +263,25 @@ def run_engine(args, rank, local_rank, world):
         achieved = algo / (hop_us * 1e-6) / 1e9
 
         # ---------------- end to end: pinned host buffers -> H2D -> hot path -> D2H --------------
-        out_host = torch.empty(n, c).pin_memory()
-        def e2e_step(i):
-            s = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % R].items()}
-            out_host.copy_(step(s), non_blocking=True)
-        for i in range(3):
-            e2e_step(i)
+        # through the public host-buffer API (graphvqa_b200.host_api.GatSeqHostRunner): copies of
+        # neighbouring batches overlap the kernels of the current one (3 streams, 2 device slots).
+        from graphvqa_b200.host_api import GatSeqHostRunner
+        runner = GatSeqHostRunner(model, dev, depth=2, use_cuda_graph=not args.no_graph,
+                                  max_nodes_per_graph=max_nodes, max_in_edges_per_graph=max_edges)
+        for i in range(6):
+            runner.submit(pinned[i % R])
+        runner.drain()
         torch.cuda.synchronize(); barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(runner.s_h2d)
+        checksum = 0.0
         for i in range(args.steps):
-            e2e_step(i)
-        e1.record(); torch.cuda.synchronize()
+            t_id = runner.submit(pinned[i % R])
+            if i >= 2:
+                checksum += float(runner.result(t_id - 2)[0, 0])    # consume results as they arrive
+        runner.drain()
+        e1.record(runner.s_d2h)
+        torch.cuda.synchronize()
         t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -316,7 +324,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged")
+    ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged, 3 block")
+    ap.add_argument("--projection", default="3xtf32", choices=["3xtf32", "cublas"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

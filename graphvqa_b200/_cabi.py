@@ -46,6 +46,9 @@ SIGNATURES = {
     "gvqa_gat_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatHopArgs), _c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
+    "gvqa_split_tf32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "gvqa_proj_gemm_3xtf32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
+                                             _c_i32, _c_vp]),
     "gvqa_gine_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                _c_i32, _c_i32, _c_f32, _c_vp]),
     "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
@@ -244,4 +247,31 @@ def lcgn_hop(xl, xr, xv, proj_cmd, cal_cmd, bias, csr, negative_slope, out=None)
         check(lib().gvqa_lcgn_hop_f32(ptr(xl), ptr(xr), ptr(xv), ld, ptr(proj_cmd), ptr(cal_cmd), ptr(bias),
                                       ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["node_graph"]), ptr(out),
                                       n, c, negative_slope, stream_handle(xl.device)), "gvqa_lcgn_hop_f32")
+    return out
+
+
+def split_tf32(w):
+    """(hi, lo) with hi = tf32(w), lo = tf32(w - hi): the weight half of the 3xTF32 GEMM."""
+    require_cuda(w)
+    w = w.contiguous().float()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        check(lib().gvqa_split_tf32(ptr(w), ptr(hi), ptr(lo), w.numel(), stream_handle(w.device)), "gvqa_split_tf32")
+    return hi, lo
+
+
+def proj_gemm_3xtf32(a, b_hi, b_lo, out=None):
+    """out[M,N] = a[M,K] @ b[N,K]^T with fp32-level accuracy on the tcgen05 tensor cores."""
+    require_cuda(a, b_hi, b_lo)
+    require_f32c(b_hi=b_hi, b_lo=b_lo, out=out)
+    if a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
+        raise ValueError("proj_gemm_3xtf32: a must be float32 [M,K] with unit column stride")
+    m, k = a.shape
+    n = b_hi.size(0)
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().gvqa_proj_gemm_3xtf32(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
+                                          ptr(out), out.stride(0), m, n, k, stream_handle(a.device)),
+              "gvqa_proj_gemm_3xtf32")
     return out

@@ -37,7 +37,10 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ edge_index, int64_t
 }
 
 // Single-CTA exclusive scan deg[N] -> rowptr[N+1]; also resets deg to 0 for reuse as fill cursor
-// and records the max in-degree.
+// and records the max in-degree.  Each thread owns kScanItems consecutive entries (serial scan in
+// registers) so N <= 1024*kScanItems needs a single block-wide scan step.
+constexpr int kScanItems = 16;
+
 __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* __restrict__ deg, int64_t N,
                                                         int32_t* __restrict__ rowptr,
                                                         int32_t* __restrict__ stats) {
@@ -47,12 +50,18 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* __restrict__ de
   if (threadIdx.x == 0) carry_s = 0;
   int32_t local_max = 0;
   __syncthreads();
-  for (int64_t base = 0; base < N; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int32_t v = i < N ? deg[i] : 0;
-    if (i < N) deg[i] = 0;
-    local_max = max(local_max, v);
-    int32_t incl = v;
+  for (int64_t base = 0; base < N; base += 1024 * kScanItems) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      v[j] = (i0 + j < N) ? deg[i0 + j] : 0;
+      if (i0 + j < N) deg[i0 + j] = 0;
+      local_max = max(local_max, v[j]);
+      tsum += v[j];
+    }
+    int32_t incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t u = __shfl_up_sync(kFull, incl, o);
@@ -72,17 +81,19 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* __restrict__ de
     __syncthreads();
     const int32_t carry = carry_s;
     const int32_t warp_off = wid > 0 ? warp_tot[wid - 1] : 0;
-    if (i < N) rowptr[i] = carry + warp_off + incl - v;
+    int32_t run = carry + warp_off + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (i0 + j < N) rowptr[i0 + j] = run;
+      run += v[j];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_off + incl;
+    if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
   if (threadIdx.x == 0) rowptr[N] = carry_s;
-  local_max = max(local_max, __shfl_xor_sync(kFull, local_max, 16));
-  local_max = max(local_max, __shfl_xor_sync(kFull, local_max, 8));
-  local_max = max(local_max, __shfl_xor_sync(kFull, local_max, 4));
-  local_max = max(local_max, __shfl_xor_sync(kFull, local_max, 2));
-  local_max = max(local_max, __shfl_xor_sync(kFull, local_max, 1));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(kFull, local_max, o));
   if (lane == 0) atomicMax(&stats[2], local_max);
 }
 

@@ -7,7 +7,7 @@ trained with the reference loads unchanged, but executes the message passing thr
 
   per batch   gvqa_build_csr (cached on the SceneGraphBatch), edge-logit skinny projection for all
               hops at once (edge_attr is hop-invariant), per-graph instruction terms (2 small bmm);
-  per hop     node projection  h @ W_h^T  (cuBLAS fp32, TF32 off),
+  per hop     node projection  h @ W_h^T  (gvqa_proj_gemm_3xtf32: tcgen05 split-TF32, fp32-level accuracy),
               gvqa_skinny_matmul_f32 for the collapsed a_l/a_r node logits,
               gvqa_gat_hop_f32: gather + logits + segment softmax + aggregate + head mean + bias +
               skip + BatchNorm(eval) + ReLU in ONE kernel.
@@ -166,6 +166,9 @@ class gat_seq(nn.Module):
         self.dropout = dropout
         self.in_channels, self.edge_attr_dim, self.ins_dim = in_channels, edge_attr_dim, ins_dim
         self.kernel_variant = _cabi.VARIANT_AUTO
+        # node projection h @ W_h^T: "3xtf32" = hand-written tcgen05 split-TF32 GEMM (fp32-level accuracy,
+        # ~2.5x cuBLAS fp32 SIMT), "cublas" = torch.mm with TF32 off
+        self.projection = "3xtf32"
         self.hop_events = None      # set to a list to collect (start, end) CUDA events per fused-hop launch
         self._packed = None
 
@@ -199,7 +202,8 @@ class gat_seq(nn.Module):
                 b = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
                 scale.append((g * inv).float().contiguous())
                 shift.append((b - bn.running_mean.detach().double() * g * inv).float().contiguous())
-        self._packed = dict(key=key, w_h=w_h, w_ins=torch.stack(w_ins), v_node=v_node,
+        w_split = [_cabi.split_tf32(w) for w in w_h] if w_h[0].is_cuda else None
+        self._packed = dict(key=key, w_h=w_h, w_split=w_split, w_ins=torch.stack(w_ins), v_node=v_node,
                             v_graph=torch.stack(v_graph), v_edge=torch.cat(v_edge).contiguous(),
                             scale=scale, shift=shift)
         return self._packed
@@ -234,8 +238,11 @@ class gat_seq(nn.Module):
         x_l = torch.empty(n, heads * c, dtype=torch.float32, device=x.device)
         a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
         for i in range(num_hops):
-            with _strict_fp32_matmul():
-                torch.mm(h, pk["w_h"][i].t(), out=x_l)
+            if self.projection == "3xtf32":
+                _cabi.proj_gemm_3xtf32(h, pk["w_split"][i][0], pk["w_split"][i][1], out=x_l)
+            else:
+                with _strict_fp32_matmul():
+                    torch.mm(h, pk["w_h"][i].t(), out=x_l)
             _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
             last = i == num_hops - 1
             h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)

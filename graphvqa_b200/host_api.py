@@ -1,0 +1,102 @@
+"""Host-buffer entry point of the hot path: ``gat_seq`` fed from (pinned) host memory.
+
+``GatSeqHostRunner`` is the call a data-loader-side user makes: it takes the five host tensors of one
+batch (``x, edge_index, edge_attr, instr_vectors, batch`` -- the arguments of the reference's
+``gat_seq.forward``, gat_skip.py:249), moves them to the GPU, builds the CSR, runs the hop stack and
+returns the node states in pinned host memory.  Consecutive batches are software-pipelined over three
+CUDA streams and ``depth`` device slots: the H2D copy of batch i+1 and the D2H copy of batch i-1
+overlap the kernels of batch i (PCIe is full duplex).  With ``use_cuda_graph`` the per-slot compute
+(CSR build + pre-pass + hops) is captured once per input shape and replayed.
+"""
+import torch
+
+from .graph_batch import GraphCSR
+
+_KEYS = ("x", "edge_index", "edge_attr", "instr_vectors", "batch")
+
+
+class _Slot:
+    def __init__(self):
+        self.dev = None            # static device input tensors
+        self.out_dev = None        # device output (static when graph-captured)
+        self.out_host = None       # pinned host output
+        self.h2d_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
+        self.d2h_done = torch.cuda.Event()
+        self.graph = None
+        self.shapes = None
+        self.busy = False
+
+
+class GatSeqHostRunner:
+    def __init__(self, model, device, depth=2, use_cuda_graph=True, max_nodes_per_graph=0,
+                 max_in_edges_per_graph=0):
+        self.model, self.device, self.depth = model, torch.device(device), depth
+        self.use_cuda_graph = use_cuda_graph
+        self.hints = dict(max_nodes_per_graph=max_nodes_per_graph, max_in_edges_per_graph=max_in_edges_per_graph)
+        self.s_h2d, self.s_compute, self.s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.slots = [_Slot() for _ in range(depth)]
+        self.count = 0
+
+    def _forward(self, d):
+        csr = GraphCSR.build(d["edge_index"], d["batch"], d["instr_vectors"].size(1), **self.hints)
+        return self.model(d["x"], d["edge_index"], d["edge_attr"], d["instr_vectors"], d["batch"], csr=csr)
+
+    @torch.no_grad()
+    def submit(self, host):
+        """Enqueue one batch (dict or 5-tuple of CPU tensors, ideally pinned).  Returns a ticket."""
+        if not isinstance(host, dict):
+            host = dict(zip(_KEYS, host))
+        slot = self.slots[self.count % self.depth]
+        if slot.busy:
+            slot.d2h_done.synchronize()     # the slot's previous result must have left the device
+        shapes = tuple((tuple(host[k].shape), host[k].dtype) for k in _KEYS)
+        if slot.shapes != shapes:
+            slot.dev = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in _KEYS}
+            slot.shapes, slot.graph, slot.out_dev, slot.out_host = shapes, None, None, None
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(slot.compute_done)          # previous compute on this slot has read its inputs
+            for k in _KEYS:
+                slot.dev[k].copy_(host[k], non_blocking=True)
+            slot.h2d_done.record(self.s_h2d)
+        with torch.cuda.stream(self.s_compute):
+            self.s_compute.wait_event(slot.h2d_done)
+            self.s_compute.wait_event(slot.d2h_done)          # static output buffer is free again
+            if self.use_cuda_graph and slot.graph is None and slot.out_dev is not None:
+                # second use of this shape: capture (the first use ran eagerly and warmed everything up)
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(self.device)
+                with torch.cuda.graph(g, stream=self.s_compute):
+                    slot.out_dev = self._forward(slot.dev)
+                slot.graph = g
+            if slot.graph is not None:
+                slot.graph.replay()
+            else:
+                slot.out_dev = self._forward(slot.dev)
+            slot.compute_done.record(self.s_compute)
+        if slot.out_host is None or slot.out_host.shape != slot.out_dev.shape:
+            slot.out_host = torch.empty(slot.out_dev.shape, dtype=slot.out_dev.dtype).pin_memory()
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(slot.compute_done)
+            slot.out_host.copy_(slot.out_dev, non_blocking=True)
+            if slot.graph is None:
+                slot.out_dev.record_stream(self.s_d2h)
+            slot.d2h_done.record(self.s_d2h)
+        slot.busy = True
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket):
+        """Pinned host tensor with the node states of batch ``ticket`` (valid until the slot is reused,
+        i.e. until ``depth`` more batches have been submitted)."""
+        slot = self.slots[ticket % self.depth]
+        slot.d2h_done.synchronize()
+        return slot.out_host
+
+    def drain(self):
+        for s in self.slots:
+            if s.busy:
+                s.d2h_done.synchronize()
+
+    def __call__(self, *host):
+        return self.result(self.submit(host if len(host) != 1 else host[0]))

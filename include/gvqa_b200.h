@@ -153,6 +153,18 @@ GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, 
                              int32_t max_nodes_per_graph, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-accurate projection GEMM on the tcgen05 tensor cores ("3xTF32"):
+ *   C[M,N] = A[M,K] @ B[N,K]^T      (x_l = lin_l(x_cat), gat_skip.py:133; a cuBLAS SGEMM there)
+ * Every operand is split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)); A_lo*B_hi + A_hi*B_lo +
+ * A_hi*B_hi is accumulated in fp32 in tensor memory.  B must be pre-split with gvqa_split_tf32
+ * (weights: once per checkpoint); A is split on the fly.  k, lda, ldb, ldc multiples of 4.
+ */
+GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream);
+GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const float* b_hi, const float* b_lo,
+                                   int64_t ldb, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
+                                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * GINE message passing: the propagate + self term of torch_geometric's GINEConv as called by
  * gine_seq.forward (baseline_and_test_models/pipeline_model_gine.py:652-665) on the concatenated
  * inputs x_cat = [h | ins[batch]], edge_cat = [edge_attr | ins[batch[src]]]:
