@@ -46,6 +46,7 @@ SIGNATURES = {
     "gvqa_gat_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatHopArgs), _c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
+    "gvqa_debug_set_gemm_trace": (None, [_c_vp]),
     "gvqa_split_tf32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_proj_gemm_3xtf32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                              _c_i32, _c_vp]),

@@ -7,22 +7,30 @@
 // x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and three tcgen05.mma.kind::tf32 products are
 // accumulated in fp32 in tensor memory:  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term
 // is ~2^-22 relative) -- "3xTF32".  B (the weights) is split once at prepack time; A (the node
-// state, new every hop) is split on the fly in shared memory by the converter warps.
+// state, new every hop) is split on the fly by the converter warps.
 //
-// The tensor core adds into its accumulator with truncation, which biases long chains (measured:
-// 8x the error of an fp32 SGEMM at K=512 with one accumulator).  So the tile keeps FOUR
-// accumulators in TMEM: the hi*hi products of three K-thirds (chains 3x shorter) and one for all
-// the small lo-terms (their truncation is 2^-11 smaller); the epilogue adds the four in fp32 RN.
+// Two measured facts shape the kernel (profiles/microbench/trace_gemm.py, ncu):
+//  * the tensor core adds into its accumulator with truncation, which biases long chains (8x the
+//    error of an fp32 SGEMM at K=512 with one accumulator).  The tile therefore keeps THREE
+//    accumulators in TMEM: hi*hi of the two K-halves and one for all the small lo-terms (their
+//    truncation is 2^-11 smaller); the epilogue adds them in fp32 RN.
+//  * with both operands in shared memory a tf32 M128 x N128 x K8 MMA needs 8 KB of smem reads per
+//    64 cycles = the whole 128 B/clk of the SM, so converter and TMA traffic stalled the tensor
+//    pipe (40 % active).  A is therefore fed from TENSOR MEMORY (tcgen05.mma "TS" form): the
+//    converters write A_hi / A_lo with tcgen05.st into a 2-stage TMEM ring and only B is read
+//    from shared memory.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: per k-block one cp.async.bulk.tensor (UTMALDG) each for the raw A
-//               tile [128 x 32], B_hi and B_lo tiles [128 x 32], 128B-swizzled, 3-stage ring
-//   warps 2-5   converters: split the A tile in place (hi) + side buffer (lo), fence.proxy.async,
-//               arrive; after the last k-block they become the epilogue: tcgen05.ld of their 32
-//               TMEM lanes -> registers -> 128-bit global stores
-//   warp 1      one elected lane issues 12 MMAs (M128 x N128 x K8) per k-block and commits the
-//               stage back to the producer (tcgen05.commit -> mbarrier)
-// Accumulators: 128 lanes x 4 x 128 columns of TMEM (fp32).
+//               tile and the B_hi / B_lo tiles, [128 x 32] floats, 128B-swizzled, 4-stage ring
+//   warps 2-5   converters: thread = one row of the A tile: 8 swizzled 128-bit smem loads, split,
+//               2 x tcgen05.st (hi, lo) into the TMEM A ring, arrive
+//   warp 1      one elected lane issues 12 MMAs (M128 x N128 x K8, A from TMEM) per k-block and
+//               commits the smem stage and the TMEM A stage back (tcgen05.commit -> mbarrier)
+//   warps 6-9   epilogue: tcgen05.ld of their 32 TMEM lanes, fp32 sum of the three accumulators,
+//               128-bit global stores
+// TMEM map (512 columns): [0,128) hi*hi first K-half, [128,256) second K-half, [256,384) lo terms,
+// [384,512) A ring: 2 stages x (32 columns hi | 32 columns lo).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,14 +38,18 @@
 namespace gvqa {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile: rows of A, rows of B, k (floats; 128 bytes)
-constexpr int kStages = 3;
-constexpr int kBigChunks = 3;                       // hi*hi accumulators over K-thirds (+1 for the lo terms)
-constexpr int kGemmThreads = 192;
+constexpr int kStages = 4;                          // shared-memory ring
+constexpr int kAStages = 2;                         // tensor-memory ring of split A tiles
+constexpr int kBigChunks = 2;                       // hi*hi accumulators over K-halves (+1 for the lo terms)
+constexpr int kGemmThreads = 320;                   // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-9 epilogue
 constexpr int kConvThreads = 128;
+constexpr int kEpiThreads = 128;
 constexpr uint32_t kABytes = kBM * kBK * 4;         // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 4;         // 16 KB
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A(hi) | A_lo | B_hi | B_lo = 64 KB
-constexpr uint32_t kTmemCols = (kBigChunks + 1) * kBN;        // 512: all of tensor memory
+constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;       // A raw | B_hi | B_lo = 48 KB
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemSmall = kBigChunks * kBN;             // 256
+constexpr uint32_t kTmemA = (kBigChunks + 1) * kBN;           // 384
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -52,11 +64,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// Round-to-nearest (ties away) fp32 -> tf32 kept in an fp32 container: add half an ulp of the
+// 10-bit mantissa, clear the 13 low bits.  Same result as cvt.rna.tf32.f32 for finite values, but
+// on the full-rate integer pipe (the converter warps do this for every element of A).
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -65,15 +76,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -82,18 +94,47 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+#define GVQA_TMEM_ST16(taddr, r, o)                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]),          \
+               "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7]), "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]),        \
+               "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15])                    \
+               : "memory")
+
+#define GVQA_TMEM_LD32(r, taddr)                                                                             \
+  asm volatile(                                                                                              \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                              \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                              \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"              \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),           \
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),           \
+        "=r"(r[30]), "=r"(r[31])                                                                             \
+      : "r"(taddr))
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                         const __grid_constant__ CUtensorMap map_blo, float* __restrict__ c, int64_t ldc, int M,
-                        int N, int K) {
+                        int N, int K, long long* __restrict__ trace) {
+  // trace (debug, may be null): CTA 0 records clock64() per k-block and role: [it][0..4] = producer issue,
+  // converter start, converter done, mma start, mma committed; [1024+tile][0..1] = epilogue start / end
+#define GVQA_TRACE(slot, col) do { if (trace && blockIdx.x == 0 && (slot) < 1100) trace[(slot) * 8 + (col)] = clock64(); } while (0)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
-  uint64_t* tma_full = bars;                    // [kStages]
-  uint64_t* conv_done = bars + kStages;         // [kStages]
-  uint64_t* empty = bars + 2 * kStages;         // [kStages]
-  uint64_t* acc_full = bars + 3 * kStages;      // [1]
-  uint64_t* acc_empty = acc_full + 1;           // [1]
+  uint64_t* tma_full = bars;                        // [kStages]   TMA bytes landed
+  uint64_t* smem_empty = bars + kStages;            // [kStages]   MMAs that read the stage are done
+  uint64_t* a_ready = bars + 2 * kStages;           // [kAStages]  converters filled the TMEM A stage
+  uint64_t* a_empty = a_ready + kAStages;           // [kAStages]  MMAs that read the TMEM A stage are done
+  uint64_t* acc_full = a_empty + kAStages;          // [1]
+  uint64_t* acc_empty = acc_full + 1;               // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,11 +145,14 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&tma_full[s], 1);
-      mbar_init(&conv_done[s], kConvThreads);
-      mbar_init(&empty[s], 1);
+      mbar_init(&smem_empty[s], 1);
+    }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&a_ready[s], kConvThreads);
+      mbar_init(&a_empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kConvThreads);
+    mbar_init(acc_empty, kEpiThreads);
     mbar_fence_init();
   }
   if (warp == 1) {  // one warp owns the TMEM allocation
@@ -130,12 +174,13 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+          mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
+          GVQA_TRACE(it, 0);
           unsigned char* st = smem + (size_t)s * kStageBytes;
           mbar_expect_tx(&tma_full[s], kABytes + 2 * kBBytes);
           tma_load_2d(st, &map_a, &tma_full[s], kb * kBK, m0);
-          tma_load_2d(st + 2 * kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
-          tma_load_2d(st + 2 * kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
+          tma_load_2d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
+          tma_load_2d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
         }
       }
     }
@@ -150,85 +195,90 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&conv_done[s], (it / kStages) & 1);
+          const int s = it % kStages, ts = it % kAStages;
+          mbar_wait(&a_ready[ts], (it / kAStages) & 1);    // implies tma_full[s]: the converters waited on it
+          GVQA_TRACE(it, 3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(smem + (size_t)s * kStageBytes);
-          const uint32_t a_lo = a_hi + kABytes, b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
-          // hi*hi goes to the accumulator of this K-third, the lo terms to the last accumulator
+          const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes + kABytes), b_lo = b_hi + kBBytes;
+          const uint32_t a_hi = tmem_base + kTmemA + (uint32_t)(ts * 2 * kBK), a_lo = a_hi + kBK;
+          // hi*hi goes to the accumulator of this K-half, the lo terms to the last accumulator
           const int chunk = (kb * kBigChunks) / kblocks;
           const bool chunk_first = kb == 0 || ((kb - 1) * kBigChunks) / kblocks != chunk;
-          const uint32_t d_big = tmem_base + (uint32_t)(chunk * kBN), d_small = tmem_base + (uint32_t)(kBigChunks * kBN);
+          const uint32_t d_big = tmem_base + (uint32_t)(chunk * kBN), d_small = tmem_base + kTmemSmall;
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {            // K = 8 per MMA = 32 bytes inside the swizzle atom
-            const uint32_t off = k * 32;
-            umma_tf32(d_small, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
-            umma_tf32(d_small, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-            umma_tf32(d_big, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, !(chunk_first && k == 0));
+          for (int k = 0; k < kBK / 8; ++k) {            // K = 8 per MMA: 8 TMEM columns of A, 32 bytes of B
+            umma_tf32_ts(d_small, a_lo + 8 * k, umma_desc(b_hi + 32 * k), idesc, (kb | k) != 0);
+            umma_tf32_ts(d_small, a_hi + 8 * k, umma_desc(b_lo + 32 * k), idesc, 1);
+            umma_tf32_ts(d_big, a_hi + 8 * k, umma_desc(b_hi + 32 * k), idesc, !(chunk_first && k == 0));
           }
-          umma_commit(&empty[s]);                          // stage reusable once these MMAs have read it
+          umma_commit(&smem_empty[s]);                     // smem stage reusable once these MMAs are done
+          umma_commit(&a_empty[ts]);                       // and so is the TMEM A stage
+          GVQA_TRACE(it, 4);
         }
-        umma_commit(acc_full);                             // accumulator complete
+        umma_commit(acc_full);                             // accumulators complete
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converters (warps 2..5): thread = one row of the A tile ===============
+    const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;                     // row of the tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages, ts = it % kAStages;
+        mbar_wait(&tma_full[s], (it / kStages) & 1);
+        mbar_wait(&a_empty[ts], ((it / kAStages) & 1) ^ 1);
+        if (threadIdx.x == 64) GVQA_TRACE(it, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t row_addr = smem_u32(smem + (size_t)s * kStageBytes) + (uint32_t)r * 128u;
+        uint32_t hi[kBK], lo[kBK];
+#pragma unroll
+        for (int cidx = 0; cidx < kBK / 4; ++cidx) {       // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
+          const float4 v = lds128(row_addr + (uint32_t)((cidx ^ (r & 7)) * 16));
+          hi[4 * cidx + 0] = to_tf32(v.x); hi[4 * cidx + 1] = to_tf32(v.y);
+          hi[4 * cidx + 2] = to_tf32(v.z); hi[4 * cidx + 3] = to_tf32(v.w);
+          lo[4 * cidx + 0] = to_tf32(v.x - __uint_as_float(hi[4 * cidx + 0]));
+          lo[4 * cidx + 1] = to_tf32(v.y - __uint_as_float(hi[4 * cidx + 1]));
+          lo[4 * cidx + 2] = to_tf32(v.z - __uint_as_float(hi[4 * cidx + 2]));
+          lo[4 * cidx + 3] = to_tf32(v.w - __uint_as_float(hi[4 * cidx + 3]));
+        }
+        const uint32_t ta = tmem_base + lane_base + kTmemA + (uint32_t)(ts * 2 * kBK);
+        GVQA_TMEM_ST16(ta, hi, 0);
+        GVQA_TMEM_ST16(ta + 16, hi, 16);
+        GVQA_TMEM_ST16(ta + kBK, lo, 0);
+        GVQA_TMEM_ST16(ta + kBK + 16, lo, 16);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&a_ready[ts]);
+        if (threadIdx.x == 64) GVQA_TRACE(it, 2);
       }
     }
   } else {
-    // ===================== converters, then epilogue (warps 2..5) =====================
-    const int t = threadIdx.x - 64;                        // 0..127
+    // ===================== epilogue (warps 6..9): TMEM -> registers -> global ====================
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
-    uint32_t it = 0, tile_it = 0;
+    uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
       const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % kStages;
-        mbar_wait(&tma_full[s], (it / kStages) & 1);
-        float4* a = reinterpret_cast<float4*>(smem + (size_t)s * kStageBytes);
-        float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * kStageBytes + kABytes);
-#pragma unroll
-        for (int j = 0; j < (int)(kABytes / 16) / kConvThreads; ++j) {
-          const int idx = t + j * kConvThreads;
-          const float4 v = a[idx];
-          uint4 h, l;
-          h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-          l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-          l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-          reinterpret_cast<uint4*>(a)[idx] = h;
-          reinterpret_cast<uint4*>(alo)[idx] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
-        mbar_arrive(&conv_done[s]);
-      }
-      // ---- epilogue: TMEM -> registers -> global ----
       mbar_wait(acc_full, tile_it & 1);
+      if (threadIdx.x == 192) GVQA_TRACE(1024 + tile_it, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + quarter * 32 + lane;
       float* crow = c + (int64_t)row * ldc + n0;
-      // accumulators that received nothing (fewer k-blocks than K-thirds) are skipped
-      int used[kBigChunks];
-#pragma unroll
-      for (int q = 0; q < kBigChunks; ++q) {
-        used[q] = 0;
-        for (int kb = 0; kb < kblocks; ++kb) used[q] |= ((kb * kBigChunks) / kblocks) == q;
-      }
+      const bool two_chunks = kblocks >= kBigChunks;       // with a single k-block the second K-half is empty
 #pragma unroll 1
       for (int cc = 0; cc < kBN / 32; ++cc) {
-        float acc[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32);
+        uint32_t rs[32], r0[32], r1[32];
+        GVQA_TMEM_LD32(rs, taddr + kTmemSmall);
+        GVQA_TMEM_LD32(r0, taddr);
+        if (two_chunks) GVQA_TMEM_LD32(r1, taddr + kBN);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float acc[32];
 #pragma unroll
-        for (int q = kBigChunks; q >= 0; --q) {            // small terms first, then the K-thirds
-          if (q < kBigChunks && !used[q]) continue;
-          uint32_t r[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr + (uint32_t)(q * kBN)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = (q == kBigChunks) ? __uint_as_float(r[e]) : acc[e] + __uint_as_float(r[e]);
+        for (int e = 0; e < 32; ++e) {
+          acc[e] = __uint_as_float(rs[e]) + __uint_as_float(r0[e]);
+          if (two_chunks) acc[e] += __uint_as_float(r1[e]);
         }
         if (row < M) {
           const int col0 = n0 + cc * 32;
@@ -246,6 +296,7 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(acc_empty);
+      if (threadIdx.x == 192) GVQA_TRACE(1024 + tile_it, 1);
     }
   }
 
@@ -300,6 +351,9 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
 
 using namespace gvqa;
 
+static long long* g_gemm_trace = nullptr;   // debug only: set through gvqa_debug_set_gemm_trace
+extern "C" GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; }
+
 extern "C" GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream_) {
   if (count < 0) return GVQA_ERR_BAD_SHAPE;
   if (count == 0) return GVQA_OK;
@@ -330,7 +384,7 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const
   const int tiles = (int)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   proj_gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream_)>>>(
-      map_a, map_bhi, map_blo, c, ldc, (int)m, n, k);
+      map_a, map_bhi, map_blo, c, ldc, (int)m, n, k, g_gemm_trace);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }

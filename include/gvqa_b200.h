@@ -159,6 +159,8 @@ GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, 
  * A_hi*B_hi is accumulated in fp32 in tensor memory.  B must be pre-split with gvqa_split_tf32
  * (weights: once per checkpoint); A is split on the fly.  k, lda, ldb, ldc multiples of 4.
  */
+/* debug: device buffer of 1100*8 int64 that CTA 0 fills with clock64() pipeline timestamps; NULL = off */
+GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer);
 GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream);
 GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const float* b_hi, const float* b_lo,
                                    int64_t ldb, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
