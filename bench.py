@@ -180,6 +180,9 @@ def run_engine(args, rank, local_rank, world):
     model = model.to(dev)
     model.kernel_variant = args.variant
     model.projection = args.projection
+    if args.l2_persist:
+        granted = _cabi.l2_persist_limit(args.l2_persist << 20, dev)
+        model.l2_persist = granted > 0
 
     # R input sets (> L2 in total: 4 x ~50 MB) rotated step to step so no step finds its inputs in L2
     R = 4
@@ -326,6 +329,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged, 3 block")
     ap.add_argument("--projection", default="3xtf32", choices=["3xtf32", "cublas"])
+    ap.add_argument("--l2-persist", type=int, default=0, help="MiB of L2 set aside to keep x_l resident (0 = off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -24,7 +24,8 @@ _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c
 class GatHopArgs(ctypes.Structure):
     """Mirror of ``struct gvqa_gat_hop_args`` (field order and types must match the header)."""
     _fields_ = [
-        ("x_l", _c_vp), ("ldx", _c_i64), ("graph_bias", _c_vp), ("a_node", _c_vp), ("a_graph", _c_vp),
+        ("x_l", _c_vp), ("ldx", _c_i64), ("graph_bias", _c_vp), ("a_node", _c_vp), ("ld_a_node", _c_i64),
+        ("a_graph", _c_vp),
         ("a_edge", _c_vp), ("lde", _c_i64), ("rowptr", _c_vp), ("col_src", _c_vp), ("perm", _c_vp),
         ("graph_ptr", _c_vp), ("node_graph", _c_vp), ("h_prev", _c_vp), ("bias", _c_vp),
         ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("alpha_out", _c_vp),
@@ -38,6 +39,8 @@ class GatHopArgs(ctypes.Structure):
 SIGNATURES = {
     "gvqa_abi_version": (ctypes.c_int, []),
     "gvqa_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "gvqa_device_set_l2_persist_limit": (ctypes.c_int, [_c_sz]),
+    "gvqa_stream_set_l2_window": (ctypes.c_int, [_c_vp, _c_sz, _c_f32, _c_vp]),
     "gvqa_csr_workspace_bytes": (_c_sz, [_c_i64, _c_i64]),
     "gvqa_build_csr": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
                                       _c_vp, _c_vp, _c_vp, _c_sz, _c_vp]),
@@ -55,6 +58,9 @@ SIGNATURES = {
     "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_gcn_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                               _c_i32, _c_vp]),
+    "gvqa_gather_add_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_segment_mean_rows_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_attention_pool_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp]),
     "gvqa_lcgn_hop_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
                                          _c_vp, _c_i64, _c_i32, _c_f32, _c_vp]),
 }
@@ -162,13 +168,14 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
             max_in_edges_per_graph=0, variant=VARIANT_AUTO):
     require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
-    require_f32c(a_node=a_node, h_out=h_out, graph_bias=graph_bias, a_graph=a_graph, h_prev=h_prev, bias=bias,
+    require_f32c(h_out=h_out, graph_bias=graph_bias, a_graph=a_graph, h_prev=h_prev, bias=bias,
                  ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
     n = h_out.size(0)
     e = csr["num_edges"]
     a = GatHopArgs()
     a.x_l, a.ldx = ptr(x_l), (x_l.stride(0) if ldx is None else ldx)
     a.graph_bias, a.a_node, a.a_graph = ptr(graph_bias), ptr(a_node), ptr(a_graph)
+    a.ld_a_node = a_node.stride(0) if a_node.dim() == 2 and a_node.size(0) > 1 else 0
     a.a_edge, a.lde = ptr(a_edge), (a_edge.stride(0) if lde is None else lde)
     a.rowptr, a.col_src, a.perm = ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"])
     a.graph_ptr, a.node_graph = ptr(csr["graph_ptr"]), ptr(csr["node_graph"])
@@ -275,4 +282,57 @@ def proj_gemm_3xtf32(a, b_hi, b_lo, out=None):
         check(lib().gvqa_proj_gemm_3xtf32(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
                                           ptr(out), out.stride(0), m, n, k, stream_handle(a.device)),
               "gvqa_proj_gemm_3xtf32")
+    return out
+
+
+def l2_persist_limit(nbytes, device):
+    with torch.cuda.device(device):
+        r = lib().gvqa_device_set_l2_persist_limit(nbytes)
+    if r < 0:
+        check(r, "gvqa_device_set_l2_persist_limit")
+    return r
+
+
+def l2_window(tensor, device, hit_ratio=1.0):
+    """Mark ``tensor`` (or clear with None) as L2-persisting for work enqueued on the current stream."""
+    with torch.cuda.device(device):
+        check(lib().gvqa_stream_set_l2_window(ptr(tensor), 0 if tensor is None else tensor.numel() * tensor.element_size(),
+                                              hit_ratio, stream_handle(device)), "gvqa_stream_set_l2_window")
+
+
+def gather_add_relu(a, b, c, bias, edge_index, relu=True):
+    """out[k] = act(a[src_k] + b[dst_k] + c[k] + bias); edge_index int64 [2,E] (reference layout)."""
+    require_cuda(a, b, c, bias, edge_index)
+    require_f32c(a=a, b=b, c=c, bias=bias)
+    e, f = edge_index.size(1), a.size(1)
+    out = torch.empty(e, f, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().gvqa_gather_add_relu_f32(ptr(a), ptr(b), ptr(c), ptr(bias), ptr(edge_index.contiguous()), ptr(out),
+                                             e, f, 1 if relu else 0, stream_handle(a.device)),
+              "gvqa_gather_add_relu_f32")
+    return out
+
+
+def segment_mean_rows(values, csr, mean=True):
+    """scatter_mean (or sum) of per-edge rows by target node over the destination-CSR."""
+    require_cuda(values)
+    require_f32c(values=values)
+    n, f = csr["rowptr"].numel() - 1, values.size(1)
+    out = torch.empty(n, f, dtype=torch.float32, device=values.device)
+    with torch.cuda.device(values.device):
+        check(lib().gvqa_segment_mean_rows_f32(ptr(values), ptr(csr["perm"]), ptr(csr["rowptr"]), ptr(out), n, f,
+                                               1 if mean else 0, stream_handle(values.device)),
+              "gvqa_segment_mean_rows_f32")
+    return out
+
+
+def attention_pool(gate, x, graph_ptr, num_graphs):
+    """out[g] = sum_n softmax_g(gate)[n] * x[n]  (PyG softmax semantics)."""
+    require_cuda(gate, x, graph_ptr)
+    gate = gate.reshape(-1).contiguous().float()
+    require_f32c(x=x)
+    out = torch.empty(num_graphs, x.size(1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_attention_pool_f32(ptr(gate), ptr(x), ptr(graph_ptr), ptr(out), num_graphs, x.size(1),
+                                            stream_handle(x.device)), "gvqa_attention_pool_f32")
     return out

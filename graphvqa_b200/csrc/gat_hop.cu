@@ -42,7 +42,7 @@ struct HopParams {
   const float* __restrict__ ep_shift;
   float* __restrict__ h_out;
   float* __restrict__ alpha_out;
-  int64_t ldx, lde;
+  int64_t ldx, lde, lda;   // row strides of x_l, a_edge, a_node (floats)
   int32_t N, E, B, C;
   float slope;
   int32_t epilogue;
@@ -62,14 +62,14 @@ struct WarpSoftmax {
       : p(p_), i(i_), g(g_), e0(e0_), e1(e1_), lane(lane_) {
     head = lane % H;
     slot = lane / H;
-    target_term = p.a_node[(int64_t)i * 2 * H + H + head];
+    target_term = p.a_node[(int64_t)i * p.lda + H + head];
     if (p.a_graph) target_term += p.a_graph[(int64_t)g * H + head];
   }
 
   __device__ __forceinline__ float logit(int k) const {
     const int src = p.col_src[k];
     const int64_t e = p.perm ? p.perm[k] : k;
-    const float v = p.a_node[(int64_t)src * 2 * H + head] + target_term + p.a_edge[e * p.lde + head];
+    const float v = p.a_node[(int64_t)src * p.lda + head] + target_term + p.a_edge[e * p.lde + head];
     return leaky_relu(v, p.slope);
   }
 
@@ -208,8 +208,9 @@ constexpr int kBlkNodes = 16;     // max destination nodes per CTA (the launch p
 constexpr int kBlkThreads = 128;  // 4 warps; warp w owns nodes w, w+4, w+8, w+12 of the CTA
 constexpr int kBlkEdgeCap = 256;  // in-edges of the CTA's nodes staged in shared memory
 
-template <int J, int H>
-__global__ void __launch_bounds__(kBlkThreads, 4) gat_hop_block_kernel(const HopParams p, const int npc) {
+template <int J, int H, int kBlkThreads = 128, int kBlkNodes = 16, int kBlkEdgeCap = 256>
+__global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_kernel(const HopParams p, const int npc) {
+  constexpr int kWarps = kBlkThreads / 32;
   __shared__ int32_t rp_s[kBlkNodes + 1];
   __shared__ int32_t gid_s[kBlkNodes];
   __shared__ float tgt_s[kBlkNodes * H];
@@ -222,21 +223,21 @@ __global__ void __launch_bounds__(kBlkThreads, 4) gat_hop_block_kernel(const Hop
   const int C4 = p.C >> 2;
 
   // ---- round trip 1: row pointers, graph ids, target-side logit terms ----------------------
-  if (tid <= nn) rp_s[tid] = p.rowptr[i0 + tid];
-  if (tid < nn * H) {
-    const int node = tid / H, h = tid - node * H;
+  for (int t = tid; t <= nn; t += kBlkThreads) rp_s[t] = p.rowptr[i0 + t];
+  for (int t = tid; t < nn * H; t += kBlkThreads) {
+    const int node = t / H, h = t - node * H;
     const int g = p.node_graph[i0 + node];
     if (h == 0) gid_s[node] = g;
-    float v = p.a_node[(int64_t)(i0 + node) * 2 * H + H + h];
+    float v = p.a_node[(int64_t)(i0 + node) * p.lda + H + h];
     if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
-    tgt_s[tid] = v;
+    tgt_s[t] = v;
   }
   __syncthreads();
   const int eA = rp_s[0], eC = rp_s[nn] - eA;
 
   if (eC > kBlkEdgeCap) {
     // hub-heavy block: per-warp chunked path (scratch carved from alpha_s / src_s)
-    for (int node = wid; node < nn; node += 4)
+    for (int node = wid; node < nn; node += kWarps)
       gather_node<J, H>(p, i0 + node, lane, 0, C4, alpha_s + wid * kEdgeChunk * H, src_s + wid * kEdgeChunk, true);
     return;
   }
@@ -247,15 +248,15 @@ __global__ void __launch_bounds__(kBlkThreads, 4) gat_hop_block_kernel(const Hop
     const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
     src_s[k] = src;
 #pragma unroll
-    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_node[(int64_t)src * 2 * H + h] + p.a_edge[e * p.lde + h];
+    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_node[(int64_t)src * p.lda + h] + p.a_edge[e * p.lde + h];
   }
   __syncthreads();
 
   // ---- softmax: one thread per (node, head), sequential over that node's in-edges -----------
-  if (tid < nn * H) {
-    const int node = tid / H, h = tid - node * H;
+  for (int t = tid; t < nn * H; t += kBlkThreads) {
+    const int node = t / H, h = t - node * H;
     const int r0 = rp_s[node] - eA, r1 = rp_s[node + 1] - eA;
-    const float tg = tgt_s[tid];
+    const float tg = tgt_s[t];
     float mx = -INFINITY;
     for (int k = r0; k < r1; ++k) {
       const float l = leaky_relu(alpha_s[k * H + h] + tg, p.slope);
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) gat_hop_block_kernel(const Hop
 
   // ---- weighted gather: warp w owns nodes w, w+4, ...; 2 edges x H x J 128-bit loads in flight
 #pragma unroll 1
-  for (int node = wid; node < nn; node += 4) {
+  for (int node = wid; node < nn; node += kWarps) {
     const int i = i0 + node;
     const int r0 = rp_s[node] - eA, r1 = rp_s[node + 1] - eA;
     float4 acc[J], skip[J], gb[J];
@@ -324,6 +325,9 @@ template <int J, int H>
 static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   if (variant == 1) {
     gat_hop_gather_kernel<J, H><<<(unsigned)((p.N + 7) / 8), 256, 0, stream>>>(p);
+  } else if (variant >= 100) {   // experiment: 256-thread CTAs of (variant - 100) nodes
+    const int npc = variant - 100;
+    gat_hop_block_kernel<J, H, 256, 32, 512><<<(unsigned)((p.N + npc - 1) / npc), 256, 0, stream>>>(p, npc);
   } else {
     int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
     npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
@@ -425,7 +429,7 @@ __global__ void __launch_bounds__(512) gat_hop_staged_kernel(const HopParams p, 
   for (int i = tid; i <= n; i += nthreads) rp_s[i] = p.rowptr[n0 + i] - e0;
   for (int t = tid; t < n * H; t += nthreads) {
     const int node = t / H, h = t - node * H;
-    float v = p.a_node[(int64_t)(n0 + node) * 2 * H + H + h];
+    float v = p.a_node[(int64_t)(n0 + node) * p.lda + H + h];
     if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
     tgt_s[t] = v;
   }
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(512) gat_hop_staged_kernel(const HopParams p, 
   for (int t = tid; t < eg * H; t += nthreads) {
     const int k = t / H, h = t - k * H;
     const int64_t e = p.perm ? p.perm[e0 + k] : (e0 + k);
-    alpha_s[t] = p.a_node[(int64_t)(src_s[k] + n0) * 2 * H + h] + p.a_edge[e * p.lde + h];
+    alpha_s[t] = p.a_node[(int64_t)(src_s[k] + n0) * p.lda + h] + p.a_edge[e * p.lde + h];
   }
   __syncthreads();
 
@@ -609,14 +613,14 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   const int H = a->heads, C = a->channels;
   if (a->num_nodes < 0 || a->num_edges < 0 || a->num_graphs < 0 || H <= 0 || C <= 0) return GVQA_ERR_BAD_SHAPE;
   if (a->num_nodes >= (1ll << 31) || a->num_edges >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
-  if (a->ldx < (int64_t)H * C || a->lde < H) return GVQA_ERR_BAD_SHAPE;
+  if (a->ldx < (int64_t)H * C || a->lde < H || (a->ld_a_node != 0 && a->ld_a_node < 2 * H)) return GVQA_ERR_BAD_SHAPE;
   if (a->num_nodes == 0) return GVQA_OK;
   if (!a->x_l || !a->a_node || !a->rowptr || !a->node_graph || !a->h_out) return GVQA_ERR_NULL_POINTER;
   if (a->num_edges > 0 && (!a->a_edge || !a->col_src)) return GVQA_ERR_NULL_POINTER;
   if (a->epilogue != GVQA_EPI_NONE && (!a->ep_scale || !a->ep_shift)) return GVQA_ERR_NULL_POINTER;
   if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
-  if (a->variant < 0 || a->variant > 3) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || (a->variant > 3 && (a->variant < 104 || a->variant > 132))) return GVQA_ERR_UNSUPPORTED;
   if ((a->ldx & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
@@ -627,7 +631,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.rowptr = a->rowptr; p.col_src = a->col_src; p.perm = a->perm; p.graph_ptr = a->graph_ptr;
   p.node_graph = a->node_graph; p.h_prev = a->h_prev; p.bias = a->bias; p.ep_scale = a->ep_scale;
   p.ep_shift = a->ep_shift; p.h_out = a->h_out; p.alpha_out = a->alpha_out;
-  p.ldx = a->ldx; p.lde = a->lde;
+  p.ldx = a->ldx; p.lde = a->lde; p.lda = a->ld_a_node > 0 ? a->ld_a_node : 2 * H;
   p.N = (int32_t)a->num_nodes; p.E = (int32_t)a->num_edges; p.B = (int32_t)a->num_graphs; p.C = C;
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -644,7 +648,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
       case 8: return launch_staged<8>(p, plan, stream);
     }
   }
-  const int variant = a->variant == 1 ? 1 : 3;
+  const int variant = a->variant == 1 ? 1 : (a->variant >= 100 ? a->variant : 3);
   switch (H) {
     case 1: return dispatch_flat<1>(p, variant, stream);
     case 2: return dispatch_flat<2>(p, variant, stream);

@@ -1,0 +1,157 @@
+// Segment / gather kernels for the steps right before and after the hop stack:
+//   gvqa_gather_add_relu_f32   : act(a[src_k] + b[dst_k] + c[k] + bias)  -- the first Linear of the
+//       scene-graph encoder's edge / node MLPs after splitting the concatenated input
+//       (pipeline_model_gat.py:75-77 cat([src, dest, edge_attr]); :94 cat([x[row], edge_attr])),
+//       so the [E,900] / [E,600] concatenations are never materialised
+//   gvqa_segment_mean_rows_f32 : torch_scatter.scatter_mean(out, col, dim=0, dim_size=N) of the node
+//       model (pipeline_model_gat.py:96) over the batch's destination-CSR (no atomics, edge order)
+//   gvqa_attention_pool_f32    : MyConditionalGlobalAttention's per-graph softmax + weighted sum
+//       (pipeline_model_gat.py:178-179), PyG softmax semantics
+// All HBM-bound: warp per output row, 128-bit lanes.
+#include "common.cuh"
+
+namespace gvqa {
+
+__global__ void __launch_bounds__(256) gather_add_relu_kernel(
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+    const float* __restrict__ bias, const int64_t* __restrict__ edge_index, float* __restrict__ out, int64_t E,
+    int F, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= E) return;
+  const int64_t src = edge_index[k], dst = edge_index[E + k];
+  const int F4 = F >> 2;
+  for (int c4 = lane; c4 < F4; c4 += 32) {
+    float4 v = ldg_cached(a + src * F + 4 * c4);
+    if (b) {
+      const float4 u = ldg_cached(b + dst * F + 4 * c4);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (c) {
+      const float4 u = ldg_stream(c + k * F + 4 * c4);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (bias) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    stg_stream(out + k * F + 4 * c4, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) segment_mean_rows_kernel(
+    const float* __restrict__ values, const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
+    float* __restrict__ out, int S, int F, int mean) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= S) return;
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  const int F4 = F >> 2;
+  for (int c4 = lane; c4 < F4; c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = e0; k < e1; ++k) {
+      const int64_t e = perm ? perm[k] : k;
+      const float4 v = ldg_stream(values + e * F + 4 * c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (mean) {   // sum / count.clamp(min=1), like torch_scatter (a true division)
+      const float cnt = (float)max(e1 - e0, 1);
+      acc.x /= cnt; acc.y /= cnt; acc.z /= cnt; acc.w /= cnt;
+    }
+    stg_stream(out + (int64_t)i * F + 4 * c4, acc);
+  }
+}
+
+// One CTA per graph: softmax of the per-node gate over the graph's nodes, then sum_n w_n x[n,:]
+__global__ void __launch_bounds__(256) attention_pool_kernel(const float* __restrict__ gate,
+                                                             const float* __restrict__ x,
+                                                             const int32_t* __restrict__ graph_ptr,
+                                                             float* __restrict__ out, int C) {
+  __shared__ float red[8];
+  __shared__ float w_s[256];
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n0 = graph_ptr[g], n1 = graph_ptr[g + 1], n = n1 - n0;
+  // pass 1: segment max (empty segment -> 0, and the output row is 0)
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += 256) mx = fmaxf(mx, gate[n0 + i]);
+  mx = warp_max(mx);
+  if (lane == 0) red[wid] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  if (n == 0) mx = 0.f;
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < n; i += 256) sum += expf(gate[n0 + i] - mx);
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float denom = sum + 1e-16f;
+  // pass 2: weighted sum over nodes in node order, chunks of 256 nodes staged in smem
+  const int C4 = C >> 2;
+  for (int c_base = 0; c_base < C4; c_base += 256) {            // all threads take part in the barriers
+    const int c4 = c_base + tid;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < n; base += 256) {
+      __syncthreads();
+      if (base + tid < n) w_s[tid] = expf(gate[n0 + base + tid] - mx) / denom;
+      __syncthreads();
+      if (c4 < C4) {
+        const int lim = min(256, n - base);
+#pragma unroll 4
+        for (int i = 0; i < lim; ++i) fma4(acc, w_s[i], ldg_stream(x + (int64_t)(n0 + base + i) * C + 4 * c4));
+      }
+    }
+    if (c4 < C4) stg_stream(out + (int64_t)g * C + 4 * c4, acc);
+  }
+}
+
+}  // namespace gvqa
+
+using namespace gvqa;
+
+extern "C" GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b, const float* c, const float* bias,
+                                                 const int64_t* edge_index, float* out, int64_t num_edges,
+                                                 int32_t feat, int32_t relu, void* stream_) {
+  if (num_edges < 0 || feat <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_edges == 0) return GVQA_OK;
+  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
+  if (feat & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)))
+    return GVQA_ERR_MISALIGNED;
+  gather_add_relu_kernel<<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      a, b, c, bias, edge_index, out, num_edges, feat, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_segment_mean_rows_f32(const float* values, const int32_t* perm, const int32_t* rowptr,
+                                                   float* out, int64_t num_segments, int32_t feat, int32_t mean,
+                                                   void* stream_) {
+  if (num_segments < 0 || feat <= 0 || num_segments >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_segments == 0) return GVQA_OK;
+  if (!values || !rowptr || !out) return GVQA_ERR_NULL_POINTER;
+  if (feat & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(values) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
+  segment_mean_rows_kernel<<<(unsigned)((num_segments + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      values, perm, rowptr, out, (int)num_segments, feat, mean);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_attention_pool_f32(const float* gate, const float* x, const int32_t* graph_ptr, float* out,
+                                                int64_t num_graphs, int32_t channels, void* stream_) {
+  if (num_graphs < 0 || channels <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_graphs == 0) return GVQA_OK;
+  if (!gate || !x || !graph_ptr || !out) return GVQA_ERR_NULL_POINTER;
+  if (channels & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
+  attention_pool_kernel<<<(unsigned)num_graphs, 256, 0, static_cast<cudaStream_t>(stream_)>>>(gate, x, graph_ptr, out,
+                                                                                                channels);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}

@@ -187,11 +187,14 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) |
-                                 ((uint32_t)(kBM >> 4) << 24);
       uint32_t it = 0, tile_it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N = this tile's width rounded up to
+        // 16 (a ragged last column tile, e.g. the 16 logit columns appended to W, costs N=16 MMAs, not 128)
+        const int n0 = (tile % n_tiles) * kBN;
+        const int ncols = min(kBN, (N - n0 + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ncols >> 3) << 17) |
+                               ((uint32_t)(kBM >> 4) << 24);
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
@@ -267,7 +270,7 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       float* crow = c + (int64_t)row * ldc + n0;
       const bool two_chunks = kblocks >= kBigChunks;       // with a single k-block the second K-half is empty
 #pragma unroll 1
-      for (int cc = 0; cc < kBN / 32; ++cc) {
+      for (int cc = 0; cc < kBN / 32 && n0 + cc * 32 < N; ++cc) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32);
         uint32_t rs[32], r0[32], r1[32];
         GVQA_TMEM_LD32(rs, taddr + kTmemSmall);

@@ -169,6 +169,8 @@ class gat_seq(nn.Module):
         # node projection h @ W_h^T: "3xtf32" = hand-written tcgen05 split-TF32 GEMM (fp32-level accuracy,
         # ~2.5x cuBLAS fp32 SIMT), "cublas" = torch.mm with TF32 off
         self.projection = "3xtf32"
+        # keep x_l (written by the GEMM, read once by the hop kernel) resident in L2 between the two
+        self.l2_persist = False
         self.hop_events = None      # set to a list to collect (start, end) CUDA events per fused-hop launch
         self._packed = None
 
@@ -202,7 +204,13 @@ class gat_seq(nn.Module):
                 b = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
                 scale.append((g * inv).float().contiguous())
                 shift.append((b - bn.running_mean.detach().double() * g * inv).float().contiguous())
-        w_split = [_cabi.split_tf32(w) for w in w_h] if w_h[0].is_cuda else None
+        # tcgen05 projection: the collapsed a_l / a_r logit vectors ride along as 16 extra output columns
+        # (8 used at H=4) so one GEMM yields x_l and a_node; split into tf32 hi/lo once
+        w_split = None
+        if w_h[0].is_cuda:
+            pad = 16 - (2 * self.convs[0].heads) % 16 if (2 * self.convs[0].heads) % 16 else 0
+            w_split = [_cabi.split_tf32(torch.cat([w, vn, vn.new_zeros(pad, vn.size(1))]))
+                       for w, vn in zip(w_h, v_node)]
         self._packed = dict(key=key, w_h=w_h, w_split=w_split, w_ins=torch.stack(w_ins), v_node=v_node,
                             v_graph=torch.stack(v_graph), v_edge=torch.cat(v_edge).contiguous(),
                             scale=scale, shift=shift)
@@ -235,15 +243,21 @@ class gat_seq(nn.Module):
 
         h = x
         hops = []
-        x_l = torch.empty(n, heads * c, dtype=torch.float32, device=x.device)
-        a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        fused_logits = self.projection == "3xtf32"
+        hc = heads * c
+        ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
+        x_l = torch.empty(n, ldx, dtype=torch.float32, device=x.device)
+        a_node = x_l[:, hc:hc + 2 * heads] if fused_logits else \
+            torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        if self.l2_persist:
+            _cabi.l2_window(x_l, x.device, 1.0)
         for i in range(num_hops):
-            if self.projection == "3xtf32":
+            if fused_logits:
                 _cabi.proj_gemm_3xtf32(h, pk["w_split"][i][0], pk["w_split"][i][1], out=x_l)
             else:
                 with _strict_fp32_matmul():
                     torch.mm(h, pk["w_h"][i].t(), out=x_l)
-            _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
+                _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
             last = i == num_hops - 1
             h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
             if self.hop_events is not None:
@@ -262,4 +276,6 @@ class gat_seq(nn.Module):
             h = h_out
             if return_hops:
                 hops.append(h)
+        if self.l2_persist:
+            _cabi.l2_window(None, x.device)
         return (h, hops) if return_hops else h

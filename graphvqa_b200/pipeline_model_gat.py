@@ -12,8 +12,9 @@ checkpoint loads through the same size-tolerant ``load_state_dict`` (:823-836). 
   modules) and the per-graph LayerNorm: hand-written sm_100a kernels through the C ABI;
 * Transformer question encoder, program decoders, answer head: ordinary PyTorch (``torch.nn``), as in
   the reference;
-* scene-graph encoder MLPs and the question-conditioned pooling: PyTorch GEMMs around
-  segment reductions that use the batch's destination-CSR (no torch_geometric / torch_scatter).
+* scene-graph encoder and question-conditioned pooling: PyTorch GEMMs around the engine's fused
+  gather+add+ReLU, CSR segment-mean and per-graph softmax-pool kernels (no torch_geometric /
+  torch_scatter, no [E,900] concatenations).
 
 The reference reads its vocabularies from class attributes of ``gqa_dataset_entry`` at construction
 (pipeline_model_gat.py:556-562, 628-634).  ``PipelineModel()`` does the same when that module is
@@ -75,16 +76,6 @@ def _batch_csr(graphs, num_graphs):
         except Exception:
             pass
     return csr
-
-
-def _segment_sum_by_dst(values, csr):
-    """sum of per-edge rows over the in-edges of every node, in CSR (= original edge) order."""
-    n = csr.num_nodes
-    out = values.new_zeros((n,) + tuple(values.shape[1:]))
-    if values.size(0) == 0:
-        return out
-    ordered = values.index_select(0, csr.perm[:values.size(0)].long())
-    return torch.segment_reduce(ordered, "sum", offsets=csr.rowptr.long(), axis=0, initial=0) if n else out
 
 
 class PositionalEncoding(nn.Module):
@@ -236,12 +227,23 @@ class _MetaLayer(nn.Module):
         self.node_model = _NodeModel(nf, ef)
 
     def forward(self, x, edge_index, edge_attr, csr):
-        row, col = edge_index[0], edge_index[1]
-        e_new = self.edge_model.edge_mlp(torch.cat([x[row], x[col], edge_attr], dim=1))
-        msg = self.node_model.node_mlp_1(torch.cat([x[row], e_new], dim=1))
-        deg = (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).to(msg.dtype).unsqueeze(1)
-        agg = _segment_sum_by_dst(msg, csr) / deg                      # scatter_mean (count clamped to 1)
-        return self.node_model.node_mlp_2(torch.cat([x, agg], dim=1)), e_new
+        """The first Linear of every MLP acts on a concatenation of gathered rows; it is evaluated as a
+        sum of per-part projections (node-level GEMMs) followed by one fused gather+add+bias+ReLU kernel,
+        so [E,900] / [E,600] are never materialised; scatter_mean runs over the destination-CSR."""
+        nf = x.size(1)
+        d = csr.as_dict()
+        em, nm = self.edge_model.edge_mlp, self.node_model
+        # edge model: e' = W2 relu(W1 [x_src | x_dst | e] + b1) + b2
+        w1 = em[0].weight
+        xa, xb = x @ w1[:, :nf].t(), x @ w1[:, nf:2 * nf].t()
+        ec = edge_attr @ w1[:, 2 * nf:].t()
+        e_new = em[2](_cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index))
+        # node model 1 on the UPDATED edges, mean over in-edges, node model 2 on [x | agg]
+        w1 = nm.node_mlp_1[0].weight
+        msg = nm.node_mlp_1[2](_cabi.gather_add_relu(x @ w1[:, :nf].t(), None, e_new @ w1[:, nf:].t(),
+                                                     nm.node_mlp_1[0].bias, edge_index))
+        agg = _cabi.segment_mean_rows(msg, d, mean=True)
+        return nm.node_mlp_2(torch.cat([x, agg], dim=1)), e_new
 
 
 class GroundTruth_SceneGraph_Encoder(nn.Module):
@@ -290,16 +292,10 @@ class MyConditionalGlobalAttention(nn.Module):
         gate = self.gate_nn(self.ques_nn(u)[batch] * x)
         if graph_ptr is None:
             counts = torch.bincount(batch, minlength=size)
-            graph_ptr = torch.zeros(size + 1, dtype=torch.long, device=x.device)
-            graph_ptr[1:] = counts.cumsum(0)
-        offsets = graph_ptr.long()
-        lengths = offsets[1:] - offsets[:-1]
-        seg_max = torch.segment_reduce(gate, "max", lengths=lengths, axis=0, initial=float("-inf"))
-        seg_max = torch.where(torch.isinf(seg_max), torch.zeros_like(seg_max), seg_max)
-        ex = (gate - seg_max[batch]).exp()
-        seg_sum = torch.segment_reduce(ex, "sum", lengths=lengths, axis=0, initial=0)
-        gate = ex / (seg_sum[batch] + 1e-16)
-        return torch.segment_reduce(gate * x, "sum", lengths=lengths, axis=0, initial=0)
+            graph_ptr = torch.zeros(size + 1, dtype=torch.int32, device=x.device)
+            graph_ptr[1:] = counts.cumsum(0).to(torch.int32)
+        # per-graph softmax + weighted sum in one kernel (replaces scatter_max / exp / scatter_add / gathers)
+        return _cabi.attention_pool(gate, x.contiguous(), graph_ptr.to(torch.int32), size)
 
 
 class PipelineModel(nn.Module):

@@ -56,6 +56,13 @@ typedef enum gvqa_epilogue {
 GVQA_API int gvqa_abi_version(void);
 GVQA_API const char* gvqa_error_string(int status);
 
+/* L2 residency for producer -> consumer tensors (x_l between the projection GEMM and the hop kernel).
+ * gvqa_device_set_l2_persist_limit: set aside up to `bytes` of L2 for persisting lines; returns the
+ * MiB granted (>= 0) or a negative status.  gvqa_stream_set_l2_window: access-policy window of the
+ * stream (ptr == NULL clears it); captured into CUDA-graph kernel nodes. */
+GVQA_API int gvqa_device_set_l2_persist_limit(size_t bytes);
+GVQA_API int gvqa_stream_set_l2_window(const void* ptr, size_t bytes, float hit_ratio, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Destination-CSR build.  Replaces what torch_geometric's MessagePassing.propagate derives
  * from `edge_index` on every call (gat_skip.py:155) and the
@@ -114,7 +121,9 @@ typedef struct gvqa_gat_hop_args {
   const float* x_l;        /* [N, ldx] projected node features, head-major columns h*C+c     */
   int64_t ldx;             /* row stride of x_l in floats (>= H*C, multiple of 4)            */
   const float* graph_bias; /* [B, C] per-graph additive output term (see above), or NULL     */
-  const float* a_node;     /* [N, 2H]: columns 0..H-1 = source term a_l, H..2H-1 = target a_r */
+  const float* a_node;     /* [N, ld_a_node]: columns 0..H-1 = source term a_l, H..2H-1 = target a_r */
+  int64_t ld_a_node;       /* row stride of a_node in floats; 0 = dense (2H).  The logit columns may
+                              live inside the x_l buffer (extra GEMM output columns)               */
   const float* a_graph;    /* [B, H] per-graph additive logit term, or NULL                  */
   const float* a_edge;     /* [E, lde] per-edge logit term                                    */
   int64_t lde;             /* row stride of a_edge in floats (>= H)                           */
@@ -208,6 +217,25 @@ GVQA_API int gvqa_lcgn_hop_f32(const float* xl, const float* xr, const float* xv
                                const int32_t* rowptr, const int32_t* col_src, const int32_t* node_graph,
                                float* out, int64_t num_nodes, int32_t channels, float negative_slope,
                                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Steps right before / after the hop stack.
+ *  gvqa_gather_add_relu_f32: out[k,:] = act(a[src_k,:] + (b ? b[dst_k,:] : 0) + (c ? c[k,:] : 0) + bias)
+ *     -- first Linear of the scene-graph encoder's edge / node MLPs on the split concatenation
+ *     (pipeline_model_gat.py:75-77, :94); edge_index is the reference's int64 [2,E].
+ *  gvqa_segment_mean_rows_f32: out[i,:] = sum (mean != 0: / max(count,1)) of values[perm[k],:] over
+ *     k in [rowptr[i], rowptr[i+1])  -- torch_scatter.scatter_mean by target (pipeline_model_gat.py:96).
+ *  gvqa_attention_pool_f32: per graph g, w = softmax(gate[n0:n1]) (exp(x-max)/(sum+1e-16)),
+ *     out[g,:] = sum_n w_n x[n,:]  -- MyConditionalGlobalAttention (pipeline_model_gat.py:178-179).
+ */
+GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b, const float* c, const float* bias,
+                                      const int64_t* edge_index, float* out, int64_t num_edges,
+                                      int32_t feat, int32_t relu, void* stream);
+GVQA_API int gvqa_segment_mean_rows_f32(const float* values, const int32_t* perm, const int32_t* rowptr,
+                                        float* out, int64_t num_segments, int32_t feat, int32_t mean,
+                                        void* stream);
+GVQA_API int gvqa_attention_pool_f32(const float* gate, const float* x, const int32_t* graph_ptr, float* out,
+                                     int64_t num_graphs, int32_t channels, void* stream);
 
 #ifdef __cplusplus
 }
