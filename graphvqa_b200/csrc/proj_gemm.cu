@@ -41,19 +41,39 @@ constexpr int kBM = 128, kBN = 128, kBK = 32;       // tile: rows of A, rows of 
 constexpr int kStages = 4;                          // shared-memory ring
 constexpr int kAStages = 2;                         // tensor-memory ring of split A tiles
 constexpr int kBigChunks = 2;                       // hi*hi accumulators over K-halves (+1 for the lo terms)
-constexpr int kGemmThreads = 320;                   // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-9 epilogue
+constexpr int kGemmThreads = 448;                   // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-13 epilogue
 constexpr int kConvThreads = 128;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiThreads = 256;                    // two warps per TMEM lane quarter, 64 accumulator columns each
 constexpr uint32_t kABytes = kBM * kBK * 4;         // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 4;         // 16 KB
 constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;       // A raw | B_hi | B_lo = 48 KB
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemSmall = kBigChunks * kBN;             // 256
 constexpr uint32_t kTmemA = (kBigChunks + 1) * kBN;           // 384
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kEpiStageBytes = 32 * 32 * 4;    // per epilogue warp: a [32 rows x 32 columns] block staged for the TMA store
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + (kEpiThreads / 32) * kEpiStageBytes +
+                             1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One lane of a fully active warp (elect.sync).  Issuing TMA / tcgen05 instructions under this predicate
+// instead of `lane == 0` lets ptxas keep their operands in uniform registers without wrapping every
+// instruction in an ELECT/BRA.U.ANY loop -- measured 148 -> 64 cycles per MMA issue
+// (profiles/microbench/mma_rate.cu).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -94,6 +114,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -119,16 +149,27 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
         "=r"(r[30]), "=r"(r[31])                                                                             \
       : "r"(taddr))
 
+#define GVQA_TMEM_LD16(r, taddr)                                                                             \
+  asm volatile(                                                                                              \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                              \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                       \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+      : "r"(taddr))
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                        const __grid_constant__ CUtensorMap map_blo, float* __restrict__ c, int64_t ldc, int M,
-                        int N, int K, long long* __restrict__ trace) {
+                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int M,
+                        int N, int K, long long* __restrict__ trace, const int dbg) {
+  // dbg (debug only, 0 in production): bit0 producer skips the TMA loads, bit1 converters skip their work,
+  // bit2 epilogue skips TMEM loads + stores -- used by profiles/microbench/gemm_dbg.py to attribute time
   // trace (debug, may be null): CTA 0 records clock64() per k-block and role: [it][0..4] = producer issue,
   // converter start, converter done, mma start, mma committed; [1024+tile][0..1] = epilogue start / end
 #define GVQA_TRACE(slot, col) do { if (trace && blockIdx.x == 0 && (slot) < 1100) trace[(slot) * 8 + (col)] = clock64(); } while (0)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;   // [8 warps][4 KB], 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (kEpiThreads / 32) * kEpiStageBytes);
   uint64_t* tma_full = bars;                        // [kStages]   TMA bytes landed
   uint64_t* smem_empty = bars + kStages;            // [kStages]   MMAs that read the stage are done
   uint64_t* a_ready = bars + 2 * kStages;           // [kAStages]  converters filled the TMEM A stage
@@ -140,7 +181,9 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + kBN - 1) / kBN;
   const int num_tiles = m_tiles * n_tiles;
-  const int kblocks = (K + kBK - 1) / kBK;
+  // k-blocks rounded up to a multiple of the ring depth (TMA zero-fills the out-of-range ones): every tile then
+  // starts at ring slot 0, so the MMA issuer's loop is unrolled over the slots with compile-time descriptors
+  const int kblocks = ((K + kBK - 1) / kBK + kStages - 1) / kStages * kStages;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -167,27 +210,34 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer: one elected lane runs the whole loop =====================
+    if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
-          GVQA_TRACE(it, 0);
           unsigned char* st = smem + (size_t)s * kStageBytes;
-          mbar_expect_tx(&tma_full[s], kABytes + 2 * kBBytes);
-          tma_load_2d(st, &map_a, &tma_full[s], kb * kBK, m0);
-          tma_load_2d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
-          tma_load_2d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
+          GVQA_TRACE(it, 0);
+          if (dbg & 1) {
+            mbar_arrive(&tma_full[s]);
+          } else {
+            mbar_expect_tx(&tma_full[s], kABytes + 2 * kBBytes);
+            tma_load_2d(st, &map_a, &tma_full[s], kb * kBK, m0);
+            tma_load_2d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
+            tma_load_2d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: one elected lane runs the whole loop (leaving and re-entering the
+    // elected region per k-block cost ~270 cycles of reconvergence after the tcgen05 instructions) ==========
+    if (elect_one()) {
       uint32_t it = 0, tile_it = 0;
+      static_assert(kAStages == 2 && kStages % kAStages == 0, "MMA loop unroll assumes 2 TMEM A stages");
+      const uint64_t desc0 = umma_desc(smem_u32(smem));   // descriptor of (base + c) == desc0 + (c >> 4)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N = this tile's width rounded up to
         // 16 (a ragged last column tile, e.g. the 16 logit columns appended to W, costs N=16 MMAs, not 128)
@@ -195,30 +245,38 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const int ncols = min(kBN, (N - n0 + 15) & ~15);
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ncols >> 3) << 17) |
                                ((uint32_t)(kBM >> 4) << 24);
+        const int half_kb = (kblocks + 1) / 2;             // first k-block of the second K-half (kBigChunks == 2)
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);          // epilogue of the previous tile has drained TMEM
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % kStages, ts = it % kAStages;
-          mbar_wait(&a_ready[ts], (it / kAStages) & 1);    // implies tma_full[s]: the converters waited on it
-          GVQA_TRACE(it, 3);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t b_hi = smem_u32(smem + (size_t)s * kStageBytes + kABytes), b_lo = b_hi + kBBytes;
-          const uint32_t a_hi = tmem_base + kTmemA + (uint32_t)(ts * 2 * kBK), a_lo = a_hi + kBK;
-          // hi*hi goes to the accumulator of this K-half, the lo terms to the last accumulator
-          const int chunk = (kb * kBigChunks) / kblocks;
-          const bool chunk_first = kb == 0 || ((kb - 1) * kBigChunks) / kblocks != chunk;
-          const uint32_t d_big = tmem_base + (uint32_t)(chunk * kBN), d_small = tmem_base + kTmemSmall;
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kStages) {
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {            // K = 8 per MMA: 8 TMEM columns of A, 32 bytes of B
-            umma_tf32_ts(d_small, a_lo + 8 * k, umma_desc(b_hi + 32 * k), idesc, (kb | k) != 0);
-            umma_tf32_ts(d_small, a_hi + 8 * k, umma_desc(b_lo + 32 * k), idesc, 1);
-            umma_tf32_ts(d_big, a_hi + 8 * k, umma_desc(b_hi + 32 * k), idesc, !(chunk_first && k == 0));
+          for (int u = 0; u < kStages; ++u, ++it) {       // u == ring slot; slot and TMEM A stage are compile-time
+            const int kb = kb0 + u;
+            constexpr int kHalf = kAStages;               // kAStages == 2: TMEM A stage = u & 1, its parity = (u >> 1) & 1
+            const int ts = u % kHalf;
+            GVQA_TRACE(it, 5);
+            mbar_wait(&a_ready[ts], (u / kHalf) & 1);     // implies tma_full[u]: the converters waited on it
+            GVQA_TRACE(it, 6);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            GVQA_TRACE(it, 3);
+            const uint64_t b_hi = desc0 + (uint64_t)((u * kStageBytes + kABytes) >> 4), b_lo = b_hi + (kBBytes >> 4);
+            const uint32_t a_hi = tmem_base + kTmemA + (uint32_t)(ts * 2 * kBK), a_lo = a_hi + kBK;
+            // hi*hi goes to the accumulator of this K-half, the lo terms to the last accumulator
+            const bool second = kb >= half_kb;
+            const bool chunk_first = kb == 0 || kb == half_kb;
+            const uint32_t d_big = tmem_base + (second ? (uint32_t)kBN : 0u), d_small = tmem_base + kTmemSmall;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {            // K = 8 per MMA: 8 TMEM columns of A, 32 bytes of B
+              umma_tf32_ts(d_small, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+              umma_tf32_ts(d_small, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+              umma_tf32_ts(d_big, a_hi + 8 * k, b_hi + 2 * k, idesc, !(chunk_first && k == 0));
+            }
+            umma_commit(&smem_empty[u]);                   // smem stage reusable once these MMAs are done
+            umma_commit(&a_empty[ts]);                     // and so is the TMEM A stage
+            if (kb == kblocks - 1) umma_commit(acc_full);  // accumulators complete
+            GVQA_TRACE(it, 4);
           }
-          umma_commit(&smem_empty[s]);                     // smem stage reusable once these MMAs are done
-          umma_commit(&a_empty[ts]);                       // and so is the TMEM A stage
-          GVQA_TRACE(it, 4);
         }
-        umma_commit(acc_full);                             // accumulators complete
       }
     }
   } else if (warp < 6) {
@@ -234,6 +292,7 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         mbar_wait(&a_empty[ts], ((it / kAStages) & 1) ^ 1);
         if (threadIdx.x == 64) GVQA_TRACE(it, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg & 2) { mbar_arrive(&a_ready[ts]); continue; }
         const uint32_t row_addr = smem_u32(smem + (size_t)s * kStageBytes) + (uint32_t)r * 128u;
         uint32_t hi[kBK], lo[kBK];
 #pragma unroll
@@ -258,49 +317,69 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9): TMEM -> registers -> global ====================
+    // ===================== epilogue (warps 6..13): TMEM -> registers, release TMEM, then global ====================
+    // Two warps per TMEM lane quarter, 64 accumulator columns each.  The three accumulators are summed into
+    // registers in 16-column pieces; TMEM is handed back to the MMA issuer as soon as the last tcgen05.ld has
+    // landed, so the global stores of tile t overlap the main loop of tile t+1 (no second accumulator set needed).
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+    const int chalf = warp >= 10 ? 1 : 0;                  // which 64 columns of the tile
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
       const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
       mbar_wait(acc_full, tile_it & 1);
       if (threadIdx.x == 192) GVQA_TRACE(1024 + tile_it, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + quarter * 32 + lane;
-      float* crow = c + (int64_t)row * ldc + n0;
-      const bool two_chunks = kblocks >= kBigChunks;       // with a single k-block the second K-half is empty
-#pragma unroll 1
-      for (int cc = 0; cc < kBN / 32 && n0 + cc * 32 < N; ++cc) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cc * 32);
-        uint32_t rs[32], r0[32], r1[32];
-        GVQA_TMEM_LD32(rs, taddr + kTmemSmall);
-        GVQA_TMEM_LD32(r0, taddr);
-        if (two_chunks) GVQA_TMEM_LD32(r1, taddr + kBN);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float acc[32];
+      const int col0 = n0 + chalf * 64;
+      float acc[64];
+      const bool live = col0 < N && !(dbg & 4);            // a ragged last column tile may leave this half empty
+      if (live) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          acc[e] = __uint_as_float(rs[e]) + __uint_as_float(r0[e]);
-          if (two_chunks) acc[e] += __uint_as_float(r1[e]);
-        }
-        if (row < M) {
-          const int col0 = n0 + cc * 32;
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64 + pc * 16);
+          uint32_t rs[16], r0[16], r1[16];
+          GVQA_TMEM_LD16(rs, taddr + kTmemSmall);
+          GVQA_TMEM_LD16(r0, taddr);
+          GVQA_TMEM_LD16(r1, taddr + kBN);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (col0 + 4 * j + 3 < N) {
-              *reinterpret_cast<float4*>(crow + cc * 32 + 4 * j) =
-                  make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            } else {
-              for (int e = 0; e < 4; ++e)
-                if (col0 + 4 * j + e < N) crow[cc * 32 + 4 * j + e] = acc[4 * j + e];
-            }
-          }
+          for (int e = 0; e < 16; ++e)
+            acc[pc * 16 + e] = (__uint_as_float(rs[e]) + __uint_as_float(r0[e])) + __uint_as_float(r1[e]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(acc_empty);
+      mbar_arrive(acc_empty);                              // TMEM is free: the next tile's MMAs may start
       if (threadIdx.x == 192) GVQA_TRACE(1024 + tile_it, 1);
+      if (live) {
+        // registers -> 128B-swizzled shared block -> one TMA store per [32 x 32] block.  Thread-per-row
+        // global stores would touch 32 different lines per instruction and saturate the LSU for ~4000
+        // cycles per tile, starving the converters' shared-memory loads (measured); the TMA store costs the
+        // LSU 8 conflict-light STS per block and clips rows >= M / columns >= N by itself.
+        const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - 6) * kEpiStageBytes);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          if (col0 + pass * 32 < N) {
+            if (pass == 1) {                               // the block is reused: its previous store must have read it
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(stage + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) * 16),
+                     acc[pass * 32 + 4 * j], acc[pass * 32 + 4 * j + 1], acc[pass * 32 + 4 * j + 2],
+                     acc[pass * 32 + 4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // before the next tile restages
+        __syncwarp();
+      }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // all stores complete
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -338,12 +417,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 // [rows, K] fp32 row-major (row stride ld floats) -> 2-D map with a [box_rows x 32] 128B-swizzled box
-static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows,
+                     int box_cols = kBK) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -355,7 +435,9 @@ static bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
 using namespace gvqa;
 
 static long long* g_gemm_trace = nullptr;   // debug only: set through gvqa_debug_set_gemm_trace
+static int g_gemm_dbg = 0;                  // debug only: set through gvqa_debug_set_gemm_flags
 extern "C" GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; }
+extern "C" GVQA_API void gvqa_debug_set_gemm_flags(int flags) { g_gemm_dbg = flags; }
 
 extern "C" GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream_) {
   if (count < 0) return GVQA_ERR_BAD_SHAPE;
@@ -376,9 +458,9 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const
   if (!a || !b_hi || !b_lo || !c) return GVQA_ERR_NULL_POINTER;
   if ((k & 3) || (lda & 3) || (ldb & 3) || (ldc & 3)) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(a) || !aligned16(b_hi) || !aligned16(b_lo) || !aligned16(c)) return GVQA_ERR_MISALIGNED;
-  CUtensorMap map_a, map_bhi, map_blo;
+  CUtensorMap map_a, map_bhi, map_blo, map_c;
   if (!make_map(&map_a, a, m, k, lda, kBM) || !make_map(&map_bhi, b_hi, n, k, ldb, kBN) ||
-      !make_map(&map_blo, b_lo, n, k, ldb, kBN))
+      !make_map(&map_blo, b_lo, n, k, ldb, kBN) || !make_map(&map_c, c, m, n, ldc, 32, 32))
     return GVQA_ERR_CUDA;
   static const bool attr_ok =
       cudaFuncSetAttribute(proj_gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) ==
@@ -387,7 +469,7 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const
   const int tiles = (int)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   proj_gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream_)>>>(
-      map_a, map_bhi, map_blo, c, ldc, (int)m, n, k, g_gemm_trace);
+      map_a, map_bhi, map_blo, map_c, (int)m, n, k, g_gemm_trace, g_gemm_dbg);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
