@@ -179,6 +179,8 @@ def run_engine(args, rank, local_rank, world):
     randomise_bn(model, 7)
     model = model.to(dev)
     model.kernel_variant = args.variant
+    if args.gemm_flags:
+        _cabi.lib().gvqa_debug_set_gemm_flags(args.gemm_flags)
     model.projection = args.projection
     if args.l2_persist:
         granted = _cabi.l2_persist_limit(args.l2_persist << 20, dev)
@@ -267,9 +269,9 @@ def run_engine(args, rank, local_rank, world):
 
         # ---------------- end to end: pinned host buffers -> H2D -> hot path -> D2H --------------
         # through the public host-buffer API (graphvqa_b200.host_api.GatSeqHostRunner): copies of
-        # neighbouring batches overlap the kernels of the current one (3 streams, 2 device slots).
+        # neighbouring batches overlap the kernels of the current one (3 streams, 3 device slots).
         from graphvqa_b200.host_api import GatSeqHostRunner
-        runner = GatSeqHostRunner(model, dev, depth=2, use_cuda_graph=not args.no_graph,
+        runner = GatSeqHostRunner(model, dev, depth=3, use_cuda_graph=not args.no_graph,
                                   max_nodes_per_graph=max_nodes, max_in_edges_per_graph=max_edges)
         for i in range(6):
             runner.submit(pinned[i % R])
@@ -281,7 +283,8 @@ def run_engine(args, rank, local_rank, world):
         for i in range(args.steps):
             t_id = runner.submit(pinned[i % R])
             if i >= 2:
-                checksum += float(runner.result(t_id - 2)[0, 0])    # consume results as they arrive
+                checksum += float(runner.result(t_id - 2)[0, 0])    # consume results as they arrive (slot i-2 is
+                                                                    # reused by batch i+1, so it is read before then)
         runner.drain()
         e1.record(runner.s_d2h)
         torch.cuda.synchronize()
@@ -329,6 +332,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged, 3 block")
     ap.add_argument("--projection", default="3xtf32", choices=["3xtf32", "cublas"])
+    ap.add_argument("--gemm-flags", type=int, default=0, help="debug flags of the projection GEMM (experiments)")
     ap.add_argument("--l2-persist", type=int, default=0, help="MiB of L2 set aside to keep x_l resident (0 = off)")
     args = ap.parse_args()
 

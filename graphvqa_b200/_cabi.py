@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK = 0, 1, 2, 3
@@ -32,6 +32,7 @@ class GatHopArgs(ctypes.Structure):
         ("num_nodes", _c_i64), ("num_edges", _c_i64), ("num_graphs", _c_i64),
         ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
         ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
+        ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64),
     ]
 
 
@@ -169,8 +170,10 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
             max_in_edges_per_graph=0, variant=VARIANT_AUTO):
     require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
-    require_f32c(h_out=h_out, graph_bias=graph_bias, a_graph=a_graph, h_prev=h_prev, bias=bias,
-                 ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
+    require_f32c(h_out=h_out, h_prev=h_prev, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
+    for name, t in (("graph_bias", graph_bias), ("a_graph", a_graph)):    # [B, .] row-strided views are fine
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError("gat_hop: %s must be float32 [B, .] with unit column stride" % name)
     n = h_out.size(0)
     e = csr["num_edges"]
     a = GatHopArgs()
@@ -187,6 +190,8 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.heads, a.channels, a.negative_slope, a.epilogue = heads, channels, negative_slope, epilogue
     a.max_nodes_per_graph, a.max_in_edges_per_graph = max_nodes_per_graph, max_in_edges_per_graph
     a.variant = variant
+    a.ld_graph_bias = graph_bias.stride(0) if graph_bias is not None and graph_bias.size(0) > 1 else 0
+    a.ld_a_graph = a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else 0
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
     return h_out

@@ -42,7 +42,7 @@ struct HopParams {
   const float* __restrict__ ep_shift;
   float* __restrict__ h_out;
   float* __restrict__ alpha_out;
-  int64_t ldx, lde, lda;   // row strides of x_l, a_edge, a_node (floats)
+  int64_t ldx, lde, lda, ldgb, ldag;   // row strides of x_l, a_edge, a_node, graph_bias, a_graph (floats)
   int32_t N, E, B, C;
   float slope;
   int32_t epilogue;
@@ -63,7 +63,7 @@ struct WarpSoftmax {
     head = lane % H;
     slot = lane / H;
     target_term = p.a_node[(int64_t)i * p.lda + H + head];
-    if (p.a_graph) target_term += p.a_graph[(int64_t)g * H + head];
+    if (p.a_graph) target_term += p.a_graph[(int64_t)g * p.ldag + head];
   }
 
   __device__ __forceinline__ float logit(int k) const {
@@ -138,7 +138,7 @@ __device__ __forceinline__ void gather_node(const HopParams& p, int i, int lane,
     const int c4 = lane + 32 * j;
     if (c4 < c4_n) {
       if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * (c4_lo + c4));
-      if (p.graph_bias && e1 > e0) gb[j] = ldg_cached(p.graph_bias + (int64_t)g * p.C + 4 * (c4_lo + c4));
+      if (p.graph_bias && e1 > e0) gb[j] = ldg_cached(p.graph_bias + (int64_t)g * p.ldgb + 4 * (c4_lo + c4));
     }
   }
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
     const int g = p.node_graph[i0 + node];
     if (h == 0) gid_s[node] = g;
     float v = p.a_node[(int64_t)(i0 + node) * p.lda + H + h];
-    if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
+    if (p.a_graph) v += p.a_graph[(int64_t)g * p.ldag + h];
     tgt_s[t] = v;
   }
   __syncthreads();
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
       const int c4 = lane + 32 * j;
       if (c4 < C4) {
         if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * c4);
-        if (p.graph_bias && r1 > r0) gb[j] = ldg_cached(p.graph_bias + (int64_t)gid_s[node] * p.C + 4 * c4);
+        if (p.graph_bias && r1 > r0) gb[j] = ldg_cached(p.graph_bias + (int64_t)gid_s[node] * p.ldgb + 4 * c4);
       }
     }
 #pragma unroll 2
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(512) gat_hop_staged_kernel(const HopParams p, 
   for (int t = tid; t < n * H; t += nthreads) {
     const int node = t / H, h = t - node * H;
     float v = p.a_node[(int64_t)(n0 + node) * p.lda + H + h];
-    if (p.a_graph) v += p.a_graph[(int64_t)g * H + h];
+    if (p.a_graph) v += p.a_graph[(int64_t)g * p.ldag + h];
     tgt_s[t] = v;
   }
   for (int k = tid; k < eg; k += nthreads) src_s[k] = p.col_src[e0 + k] - n0;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(512) gat_hop_staged_kernel(const HopParams p, 
         if (c4 < w4) {
           float4 skip = make_float4(0.f, 0.f, 0.f, 0.f), gb = skip;
           if (p.h_prev) skip = ldg_stream(p.h_prev + (int64_t)(n0 + node) * p.C + 4 * (c4_lo + c4));
-          if (p.graph_bias && has_in) gb = ldg_cached(p.graph_bias + (int64_t)g * p.C + 4 * (c4_lo + c4));
+          if (p.graph_bias && has_in) gb = ldg_cached(p.graph_bias + (int64_t)g * p.ldgb + 4 * (c4_lo + c4));
           epilogue_store4(p, n0 + node, c4_lo + c4, acc[t][j], 1.0f / H, p.graph_bias != nullptr && has_in, gb,
                           p.h_prev != nullptr, skip);
         }
@@ -628,6 +628,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->num_nodes < 0 || a->num_edges < 0 || a->num_graphs < 0 || H <= 0 || C <= 0) return GVQA_ERR_BAD_SHAPE;
   if (a->num_nodes >= (1ll << 31) || a->num_edges >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
   if (a->ldx < (int64_t)H * C || a->lde < H || (a->ld_a_node != 0 && a->ld_a_node < 2 * H)) return GVQA_ERR_BAD_SHAPE;
+  if ((a->ld_graph_bias != 0 && a->ld_graph_bias < C) || (a->ld_a_graph != 0 && a->ld_a_graph < H)) return GVQA_ERR_BAD_SHAPE;
   if (a->num_nodes == 0) return GVQA_OK;
   if (!a->x_l || !a->a_node || !a->rowptr || !a->node_graph || !a->h_out) return GVQA_ERR_NULL_POINTER;
   if (a->num_edges > 0 && (!a->a_edge || !a->col_src)) return GVQA_ERR_NULL_POINTER;
@@ -635,7 +636,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
   if (a->variant < 0 || (a->variant > 4 && (a->variant < 104 || a->variant > 132))) return GVQA_ERR_UNSUPPORTED;
-  if ((a->ldx & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
+  if ((a->ldx & 3) || (a->ld_graph_bias & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
     return GVQA_ERR_MISALIGNED;
@@ -646,6 +647,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.node_graph = a->node_graph; p.h_prev = a->h_prev; p.bias = a->bias; p.ep_scale = a->ep_scale;
   p.ep_shift = a->ep_shift; p.h_out = a->h_out; p.alpha_out = a->alpha_out;
   p.ldx = a->ldx; p.lde = a->lde; p.lda = a->ld_a_node > 0 ? a->ld_a_node : 2 * H;
+  p.ldgb = a->ld_graph_bias > 0 ? a->ld_graph_bias : C; p.ldag = a->ld_a_graph > 0 ? a->ld_a_graph : H;
   p.N = (int32_t)a->num_nodes; p.E = (int32_t)a->num_edges; p.B = (int32_t)a->num_graphs; p.C = C;
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -120,6 +120,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
                : "memory");
 }
 
+// same, with an L2 eviction-priority policy (createpolicy) attached to the written lines
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t smem_src, int c0, int c1,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -370,7 +384,10 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32);
+              if (dbg & 8)
+                tma_store_2d_hint(&map_c, stage, col0 + pass * 32, m0 + quarter * 32, l2_policy_evict_last());
+              else
+                tma_store_2d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }

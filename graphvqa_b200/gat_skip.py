@@ -206,13 +206,22 @@ class gat_seq(nn.Module):
                 shift.append((b - bn.running_mean.detach().double() * g * inv).float().contiguous())
         # tcgen05 projection: the collapsed a_l / a_r logit vectors ride along as 16 extra output columns
         # (8 used at H=4) so one GEMM yields x_l and a_node; split into tf32 hi/lo once
-        w_split = None
+        w_split = edge_split = ins_split = None
+        v_edge_all = torch.cat(v_edge).contiguous()                      # [hops*H, Fe]
         if w_h[0].is_cuda:
-            pad = 16 - (2 * self.convs[0].heads) % 16 if (2 * self.convs[0].heads) % 16 else 0
-            w_split = [_cabi.split_tf32(torch.cat([w, vn, vn.new_zeros(pad, vn.size(1))]))
-                       for w, vn in zip(w_h, v_node)]
+            def pad16(t):
+                r = (-t.size(0)) % 16
+                return torch.cat([t, t.new_zeros(r, t.size(1))]) if r else t
+            w_split = [_cabi.split_tf32(pad16(torch.cat([w, vn]))) for w, vn in zip(w_h, v_node)]
+            # pre-pass operands for the same GEMM: all hops' edge-logit vectors as one [hops*H (+pad), Fe] matrix,
+            # and per hop the instruction weights [C + H (+pad), D] = [W_ins_mean^T ; V_graph^T] stacked over hops
+            edge_split = _cabi.split_tf32(pad16(v_edge_all))
+            ins_rows = [pad16(torch.cat([wi.t(), vg.t()])) for wi, vg in zip(w_ins, v_graph)]
+            ins_split = _cabi.split_tf32(torch.cat(ins_rows).contiguous())
+            ins_ld = ins_rows[0].size(0)
         self._packed = dict(key=key, w_h=w_h, w_split=w_split, w_ins=torch.stack(w_ins), v_node=v_node,
-                            v_graph=torch.stack(v_graph), v_edge=torch.cat(v_edge).contiguous(),
+                            v_graph=torch.stack(v_graph), v_edge=v_edge_all, edge_split=edge_split,
+                            ins_split=ins_split, ins_ld=ins_ld if ins_split is not None else 0,
                             scale=scale, shift=shift)
         return self._packed
 
@@ -235,11 +244,24 @@ class gat_seq(nn.Module):
 
         # hop-invariant pre-pass: all hops' edge logits in one sweep over edge_attr, and the
         # per-graph instruction terms of x_l and of the logits
-        a_edge_all = (_cabi.skinny_matmul(edge_attr, pk["v_edge"]) if e > 0
-                      else x.new_zeros(1, num_hops * heads))                    # [E, hops*H]
-        with _strict_fp32_matmul():
-            graph_bias_all = torch.bmm(ins, pk["w_ins"])                        # [hops, B, C]
-            a_graph_all = torch.bmm(ins, pk["v_graph"])                         # [hops, B, H]
+        tensor_core = self.projection == "3xtf32"
+        if e == 0:
+            a_edge_all = x.new_zeros(1, num_hops * heads)
+        elif tensor_core:
+            a_edge_all = _cabi.proj_gemm_3xtf32(edge_attr, *pk["edge_split"])   # [E, hops*H (+pad)], one sweep
+        else:
+            a_edge_all = _cabi.skinny_matmul(edge_attr, pk["v_edge"])           # [E, hops*H]
+        if tensor_core:
+            # one GEMM for every hop's per-graph terms: rows = (hop, graph), columns = (hop', C + H); only the
+            # hop == hop' blocks are used (the cross blocks are wasted flops, ~5 us, cheaper than 5 launches)
+            ld = pk["ins_ld"]
+            g_all = _cabi.proj_gemm_3xtf32(ins.view(num_hops * b, -1), *pk["ins_split"]).view(num_hops, b, num_hops, ld)
+            graph_bias_all = [g_all[i, :, i, :c] for i in range(num_hops)]      # [B, C] views, row stride hops*ld
+            a_graph_all = [g_all[i, :, i, c:c + heads] for i in range(num_hops)]
+        else:
+            with _strict_fp32_matmul():
+                graph_bias_all = torch.bmm(ins, pk["w_ins"])                    # [hops, B, C]
+                a_graph_all = torch.bmm(ins, pk["v_graph"])                     # [hops, B, H]
 
         h = x
         hops = []

@@ -5,7 +5,9 @@ batch (``x, edge_index, edge_attr, instr_vectors, batch`` -- the arguments of th
 ``gat_seq.forward``, gat_skip.py:249), moves them to the GPU, builds the CSR, runs the hop stack and
 returns the node states in pinned host memory.  Consecutive batches are software-pipelined over three
 CUDA streams and ``depth`` device slots: the H2D copy of batch i+1 and the D2H copy of batch i-1
-overlap the kernels of batch i (PCIe is full duplex).  With ``use_cuda_graph`` the per-slot compute
+overlap the kernels of batch i (PCIe is full duplex).  ``depth`` = 3 keeps the H2D engine saturated: with 2
+slots the host has to wait for batch i-2's result before it may enqueue batch i's copy, which left the link
+idle ~45 % of the time (profiles/microbench/e2e_probe.py: 1.75 ms -> 0.98 ms per cfg2 batch, the PCIe bound).  With ``use_cuda_graph`` the per-slot compute
 (CSR build + pre-pass + hops) is captured once per input shape and replayed.
 """
 import torch
@@ -29,7 +31,7 @@ class _Slot:
 
 
 class GatSeqHostRunner:
-    def __init__(self, model, device, depth=2, use_cuda_graph=True, max_nodes_per_graph=0,
+    def __init__(self, model, device, depth=3, use_cuda_graph=True, max_nodes_per_graph=0,
                  max_in_edges_per_graph=0):
         self.model, self.device, self.depth = model, torch.device(device), depth
         self.use_cuda_graph = use_cuda_graph

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVQA_ABI_VERSION 1
+#define GVQA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GVQA_API __attribute__((visibility("default")))
@@ -145,6 +145,9 @@ typedef struct gvqa_gat_hop_args {
   int32_t max_nodes_per_graph;    /* loader hints (0 = unknown) that size the shared-memory staged  */
   int32_t max_in_edges_per_graph; /* kernel; never a correctness input (oversize graphs fall back)   */
   int32_t variant;         /* 0 = auto, 1 = warp-per-node gather, 2 = TMA smem-staged, 3 = block-phase gather */
+  int64_t ld_graph_bias;   /* row stride of graph_bias in floats; 0 = dense (C); multiple of 4            */
+  int64_t ld_a_graph;      /* row stride of a_graph in floats; 0 = dense (H).  Both terms may be column
+                              blocks of one pre-pass GEMM output                                          */
 } gvqa_gat_hop_args;
 
 GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* args, void* stream);
