@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-hop launch at cfg2 from the committed ncu --set full
+# capture (cold L2; the 15.7 MB output is still dirty in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES = 85604864
+NCU_TRAFFIC_SOURCE = "profiles/r01/hop_full_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
 UNIT = "questions/s"
@@ -267,6 +271,39 @@ def run_engine(args, rank, local_rank, world):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = algo / (hop_us * 1e-6) / 1e9
 
+        # ---------------- fused-hop time inside the replayed graph (differential) ----------------
+        # The bracket above puts two event records around every launch; an event pair around an EMPTY stream
+        # position already reads ~2.7 us on this hardware (profiles/microbench/event_overhead.py).  Second
+        # view: replay the step graphs with and without the hop launches (the GEMMs' time does not depend on
+        # the data) and attribute the difference to the hops, launch gaps as they really are in the graph.
+        hop_in_graph_us = None
+        if graphs is not None:
+            model.skip_hop_launch = True
+            for r in range(R):
+                step(dev_sets[r])
+            torch.cuda.synchronize()
+            graphs_nohop = []
+            for r in range(R):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    step(dev_sets[r])
+                graphs_nohop.append(gph)
+            model.skip_hop_launch = False
+
+            def timed(gs):
+                a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(args.steps):
+                    gs[i % R].replay()
+                z.record(); torch.cuda.synchronize()
+                return a.elapsed_time(z) / args.steps
+            for gs in (graphs, graphs_nohop):
+                timed(gs)
+            full = min(timed(graphs) for _ in range(3))
+            nohop = min(timed(graphs_nohop) for _ in range(3))
+            hop_in_graph_us = 1e3 * (full - nohop) / hops
+            del graphs_nohop
+
         # ---------------- end to end: pinned host buffers -> H2D -> hot path -> D2H --------------
         # through the public host-buffer API (graphvqa_b200.host_api.GatSeqHostRunner): copies of
         # neighbouring batches overlap the kernels of the current one (3 streams, 3 device slots).
@@ -295,6 +332,11 @@ def run_engine(args, rank, local_rank, world):
 
     if rank != 0:
         return
+    if hop_in_graph_us:
+        primary_us, primary_method = hop_in_graph_us, "in_graph_differential"
+    else:
+        primary_us, primary_method = hop_us, "event_bracket"
+    primary_achieved = algo / (primary_us * 1e-6) / 1e9
     base = cpu_baseline(cfg, steps=3, warmup=1) if not args.skip_cpu else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -310,12 +352,17 @@ def run_engine(args, rank, local_rank, world):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": n * c * 4},
         "gpu_launches": args.steps * (5 + 1 + 2 * hops),
-        "roofline": {"bound": "hbm", "kernel": "gat_hop (gvqa_gat_hop_f32)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": algo, "avg_launch_us": hop_us,
-                     "launches_timed": len(hop_ms),
-                     "note": "timed in situ (eager launches, CUDA events around each hop launch); x_l was "
-                             "just written by the projection GEMM so part of it is L2-resident"},
+        "roofline": {"bound": "hbm", "kernel": "gat_hop_block_kernel (gvqa_gat_hop_f32)",
+                     "achieved": primary_achieved, "peak": peak, "unit": "GB/s", "frac": primary_achieved / peak,
+                     "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo, "avg_launch_us": primary_us, "method": primary_method,
+                     "bracketed_us": hop_us, "bracketed_frac": achieved / peak, "launches_bracketed": len(hop_ms),
+                     "in_graph_us": hop_in_graph_us,
+                     "note": "in_graph_differential: CUDA events around K replays of the step graph minus K replays of the "
+                             "same graph captured without the 5 fused-hop launches, per hop (the launch as it runs in "
+                             "the timed region).  bracketed_*: eager launches with an event pair around every hop "
+                             "launch of K steps; an event pair around an empty stream position already reads ~2.7 us "
+                             "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"},
     }
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}

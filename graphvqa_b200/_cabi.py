@@ -52,6 +52,7 @@ SIGNATURES = {
                                                 _c_f32, _c_i32, _c_vp]),
     "gvqa_debug_set_gemm_trace": (None, [_c_vp]),
     "gvqa_debug_set_gemm_flags": (None, [ctypes.c_int]),
+    "gvqa_debug_set_hop_trace": (None, [_c_vp]),
     "gvqa_split_tf32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_proj_gemm_3xtf32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                              _c_i32, _c_vp]),

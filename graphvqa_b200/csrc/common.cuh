@@ -112,9 +112,4 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
-// L2 prefetch of `bytes` (multiple of 16, 16-byte aligned) by the TMA engine; no destination, no completion.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
-
 }  // namespace gvqa

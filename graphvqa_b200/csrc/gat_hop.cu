@@ -25,7 +25,14 @@ namespace gvqa {
 
 constexpr int kEdgeChunk = 32;  // in-edges whose alpha are staged per warp at a time
 
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct HopParams {
+  unsigned long long* trace;   // debug only (gvqa_debug_set_hop_trace): [grid][8] globaltimer stamps per CTA
   const float* __restrict__ x_l;
   const float* __restrict__ graph_bias;
   const float* __restrict__ a_node;
@@ -208,9 +215,10 @@ constexpr int kBlkNodes = 16;     // max destination nodes per CTA (the launch p
 constexpr int kBlkThreads = 128;  // 4 warps; warp w owns nodes w, w+4, w+8, w+12 of the CTA
 constexpr int kBlkEdgeCap = 256;  // in-edges of the CTA's nodes staged in shared memory
 
-template <int J, int H, int kBlkThreads = 128, int kBlkNodes = 16, int kBlkEdgeCap = 256, bool kPrefetch = false>
+template <int J, int H, int kBlkThreads = 128, int kBlkNodes = 16, int kBlkEdgeCap = 256>
 __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_kernel(const HopParams p, const int npc) {
   constexpr int kWarps = kBlkThreads / 32;
+  static_assert(kBlkNodes * H <= kBlkThreads || H > 8, "one (node, head) pair per thread in the prologue");
   __shared__ int32_t rp_s[kBlkNodes + 1];
   __shared__ int32_t gid_s[kBlkNodes];
   __shared__ float tgt_s[kBlkNodes * H];
@@ -221,29 +229,22 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
   const int i0 = blockIdx.x * npc;
   const int nn = min(npc, p.N - i0);
   const int C4 = p.C >> 2;
+#define GVQA_HOP_TRACE(col) do { if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 8 + (col)] = gtime_ns(); } while (0)
+  GVQA_HOP_TRACE(0);
 
-  // ---- start the HBM stream before the topology is known: the projected rows and skip rows of this
-  // CTA's own nodes are pulled into L2 by the TMA engine (one bulk prefetch per row) while the
-  // dependent index round trips below are in flight.  Scene graphs are small and carry a self-loop
-  // per node (gqa_dataset_entry.py:292-297), so these are exactly the rows the graph's CTAs gather.
-  if (kPrefetch) {
-    for (int t = tid; t < nn; t += kBlkThreads) {
-      bulk_prefetch_l2(p.x_l + (int64_t)(i0 + t) * p.ldx, (uint32_t)(H * p.C * 4));
-      if (p.h_prev) bulk_prefetch_l2(p.h_prev + (int64_t)(i0 + t) * p.C, (uint32_t)(p.C * 4));
-    }
-  }
-
-  // ---- round trip 1: row pointers, graph ids, target-side logit terms ----------------------
+  // ---- round trip 1: row pointers (the only thing the first barrier waits for).  The target-side logit
+  // terms (a DRAM access: a_node lives in the GEMM's output rows) and the graph ids are requested now but
+  // consumed after the second barrier, so their latency overlaps round trips 2+3 -------------------------
   for (int t = tid; t <= nn; t += kBlkThreads) rp_s[t] = p.rowptr[i0 + t];
-  for (int t = tid; t < nn * H; t += kBlkThreads) {
-    const int node = t / H, h = t - node * H;
-    const int g = p.node_graph[i0 + node];
-    if (h == 0) gid_s[node] = g;
-    float v = p.a_node[(int64_t)(i0 + node) * p.lda + H + h];
-    if (p.a_graph) v += p.a_graph[(int64_t)g * p.ldag + h];
-    tgt_s[t] = v;
+  float tg_reg = 0.f;
+  int g_reg = 0;
+  const int my_node = tid / H, my_head = tid - my_node * H;
+  if (tid < nn * H) {
+    g_reg = p.node_graph[i0 + my_node];
+    tg_reg = p.a_node[(int64_t)(i0 + my_node) * p.lda + H + my_head];
   }
   __syncthreads();
+  GVQA_HOP_TRACE(1);
   const int eA = rp_s[0], eC = rp_s[nn] - eA;
 
   if (eC > kBlkEdgeCap) {
@@ -261,29 +262,32 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
 #pragma unroll
     for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_node[(int64_t)src * p.lda + h] + p.a_edge[e * p.lde + h];
   }
+  if (tid < nn * H) {
+    if (p.a_graph) tg_reg += p.a_graph[(int64_t)g_reg * p.ldag + my_head];
+    tgt_s[tid] = tg_reg;
+    if (my_head == 0) gid_s[my_node] = g_reg;
+  }
   __syncthreads();
+  GVQA_HOP_TRACE(2);
 
-  // ---- softmax: one thread per (node, head), sequential over that node's in-edges -----------
-  for (int t = tid; t < nn * H; t += kBlkThreads) {
-    const int node = t / H, h = t - node * H;
-    const int r0 = rp_s[node] - eA, r1 = rp_s[node + 1] - eA;
-    const float tg = tgt_s[t];
+  // ---- softmax: one thread per (node, head).  The passes over the node's in-edges only READ shared memory
+  // (the logit is recomputed instead of being written back), so the unrolled iterations overlap instead of
+  // forming one long load-store chain ----------------------------------------------------------
+  if (tid < nn * H) {
+    const int r0 = rp_s[my_node] - eA, r1 = rp_s[my_node + 1] - eA;
+    const float tg = tg_reg;
+    const int h = my_head;
     float mx = -INFINITY;
-    for (int k = r0; k < r1; ++k) {
-      const float l = leaky_relu(alpha_s[k * H + h] + tg, p.slope);
-      alpha_s[k * H + h] = l;
-      mx = fmaxf(mx, l);
-    }
+#pragma unroll 4
+    for (int k = r0; k < r1; ++k) mx = fmaxf(mx, leaky_relu(alpha_s[k * H + h] + tg, p.slope));
     float sum = 0.f;
-    for (int k = r0; k < r1; ++k) {
-      const float ex = expf(alpha_s[k * H + h] - mx);
-      alpha_s[k * H + h] = ex;
-      sum += ex;
-    }
+#pragma unroll 4
+    for (int k = r0; k < r1; ++k) sum += expf(leaky_relu(alpha_s[k * H + h] + tg, p.slope) - mx);
     const float inv = 1.0f / (sum + 1e-16f);
+#pragma unroll 4
     for (int k = r0; k < r1; ++k) {
-      const float a = alpha_s[k * H + h] * inv;
-      alpha_s[k * H + h] = a;
+      const float a = expf(leaky_relu(alpha_s[k * H + h] + tg, p.slope) - mx) * inv;
+      alpha_s[k * H + h] = a;     // this thread is the only reader and writer of column h of these rows
       if (p.alpha_out) {
         const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
         p.alpha_out[e * H + h] = a;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
     }
   }
   __syncthreads();
+  GVQA_HOP_TRACE(3);
 
   // ---- weighted gather: warp w owns nodes w, w+4, ...; 2 edges x H x J 128-bit loads in flight
 #pragma unroll 1
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
                         p.h_prev != nullptr, skip[j]);
     }
   }
+  if (p.trace && lane == 0 && wid < 4) p.trace[(size_t)blockIdx.x * 8 + 4 + wid] = gtime_ns();   // per-warp finish
 }
 
 template <int J, int H>
@@ -342,10 +348,7 @@ static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   } else {
     int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
     npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
-    if (variant == 4)
-      gat_hop_block_kernel<J, H, 128, 16, 256, true><<<(unsigned)((p.N + npc - 1) / npc), kBlkThreads, 0, stream>>>(p, npc);
-    else
-      gat_hop_block_kernel<J, H><<<(unsigned)((p.N + npc - 1) / npc), kBlkThreads, 0, stream>>>(p, npc);
+    gat_hop_block_kernel<J, H><<<(unsigned)((p.N + npc - 1) / npc), kBlkThreads, 0, stream>>>(p, npc);
   }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
@@ -621,6 +624,9 @@ static int launch_staged(const HopParams& p, const StagedPlan& pl, cudaStream_t 
 
 }  // namespace gvqa
 
+static unsigned long long* g_hop_trace = nullptr;   // debug only
+extern "C" GVQA_API void gvqa_debug_set_hop_trace(unsigned long long* device_buffer) { g_hop_trace = device_buffer; }
+
 extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* stream_) {
   using namespace gvqa;
   if (!a) return GVQA_ERR_NULL_POINTER;
@@ -635,13 +641,14 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->epilogue != GVQA_EPI_NONE && (!a->ep_scale || !a->ep_shift)) return GVQA_ERR_NULL_POINTER;
   if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
-  if (a->variant < 0 || (a->variant > 4 && (a->variant < 104 || a->variant > 132))) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || (a->variant > 3 && (a->variant < 104 || a->variant > 132))) return GVQA_ERR_UNSUPPORTED;
   if ((a->ldx & 3) || (a->ld_graph_bias & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
     return GVQA_ERR_MISALIGNED;
 
   HopParams p;
+  p.trace = g_hop_trace;
   p.x_l = a->x_l; p.graph_bias = a->graph_bias; p.a_node = a->a_node; p.a_graph = a->a_graph; p.a_edge = a->a_edge;
   p.rowptr = a->rowptr; p.col_src = a->col_src; p.perm = a->perm; p.graph_ptr = a->graph_ptr;
   p.node_graph = a->node_graph; p.h_prev = a->h_prev; p.bias = a->bias; p.ep_scale = a->ep_scale;
@@ -664,7 +671,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
       case 8: return launch_staged<8>(p, plan, stream);
     }
   }
-  const int variant = a->variant == 1 ? 1 : (a->variant >= 100 ? a->variant : (a->variant == 4 ? 4 : 3));
+  const int variant = a->variant == 1 ? 1 : (a->variant >= 100 ? a->variant : 3);
   switch (H) {
     case 1: return dispatch_flat<1>(p, variant, stream);
     case 2: return dispatch_flat<2>(p, variant, stream);

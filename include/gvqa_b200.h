@@ -176,6 +176,9 @@ GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer);
 /* Debug only: bit0 skip TMA loads, bit1 skip the A converters, bit2 skip the epilogue (results are then wrong;
  * used to attribute kernel time in profiles/microbench/gemm_dbg.py).  0 = production behaviour. */
 GVQA_API void gvqa_debug_set_gemm_flags(int flags);
+/* Debug only: per-CTA %globaltimer stamps of the block hop kernel ([grid][8] uint64: start, row pointers loaded,
+ * logit terms loaded, softmax done, finish time of warps 0..3); NULL disables.  profiles/microbench/hop_trace.py */
+GVQA_API void gvqa_debug_set_hop_trace(unsigned long long* device_buffer);
 GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream);
 GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const float* b_hi, const float* b_lo,
                                    int64_t ldb, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
