@@ -16,6 +16,7 @@ ABI_VERSION = 2
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK = 0, 1, 2, 3
+HOP_INPUTS_OLDER_THAN_PREDECESSOR = 1
 
 _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
                                         ctypes.c_void_p, ctypes.c_size_t)
@@ -32,7 +33,7 @@ class GatHopArgs(ctypes.Structure):
         ("num_nodes", _c_i64), ("num_edges", _c_i64), ("num_graphs", _c_i64),
         ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
         ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
-        ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64),
+        ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64), ("flags", _c_i32),
     ]
 
 
@@ -169,7 +170,7 @@ def skinny_matmul(x, v, out=None):
 def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, graph_bias=None,
             a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
-            max_in_edges_per_graph=0, variant=VARIANT_AUTO):
+            max_in_edges_per_graph=0, variant=VARIANT_AUTO, inputs_older_than_predecessor=False):
     require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
     require_f32c(h_out=h_out, h_prev=h_prev, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
     for name, t in (("graph_bias", graph_bias), ("a_graph", a_graph)):    # [B, .] row-strided views are fine
@@ -193,6 +194,7 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.variant = variant
     a.ld_graph_bias = graph_bias.stride(0) if graph_bias is not None and graph_bias.size(0) > 1 else 0
     a.ld_a_graph = a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else 0
+    a.flags = HOP_INPUTS_OLDER_THAN_PREDECESSOR if inputs_older_than_predecessor else 0
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
     return h_out

@@ -53,6 +53,7 @@ struct HopParams {
   int32_t N, E, B, C;
   float slope;
   int32_t epilogue;
+  int32_t early;   // GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR: topology / a_edge / a_graph may be read before pdl_wait()
 };
 
 // Softmax weights of the in-edges [e0,e1) of node `i` for all H heads, computed by one warp.
@@ -232,16 +233,21 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
 #define GVQA_HOP_TRACE(col) do { if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 8 + (col)] = gtime_ns(); } while (0)
   GVQA_HOP_TRACE(0);
 
-  // ---- round trip 1: row pointers (the only thing the first barrier waits for).  The target-side logit
-  // terms (a DRAM access: a_node lives in the GEMM's output rows) and the graph ids are requested now but
-  // consumed after the second barrier, so their latency overlaps round trips 2+3 -------------------------
+  // ---- round trips 1+2 touch only the per-batch topology and the pre-pass outputs, none of which the
+  // projection GEMM right before this kernel writes: under programmatic dependent launch they run while that
+  // GEMM is still draining on other SMs.  Row pointers first (the only thing the first barrier waits for);
+  // graph ids and their logit terms are requested now and consumed after the second barrier.
+  if (!p.early) {            // the caller made no promise about the previous kernel: wait first
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   for (int t = tid; t <= nn; t += kBlkThreads) rp_s[t] = p.rowptr[i0 + t];
   float tg_reg = 0.f;
   int g_reg = 0;
   const int my_node = tid / H, my_head = tid - my_node * H;
   if (tid < nn * H) {
     g_reg = p.node_graph[i0 + my_node];
-    tg_reg = p.a_node[(int64_t)(i0 + my_node) * p.lda + H + my_head];
+    if (p.a_graph) tg_reg = p.a_graph[(int64_t)g_reg * p.ldag + my_head];
   }
   __syncthreads();
   GVQA_HOP_TRACE(1);
@@ -249,21 +255,38 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
 
   if (eC > kBlkEdgeCap) {
     // hub-heavy block: per-warp chunked path (scratch carved from alpha_s / src_s)
+    if (p.early) {
+      pdl_wait();
+      pdl_launch_dependents();
+    }
     for (int node = wid; node < nn; node += kWarps)
       gather_node<J, H>(p, i0 + node, lane, 0, C4, alpha_s + wid * kEdgeChunk * H, src_s + wid * kEdgeChunk, true);
     return;
   }
 
-  // ---- round trips 2+3: sources, then source/edge logit terms, edge-parallel ----------------
+  // sources and edge logit terms, edge-parallel
   for (int k = tid; k < eC; k += kBlkThreads) {
     const int src = p.col_src[eA + k];
     const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
     src_s[k] = src;
 #pragma unroll
-    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_node[(int64_t)src * p.lda + h] + p.a_edge[e * p.lde + h];
+    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_edge[e * p.lde + h];
+  }
+
+  // ---- everything below reads what the previous kernel wrote (a_node and x_l come out of the GEMM) --------
+  if (p.early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
+
+  // round trip 3: source / target logit terms (each thread revisits the edges it staged above)
+  for (int k = tid; k < eC; k += kBlkThreads) {
+    const float* an = p.a_node + (int64_t)src_s[k] * p.lda;
+#pragma unroll
+    for (int h = 0; h < H; ++h) alpha_s[k * H + h] += an[h];
   }
   if (tid < nn * H) {
-    if (p.a_graph) tg_reg += p.a_graph[(int64_t)g_reg * p.ldag + my_head];
+    tg_reg += p.a_node[(int64_t)(i0 + my_node) * p.lda + H + my_head];
     tgt_s[tid] = tg_reg;
     if (my_head == 0) gid_s[my_node] = g_reg;
   }
@@ -348,7 +371,11 @@ static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   } else {
     int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
     npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
-    gat_hop_block_kernel<J, H><<<(unsigned)((p.N + npc - 1) / npc), kBlkThreads, 0, stream>>>(p, npc);
+    if (launch_pdl(2, gat_hop_block_kernel<J, H>, dim3((unsigned)((p.N + npc - 1) / npc)), dim3(kBlkThreads), 0, stream, p,
+                   npc) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return GVQA_ERR_CUDA;
+    }
   }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
@@ -657,6 +684,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.ldgb = a->ld_graph_bias > 0 ? a->ld_graph_bias : C; p.ldag = a->ld_a_graph > 0 ? a->ld_a_graph : H;
   p.N = (int32_t)a->num_nodes; p.E = (int32_t)a->num_edges; p.B = (int32_t)a->num_graphs; p.C = C;
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
+  p.early = (a->flags & GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR) ? 1 : 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   if (a->variant == 2) {

@@ -223,6 +223,11 @@ proj_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  // PDL: barrier init and the TMEM allocation above overlap the tail of the previous kernel (the fused hop whose
+  // output is this GEMM's A operand and which still reads the x_l buffer this GEMM overwrites)
+  pdl_wait();
+  pdl_launch_dependents();
+
   if (warp == 0) {
     // ===================== TMA producer: one elected lane runs the whole loop =====================
     if (elect_one()) {
@@ -485,8 +490,11 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const
   if (!attr_ok) return GVQA_ERR_CUDA;
   const int tiles = (int)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  proj_gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream_)>>>(
-      map_a, map_bhi, map_blo, map_c, (int)m, n, k, g_gemm_trace, g_gemm_dbg);
+  if (launch_pdl(1, proj_gemm_3xtf32_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, static_cast<cudaStream_t>(stream_),
+                 map_a, map_bhi, map_blo, map_c, (int)m, n, k, g_gemm_trace, g_gemm_dbg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return GVQA_ERR_CUDA;
+  }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }

@@ -293,7 +293,9 @@ class gat_seq(nn.Module):
                               ep_scale=None if last else pk["scale"][i], ep_shift=None if last else pk["shift"][i],
                               negative_slope=self.convs[i].negative_slope,
                               epilogue=_cabi.EPI_NONE if last else _cabi.EPI_AFFINE_RELU,
-                              variant=self.kernel_variant, **csr.hints())
+                              variant=self.kernel_variant,
+                              # topology and pre-pass outputs are older than the projection launched just above
+                              inputs_older_than_predecessor=fused_logits, **csr.hints())
             if self.hop_events is not None:
                 ev[1].record()
                 self.hop_events.append(ev)

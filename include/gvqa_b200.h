@@ -148,7 +148,16 @@ typedef struct gvqa_gat_hop_args {
   int64_t ld_graph_bias;   /* row stride of graph_bias in floats; 0 = dense (C); multiple of 4            */
   int64_t ld_a_graph;      /* row stride of a_graph in floats; 0 = dense (H).  Both terms may be column
                               blocks of one pre-pass GEMM output                                          */
+  int32_t flags;           /* GVQA_HOP_* bits                                                             */
 } gvqa_gat_hop_args;
+
+/* The block kernel is launched with programmatic stream serialization: its CTAs may start while the previous
+ * kernel of the stream drains, and block (griddepcontrol.wait) before touching anything that kernel wrote.
+ * Set this bit when rowptr / col_src / perm / node_graph / a_edge / a_graph were NOT written by the kernel
+ * launched immediately before this one (in gat_seq they come from the per-batch pre-pass, the predecessor is the
+ * projection GEMM): the index round trips then overlap the predecessor's tail.  x_l, a_node, h_prev and all
+ * outputs are always accessed after the wait.  Leaving the bit clear is always safe. */
+#define GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR 1
 
 GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* args, void* stream);
 
