@@ -330,6 +330,7 @@ def run_engine(args, rank, local_rank, world):
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_value = b * world / (float(t2) / args.steps / 1e3)
 
+    model.check_overflow()      # the fp16-split projection's range flag: the timed path computed valid results
     if rank != 0:
         return
     if hop_in_graph_us:
@@ -378,7 +379,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged, 3 block")
-    ap.add_argument("--projection", default="3xtf32", choices=["3xtf32", "cublas"])
+    ap.add_argument("--projection", default="3xf16", choices=["3xf16", "3xtf32", "cublas"])
     ap.add_argument("--gemm-flags", type=int, default=0, help="debug flags of the projection GEMM (experiments)")
     ap.add_argument("--l2-persist", type=int, default=0, help="MiB of L2 set aside to keep x_l resident (0 = off)")
     args = ap.parse_args()

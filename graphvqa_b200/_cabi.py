@@ -57,6 +57,9 @@ SIGNATURES = {
     "gvqa_split_tf32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_proj_gemm_3xtf32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                              _c_i32, _c_vp]),
+    "gvqa_split_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp]),
+    "gvqa_proj_gemm_3xf16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
+                                            _c_i32, _c_vp, _c_vp]),
     "gvqa_gine_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                _c_i32, _c_i32, _c_f32, _c_vp]),
     "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
@@ -291,6 +294,41 @@ def proj_gemm_3xtf32(a, b_hi, b_lo, out=None):
         check(lib().gvqa_proj_gemm_3xtf32(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
                                           ptr(out), out.stride(0), m, n, k, stream_handle(a.device)),
               "gvqa_proj_gemm_3xtf32")
+    return out
+
+
+def split_f16(w):
+    """w [rows, cols] float32 -> (hi, lo') float16 [rows, ld] with ld = cols rounded up to 8 (zero padded)."""
+    require_cuda(w)
+    if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1:
+        raise ValueError("split_f16: w must be float32 [rows, cols] with unit column stride")
+    rows, cols = w.shape
+    ld = (cols + 7) // 8 * 8
+    hi = torch.empty(rows, ld, dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(w.device):
+        check(lib().gvqa_split_f16(ptr(w), w.stride(0) if rows > 1 else cols, ptr(hi), ptr(lo), ld, rows, cols,
+                                   stream_handle(w.device)), "gvqa_split_f16")
+    return hi[:, :cols], lo[:, :cols]
+
+
+def proj_gemm_3xf16(a, b_hi, b_lo, out=None, overflow=None):
+    """out[M,N] = a[M,K] @ b[N,K]^T, fp32-level accuracy from fp16 tensor-core operands (|a| < 65504).
+    ``overflow``: optional int32[1] device tensor, set to 1 when an element of ``a`` does not fit fp16."""
+    require_cuda(a, b_hi, b_lo, overflow)
+    if a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
+        raise ValueError("proj_gemm_3xf16: a must be float32 [M,K] with unit column stride")
+    for t in (b_hi, b_lo):
+        if t.dtype != torch.float16 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 8:
+            raise ValueError("proj_gemm_3xf16: b_hi / b_lo must come from split_f16")
+    m, k = a.shape
+    n = b_hi.size(0)
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().gvqa_proj_gemm_3xf16(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
+                                         ptr(out), out.stride(0), m, n, k, ptr(overflow), stream_handle(a.device)),
+              "gvqa_proj_gemm_3xf16")
     return out
 
 

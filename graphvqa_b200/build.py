@@ -43,8 +43,8 @@ def _sources():
 def _digest(src):
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
-    for path in [os.path.join(CSRC, src), os.path.join(CSRC, "common.cuh"),
-                 os.path.join(INCLUDE, "gvqa_b200.h")]:
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    for path in [os.path.join(CSRC, src)] + headers + [os.path.join(INCLUDE, "gvqa_b200.h")]:
         with open(path, "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]

@@ -1,0 +1,319 @@
+// fp32-accurate node projection with fp16 tensor-core operands (see include/gvqa_b200.h:
+// gvqa_proj_gemm_3xf16, gvqa_split_f16).  Same job and same structure as proj_gemm.cu
+// (C[M,N] = A[M,K] @ B[N,K]^T for the reference's x_l = lin_l(x_cat), gat_skip.py:133), different split:
+//
+//   x = hi + lo,  hi = fp16(x),  lo = x - hi (exact in fp32),  lo' = fp16(lo * 2^11)
+//   C = A_hi*B_hi  +  2^-11 * (A_hi*B_lo' + A_lo'*B_hi)              (the lo*lo term is ~2^-22 relative, dropped)
+//
+// fp16 carries the same 11 significant bits as tf32, so the three-product result has the accuracy of the
+// 3xTF32 kernel, but tcgen05.mma.kind::f16 consumes K = 16 per instruction where kind::tf32 consumes K = 8
+// (profiles/r01/mma_rate_elect.txt: 4096 vs 2048 FMA/clk/SM), and the fp16 B tiles are half the bytes of the
+// tf32 ones, which matters because the tf32 kernel runs close to the SM's shared-memory bandwidth.  The lo
+// parts are scaled by 2^11 so they stay in fp16's normal range; the scale is undone once, in the epilogue.
+//
+// Range: fp16 tops out at 65504.  The converters track max|A| and raise a sticky flag (`overflow`, optional)
+// when an element would not fit; callers fall back to gvqa_proj_gemm_3xtf32 for such inputs.  GraphVQA's node
+// states are graph-LayerNorm / BatchNorm outputs of order 1-10.
+//
+// One k-block = 64 K-elements: A raw [128 x 64] fp32 (two 128B-swizzled [128 x 32] boxes), B_hi and B_lo'
+// [128 x 64] fp16 (one 128B-swizzled box each) = 64 KB per stage, 3 stages.  Warp roles, TMEM map, the early
+// TMEM release and the TMA-store epilogue are those of proj_gemm.cu.
+#include <cuda_fp16.h>
+
+#include "tcgen05_utils.cuh"
+
+namespace gvqa {
+namespace f16gemm {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;       // tile: rows of A, rows of B, k elements per k-block
+constexpr int kStages = 3;                          // shared-memory ring
+constexpr int kAStages = 2;                         // tensor-memory ring of split A tiles
+constexpr int kGemmThreads = 448;                   // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-13 epilogue
+constexpr int kConvThreads = 128;
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kAHalfBytes = kBM * 32 * 4;      // one [128 x 32] fp32 box = 16 KB
+constexpr uint32_t kABytes = 2 * kAHalfBytes;       // 32 KB
+constexpr uint32_t kBBytes = kBN * kBK * 2;         // 16 KB
+constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;       // 64 KB
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemSmall = 2 * kBN;            // accumulators: [0,128) hi*hi first K-half, [128,256) second, [256,384) lo terms
+constexpr uint32_t kTmemA = 3 * kBN;                // A ring: 2 stages x (32 columns hi | 32 columns lo'), 2 halves per column
+constexpr uint32_t kACols = kBK / 2;                // 32 TMEM columns per 64 fp16
+constexpr uint32_t kEpiStageBytes = 32 * 32 * 4;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + (kEpiThreads / 32) * kEpiStageBytes + 1024 + 256;
+constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {   // a -> low half (lower k), b -> high half
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&v);
+  return __half22float2(h);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int M,
+                       int N, int K, int32_t* __restrict__ overflow) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (kEpiThreads / 32) * kEpiStageBytes);
+  uint64_t* tma_full = bars;                        // [kStages]
+  uint64_t* smem_empty = bars + kStages;            // [kStages]
+  uint64_t* a_ready = bars + 2 * kStages;           // [kAStages]
+  uint64_t* a_empty = a_ready + kAStages;           // [kAStages]
+  uint64_t* acc_full = a_empty + kAStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + kBN - 1) / kBN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kblocks = (K + kBK - 1) / kBK;          // the ragged last k-block is zero-filled by TMA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&tma_full[s], 1);
+      mbar_init(&smem_empty[s], 1);
+    }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&a_ready[s], kConvThreads);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kEpiThreads);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();                 // set-up above overlaps the previous kernel's tail (see common.cuh)
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer: one elected lane runs the whole loop =====================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
+          unsigned char* st = smem + (size_t)s * kStageBytes;
+          mbar_expect_tx(&tma_full[s], kStageBytes);
+          tma_load_2d(st, &map_a, &tma_full[s], kb * kBK, m0);
+          tma_load_2d(st + kAHalfBytes, &map_a, &tma_full[s], kb * kBK + 32, m0);
+          tma_load_2d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
+          tma_load_2d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one elected lane runs the whole loop =====================
+    if (elect_one()) {
+      uint32_t it = 0, tile_it = 0;
+      const uint64_t desc0 = umma_desc(smem_u32(smem));   // descriptor of (base + c) == desc0 + (c >> 4)
+      const int half_kb = (kblocks + 1) / 2;              // first k-block of the second K-half
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+        // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, M = 128, N = tile width (x16)
+        const int n0 = (tile % n_tiles) * kBN;
+        const int ncols = min(kBN, (N - n0 + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        mbar_wait(acc_empty, (tile_it & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % kStages, ts = it & 1;
+          mbar_wait(&a_ready[ts], (it >> 1) & 1);         // implies tma_full[s]: the converters waited on it
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t b_hi = desc0 + (uint64_t)((s * kStageBytes + kABytes) >> 4), b_lo = b_hi + (kBBytes >> 4);
+          const uint32_t a_hi = tmem_base + kTmemA + ts * 2 * kACols, a_lo = a_hi + kACols;
+          const bool second = kb >= half_kb;
+          const bool chunk_first = kb == 0 || kb == half_kb;
+          const uint32_t d_big = tmem_base + (second ? (uint32_t)kBN : 0u), d_small = tmem_base + kTmemSmall;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {            // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
+            umma_f16_ts(d_small, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+            umma_f16_ts(d_small, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+            umma_f16_ts(d_big, a_hi + 8 * k, b_hi + 2 * k, idesc, !(chunk_first && k == 0));
+          }
+          umma_commit(&smem_empty[s]);
+          umma_commit(&a_empty[ts]);
+          if (kb == kblocks - 1) umma_commit(acc_full);
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converters (warps 2..5): thread = one row of the A tile ===============
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    uint32_t it = 0;
+    float amax = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages, ts = it & 1;
+        mbar_wait(&tma_full[s], (it / kStages) & 1);
+        mbar_wait(&a_empty[ts], ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t row_addr = smem_u32(smem + (size_t)s * kStageBytes) + (uint32_t)r * 128u;
+        const uint32_t ta = tmem_base + lane_base + kTmemA + (uint32_t)ts * 2 * kACols;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {             // the two [128 x 32] fp32 boxes of the stage
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int cidx = 0; cidx < 8; ++cidx) {           // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
+            const float4 v = lds128(row_addr + half * kAHalfBytes + (uint32_t)((cidx ^ (r & 7)) * 16));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            const uint32_t h01 = pack_half2(v.x, v.y), h23 = pack_half2(v.z, v.w);
+            const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
+            hi[2 * cidx] = h01;
+            hi[2 * cidx + 1] = h23;
+            lo[2 * cidx] = pack_half2((v.x - f01.x) * kLoScale, (v.y - f01.y) * kLoScale);
+            lo[2 * cidx + 1] = pack_half2((v.z - f23.x) * kLoScale, (v.w - f23.y) * kLoScale);
+          }
+          GVQA_TMEM_ST16(ta + half * 16, hi, 0);
+          GVQA_TMEM_ST16(ta + kACols + half * 16, lo, 0);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&a_ready[ts]);
+      }
+    }
+    if (overflow != nullptr && !(amax <= 65000.0f)) atomicOr(overflow, 1);   // also catches NaN / inf inputs
+  } else {
+    // ===================== epilogue (warps 6..13): TMEM -> registers, release TMEM, then TMA store =============
+    const int quarter = warp & 3;
+    const int chalf = warp >= 10 ? 1 : 0;
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+      mbar_wait(acc_full, tile_it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int col0 = n0 + chalf * 64;
+      float acc[64];
+      const bool live = col0 < N;
+      const bool two_chunks = kblocks >= 2;                // with a single k-block the second K-half is never written
+      if (live) {
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64 + pc * 16);
+          uint32_t rs[16], r0[16], r1[16];
+          GVQA_TMEM_LD16(rs, taddr + kTmemSmall);
+          GVQA_TMEM_LD16(r0, taddr);
+          if (two_chunks) GVQA_TMEM_LD16(r1, taddr + kBN);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float big = two_chunks ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
+            acc[pc * 16 + e] = fmaf(__uint_as_float(rs[e]), kLoUnscale, big);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(acc_empty);                              // TMEM is free: the next tile's MMAs may start
+      if (live) {
+        const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - 6) * kEpiStageBytes);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          if (col0 + pass * 32 < N) {
+            if (pass == 1) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(stage + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) * 16), acc[pass * 32 + 4 * j],
+                     acc[pass * 32 + 4 * j + 1], acc[pass * 32 + 4 * j + 2], acc[pass * 32 + 4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// hi = fp16(x), lo' = fp16((x - hi) * 2^11): the weight half of the split, done once at prepack time.
+// Rows are re-pitched from ld_in floats to ld_out halves (ld_out a multiple of 8, zero padded).
+__global__ void split_f16_kernel(const float* __restrict__ w, int64_t ld_in, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, int64_t ld_out, int64_t rows, int64_t cols) {
+  const int64_t total = rows * ld_out;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_out, c = i - r * ld_out;
+    const float x = c < cols ? w[r * ld_in + c] : 0.f;
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn((x - __half2float(h)) * kLoScale);
+  }
+}
+
+}  // namespace f16gemm
+}  // namespace gvqa
+
+using namespace gvqa;
+
+extern "C" GVQA_API int gvqa_split_f16(const float* w, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int64_t rows,
+                                       int64_t cols, void* stream_) {
+  if (rows < 0 || cols <= 0 || ld_in < cols || ld_out < cols || (ld_out & 7)) return GVQA_ERR_BAD_SHAPE;
+  if (rows == 0) return GVQA_OK;
+  if (!w || !hi || !lo) return GVQA_ERR_NULL_POINTER;
+  const int64_t blocks = (rows * ld_out + 255) / 256;
+  f16gemm::split_f16_kernel<<<(unsigned)(blocks < 4 * kNumSMs ? blocks : 4 * kNumSMs), 256, 0,
+                              static_cast<cudaStream_t>(stream_)>>>(w, ld_in, static_cast<__half*>(hi),
+                                                                    static_cast<__half*>(lo), ld_out, rows, cols);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                                             float* c, int64_t ldc, int64_t m, int32_t n, int32_t k, int32_t* overflow,
+                                             void* stream_) {
+  using namespace f16gemm;
+  if (m < 0 || n <= 0 || k <= 0 || lda < k || ldb < k || ldc < n || m >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (m == 0) return GVQA_OK;
+  if (!a || !b_hi || !b_lo || !c) return GVQA_ERR_NULL_POINTER;
+  if ((k & 3) || (lda & 3) || (ldb & 7) || (ldc & 3)) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(a) || !aligned16(b_hi) || !aligned16(b_lo) || !aligned16(c)) return GVQA_ERR_MISALIGNED;
+  CUtensorMap map_a, map_bhi, map_blo, map_c;
+  if (!make_map(&map_a, a, m, k, lda, kBM) || !make_map_f16(&map_bhi, b_hi, n, k, ldb, kBN) ||
+      !make_map_f16(&map_blo, b_lo, n, k, ldb, kBN) || !make_map(&map_c, c, m, n, ldc, 32, 32))
+    return GVQA_ERR_CUDA;
+  static const bool attr_ok =
+      cudaFuncSetAttribute(proj_gemm_3xf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) ==
+      cudaSuccess;
+  if (!attr_ok) return GVQA_ERR_CUDA;
+  const int tiles = (int)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  if (launch_pdl(1, proj_gemm_3xf16_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, static_cast<cudaStream_t>(stream_),
+                 map_a, map_bhi, map_blo, map_c, (int)m, n, k, overflow) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return GVQA_ERR_CUDA;
+  }
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}

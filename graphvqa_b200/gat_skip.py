@@ -166,9 +166,13 @@ class gat_seq(nn.Module):
         self.dropout = dropout
         self.in_channels, self.edge_attr_dim, self.ins_dim = in_channels, edge_attr_dim, ins_dim
         self.kernel_variant = _cabi.VARIANT_AUTO
-        # node projection h @ W_h^T: "3xtf32" = hand-written tcgen05 split-TF32 GEMM (fp32-level accuracy,
-        # ~2.5x cuBLAS fp32 SIMT), "cublas" = torch.mm with TF32 off
-        self.projection = "3xtf32"
+        # node projection h @ W_h^T, all with fp32-level accuracy:
+        #   "3xf16"  hand-written tcgen05 GEMM on fp16-split operands (default; inputs must fit fp16's range,
+        #            guarded by a device flag, see check_overflow)
+        #   "3xtf32" the same kernel structure on tf32-split operands (full fp32 range, ~1.4x slower)
+        #   "cublas" torch.mm with TF32 off (fp32 SIMT, ~6x slower)
+        self.projection = "3xf16"
+        self._overflow, self._overflow_pending = None, []
         # keep x_l (written by the GEMM, read once by the hop kernel) resident in L2 between the two
         self.l2_persist = False
         self.skip_hop_launch = False  # measurement only (bench.py): omit the fused-hop launches, results are garbage
@@ -183,7 +187,7 @@ class gat_seq(nn.Module):
 
     # ---- weight prepack ---------------------------------------------------------------------
     def packed(self):
-        key = _param_key(self)
+        key = (_param_key(self), self.projection)
         if self._packed is not None and self._packed["key"] == key:
             return self._packed
         f, fe = self.in_channels, self.edge_attr_dim
@@ -213,12 +217,13 @@ class gat_seq(nn.Module):
             def pad16(t):
                 r = (-t.size(0)) % 16
                 return torch.cat([t, t.new_zeros(r, t.size(1))]) if r else t
-            w_split = [_cabi.split_tf32(pad16(torch.cat([w, vn]))) for w, vn in zip(w_h, v_node)]
+            split = _cabi.split_f16 if self.projection == "3xf16" else _cabi.split_tf32
+            w_split = [split(pad16(torch.cat([w, vn]))) for w, vn in zip(w_h, v_node)]
             # pre-pass operands for the same GEMM: all hops' edge-logit vectors as one [hops*H (+pad), Fe] matrix,
             # and per hop the instruction weights [C + H (+pad), D] = [W_ins_mean^T ; V_graph^T] stacked over hops
-            edge_split = _cabi.split_tf32(pad16(v_edge_all))
+            edge_split = split(pad16(v_edge_all))
             ins_rows = [pad16(torch.cat([wi.t(), vg.t()])) for wi, vg in zip(w_ins, v_graph)]
-            ins_split = _cabi.split_tf32(torch.cat(ins_rows).contiguous())
+            ins_split = split(torch.cat(ins_rows).contiguous())
             ins_ld = ins_rows[0].size(0)
         self._packed = dict(key=key, w_h=w_h, w_split=w_split, w_ins=torch.stack(w_ins), v_node=v_node,
                             v_graph=torch.stack(v_graph), v_edge=v_edge_all, edge_split=edge_split,
@@ -245,18 +250,31 @@ class gat_seq(nn.Module):
 
         # hop-invariant pre-pass: all hops' edge logits in one sweep over edge_attr, and the
         # per-graph instruction terms of x_l and of the logits
-        tensor_core = self.projection == "3xtf32"
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._poll_overflow()
+        tensor_core = self.projection in ("3xtf32", "3xf16")
+        if self.projection == "3xf16":
+            if self._overflow is None or self._overflow.device != x.device:
+                self._overflow = torch.zeros(1, dtype=torch.int32, device=x.device)
+            flag = self._overflow
+
+            def gemm(a, split, out=None):
+                return _cabi.proj_gemm_3xf16(a, split[0], split[1], out=out, overflow=flag)
+        else:
+            def gemm(a, split, out=None):
+                return _cabi.proj_gemm_3xtf32(a, split[0], split[1], out=out)
         if e == 0:
             a_edge_all = x.new_zeros(1, num_hops * heads)
         elif tensor_core:
-            a_edge_all = _cabi.proj_gemm_3xtf32(edge_attr, *pk["edge_split"])   # [E, hops*H (+pad)], one sweep
+            a_edge_all = gemm(edge_attr, pk["edge_split"])                      # [E, hops*H (+pad)], one sweep
         else:
             a_edge_all = _cabi.skinny_matmul(edge_attr, pk["v_edge"])           # [E, hops*H]
         if tensor_core:
             # one GEMM for every hop's per-graph terms: rows = (hop, graph), columns = (hop', C + H); only the
             # hop == hop' blocks are used (the cross blocks are wasted flops, ~5 us, cheaper than 5 launches)
             ld = pk["ins_ld"]
-            g_all = _cabi.proj_gemm_3xtf32(ins.view(num_hops * b, -1), *pk["ins_split"]).view(num_hops, b, num_hops, ld)
+            g_all = gemm(ins.view(num_hops * b, -1), pk["ins_split"]).view(num_hops, b, num_hops, ld)
             graph_bias_all = [g_all[i, :, i, :c] for i in range(num_hops)]      # [B, C] views, row stride hops*ld
             a_graph_all = [g_all[i, :, i, c:c + heads] for i in range(num_hops)]
         else:
@@ -266,7 +284,7 @@ class gat_seq(nn.Module):
 
         h = x
         hops = []
-        fused_logits = self.projection == "3xtf32"
+        fused_logits = tensor_core
         hc = heads * c
         ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
         x_l = torch.empty(n, ldx, dtype=torch.float32, device=x.device)
@@ -276,7 +294,7 @@ class gat_seq(nn.Module):
             _cabi.l2_window(x_l, x.device, 1.0)
         for i in range(num_hops):
             if fused_logits:
-                _cabi.proj_gemm_3xtf32(h, pk["w_split"][i][0], pk["w_split"][i][1], out=x_l)
+                gemm(h, pk["w_split"][i], out=x_l)
             else:
                 with _strict_fp32_matmul():
                     torch.mm(h, pk["w_h"][i].t(), out=x_l)
@@ -304,4 +322,45 @@ class gat_seq(nn.Module):
                 hops.append(h)
         if self.l2_persist:
             _cabi.l2_window(None, x.device)
+        if self.projection == "3xf16" and not capturing:
+            self._queue_overflow_check()
         return (h, hops) if return_hops else h
+
+    # ---- fp16 range guard of the "3xf16" projection -----------------------------------------------
+    # The kernels OR a device flag when an input element does not fit fp16 (|x| >= 65504 or not finite).
+    # Reading it must not stall the stream, so every eager forward queues an asynchronous copy of the flag and
+    # the NEXT forward (or an explicit check_overflow()) looks at the copies that have landed.
+    def _queue_overflow_check(self):
+        host = torch.empty(1, dtype=torch.int32).pin_memory()
+        host.copy_(self._overflow, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._overflow_pending.append((host, ev))
+        del self._overflow_pending[:-8]
+
+    def _poll_overflow(self, wait=False):
+        keep = []
+        for host, ev in self._overflow_pending:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                if int(host) != 0:
+                    self._overflow_pending = []
+                    self._overflow.zero_()
+                    raise FloatingPointError(
+                        "gat_seq: an input of the fp16-split projection was outside fp16's range (|x| >= 65504 or "
+                        "not finite); the results of that forward are invalid. Set gat_seq.projection = '3xtf32' "
+                        "(full fp32 range, ~1.4x slower projection) and rerun.")
+            else:
+                keep.append((host, ev))
+        self._overflow_pending = keep
+
+    def check_overflow(self):
+        """Synchronising check of the fp16 range flag (after CUDA-graph replays or before trusting results)."""
+        if self.projection != "3xf16" or self._overflow is None:
+            return
+        self._poll_overflow(wait=True)
+        if int(self._overflow) != 0:
+            self._overflow.zero_()
+            raise FloatingPointError("gat_seq: input outside fp16's range in the fp16-split projection; use "
+                                     "gat_seq.projection = '3xtf32'")

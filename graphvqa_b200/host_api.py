@@ -22,6 +22,8 @@ class _Slot:
         self.dev = None            # static device input tensors
         self.out_dev = None        # device output (static when graph-captured)
         self.out_host = None       # pinned host output
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()   # fp16 range flag of this batch
+        self.host_in = None        # the caller's host tensors (for the full-range rerun)
         self.h2d_done = torch.cuda.Event()
         self.compute_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
@@ -78,9 +80,14 @@ class GatSeqHostRunner:
             slot.compute_done.record(self.s_compute)
         if slot.out_host is None or slot.out_host.shape != slot.out_dev.shape:
             slot.out_host = torch.empty(slot.out_dev.shape, dtype=slot.out_dev.dtype).pin_memory()
+        slot.host_in = host
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(slot.compute_done)
             slot.out_host.copy_(slot.out_dev, non_blocking=True)
+            flag = getattr(self.model, "_overflow", None)
+            if flag is not None:       # fp16-split projection: its range flag travels with the result
+                slot.flag_host.copy_(flag, non_blocking=True)
+                flag.zero_()
             if slot.graph is None:
                 slot.out_dev.record_stream(self.s_d2h)
             slot.d2h_done.record(self.s_d2h)
@@ -93,6 +100,18 @@ class GatSeqHostRunner:
         i.e. until ``depth`` more batches have been submitted)."""
         slot = self.slots[ticket % self.depth]
         slot.d2h_done.synchronize()
+        if int(slot.flag_host) != 0:
+            # an input did not fit fp16: redo this batch with the tf32-split projection (full fp32 range)
+            slot.flag_host.zero_()
+            prev = self.model.projection
+            self.model.projection = "3xtf32"
+            try:
+                with torch.no_grad(), torch.cuda.stream(self.s_compute):
+                    dev = {k: slot.host_in[k].to(self.device, non_blocking=True) for k in _KEYS}
+                    slot.out_host.copy_(self._forward(dev))
+                self.s_compute.synchronize()
+            finally:
+                self.model.projection = prev
         return slot.out_host
 
     def drain(self):

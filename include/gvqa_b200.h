@@ -193,6 +193,19 @@ GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const float* b_h
                                    int64_t ldb, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
                                    void* stream);
 
+/* Same projection with fp16 tensor-core operands: x = hi + 2^-11 * lo', hi = fp16(x), lo' = fp16((x - hi) * 2^11);
+ * C = A_hi*B_hi + 2^-11 (A_hi*B_lo' + A_lo'*B_hi), fp32 accumulation -- the accuracy of the 3xTF32 kernel at twice
+ * the tensor-core rate and 2/3 of its shared-memory traffic.  Requires |A| < 65504 (fp16 range): when `overflow`
+ * (device int32, may be NULL) is given, it is OR-ed with 1 if an element of A is outside the range or not finite;
+ * callers then redo the product with gvqa_proj_gemm_3xtf32.
+ * gvqa_split_f16 prepacks the weights: w [rows, cols] fp32 (row stride ld_in) -> hi, lo' [rows, ld_out] fp16,
+ * ld_out a multiple of 8 (zero padded).  k and lda multiples of 4, ldb a multiple of 8, ldc a multiple of 4. */
+GVQA_API int gvqa_split_f16(const float* w, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int64_t rows,
+                            int64_t cols, void* stream);
+GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                                  float* c, int64_t ldc, int64_t m, int32_t n, int32_t k, int32_t* overflow,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * GINE message passing: the propagate + self term of torch_geometric's GINEConv as called by
  * gine_seq.forward (baseline_and_test_models/pipeline_model_gine.py:652-665) on the concatenated

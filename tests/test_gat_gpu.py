@@ -241,7 +241,7 @@ def test_gat_seq_cfg4_shape_large_graphs():
 
 
 def test_gat_seq_projection_paths_agree():
-    """tcgen05 3xTF32 projection vs cuBLAS fp32 projection inside gat_seq: same result to 1e-5."""
+    """tcgen05 3xTF32 / 3xF16 projections vs cuBLAS fp32 projection inside gat_seq: same result to 2e-5."""
     cfg = dict(in_channels=300, out_channels=300, edge_attr_dim=300, ins_dim=512, num_ins=5, gat_heads=4)
     _, e = _pair(cfg, seed=51)
     ei, batch = random_graphs(20, 5, 40, 2.0, seed=6)
@@ -249,4 +249,24 @@ def test_gat_seq_projection_paths_agree():
     with torch.no_grad():
         e.projection = "3xtf32"; a = e(*args)
         e.projection = "cublas"; b = e(*args)
+        e.projection = "3xf16"; c = e(*args)
+    e.check_overflow()
     assert (a - b).abs().max() <= 2e-5
+    assert (c - b).abs().max() <= 2e-5
+
+
+def test_gat_seq_fp16_projection_flags_out_of_range_inputs():
+    """The default fp16-split projection refuses to return silently wrong results for |x| >= 65504."""
+    cfg = dict(in_channels=64, out_channels=64, edge_attr_dim=64, ins_dim=32, num_ins=2, gat_heads=4)
+    _, e = _pair(cfg, seed=53)
+    ei, batch = random_graphs(6, 4, 12, 2.0, seed=7)
+    args = [a.to(DEV) for a in _inputs(ei, batch, 6, 64, 64, 32, 2, seed=54)]
+    args[0][3, 5] = 1.0e5
+    with torch.no_grad():
+        e(*args)
+    with pytest.raises(FloatingPointError):
+        e.check_overflow()
+    e.projection = "3xtf32"                     # full-range path handles the same input
+    with torch.no_grad():
+        out = e(*args)
+    assert torch.isfinite(out).all()

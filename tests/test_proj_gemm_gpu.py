@@ -57,3 +57,70 @@ def test_proj_gemm_timing_report():
             fn()
         e1.record(); torch.cuda.synchronize()
         print("%s: %.1f us" % (name, e0.elapsed_time(e1) / 20 * 1e3))
+
+
+# ---- fp16-split variant (gvqa_proj_gemm_3xf16): same accuracy bar, plus the range guard --------------------
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 128), (7680, 2064, 512), (59, 1200, 300),
+                                   (1000, 2048, 512), (130, 260, 36), (7680, 1216, 300), (300, 32, 512)])
+def test_proj_gemm_3xf16_matches_fp64(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k + 1)
+    a = torch.randn(m, k, generator=g) * 3.0
+    b = torch.randn(n, k, generator=g) * 0.05
+    hi, lo = _cabi.split_f16(b.to(DEV))
+    recon = hi.double() + lo.double() / 2048.0
+    assert (recon.cpu() - b.double()).abs().max() <= 2.0 ** -21 * float(b.abs().max())
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = _cabi.proj_gemm_3xf16(a.to(DEV), hi, lo, overflow=flag).cpu()
+    assert int(flag) == 0
+    want = a.double() @ b.double().t()
+    err = (out.double() - want).abs().max()
+    err32 = ((a @ b.t()).double() - want).abs().max()
+    scale = float(want.abs().max())
+    assert err <= max(4 * float(err32), 2e-6 * scale), "3xF16 err %g vs fp32 err %g (scale %g)" % (err, err32, scale)
+
+
+def test_proj_gemm_3xf16_small_and_large_magnitudes():
+    """Blocks of A/B in fp16's subnormal range (values ~1e-6) next to blocks of order 1e3-1e4: the error stays at
+    fp32 level relative to each output row (tiny operands lose relative, not absolute, precision)."""
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(256, 256, generator=g)
+    a[:, :64] *= 1e-6
+    a[:, 64:128] *= 2.0e3
+    b = torch.randn(128, 256, generator=g) * 0.05
+    b[:32] *= 1e-5
+    hi, lo = _cabi.split_f16(b.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = _cabi.proj_gemm_3xf16(a.to(DEV), hi, lo, overflow=flag).cpu()
+    want = a.double() @ b.double().t()
+    # rows of `want` are dominated by the 2e4-scaled block; the bar is relative to each row's magnitude
+    rel = ((out.double() - want).abs().max(1).values / want.abs().max(1).values).max()
+    assert float(rel) <= 2e-6 and int(flag) == 0
+
+
+def test_proj_gemm_3xf16_flags_out_of_range_input():
+    a = torch.ones(128, 64)
+    a[5, 7] = 7.0e4
+    b = torch.ones(128, 64) * 0.01
+    hi, lo = _cabi.split_f16(b.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _cabi.proj_gemm_3xf16(a.to(DEV), hi, lo, overflow=flag)
+    assert int(flag) == 1
+
+
+def test_proj_gemm_3xf16_timing_report():
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(7680, 512, generator=g).to(DEV)
+    b = (torch.randn(2064, 512, generator=g) * 0.05).to(DEV)
+    hi, lo = _cabi.split_f16(b)
+    thi, tlo = _cabi.split_tf32(b)
+    out = torch.empty(7680, 2064, device=DEV)
+    for fn, name in ((lambda: _cabi.proj_gemm_3xf16(a, hi, lo, out=out), "3xf16"),
+                     (lambda: _cabi.proj_gemm_3xtf32(a, thi, tlo, out=out), "3xtf32")):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print("%s: %.1f us" % (name, e0.elapsed_time(e1) / 20 * 1e3))
