@@ -173,6 +173,7 @@ class gat_seq(nn.Module):
         #   "cublas" torch.mm with TF32 off (fp32 SIMT, ~6x slower)
         self.projection = "3xf16"
         self._overflow, self._overflow_pending = None, []
+        self._side = None
         # keep x_l (written by the GEMM, read once by the hop kernel) resident in L2 between the two
         self.l2_persist = False
         self.skip_hop_launch = False  # measurement only (bench.py): omit the fused-hop launches, results are garbage
@@ -231,17 +232,26 @@ class gat_seq(nn.Module):
                             scale=scale, shift=shift)
         return self._packed
 
-    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, csr=None, return_hops=False):
+    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, csr=None, return_hops=False, csr_hints=None):
         """x [N,F], edge_index [2,E] i64, edge_attr [E,Fe], instr_vectors [num_ins,B,D], batch [N] i64
-        -> h [N,F].  ``csr`` (a GraphCSR) may be passed to reuse the per-batch pre-pass."""
+        -> h [N,F].  ``csr`` (a GraphCSR) may be passed to reuse the per-batch pre-pass; otherwise it is built
+        here, on a side stream, concurrently with the pre-pass GEMMs and the first projection (none of which
+        needs the topology).  ``csr_hints``: optional max_nodes_per_graph / max_in_edges_per_graph loader hints."""
         _require_inference(self, x, edge_attr, instr_vectors)
         _cabi.require_cuda(x, edge_index, edge_attr, instr_vectors, batch)
         num_hops = len(self.convs)
         n, e = x.size(0), edge_index.size(1)
         b = instr_vectors.size(1)
         heads, c = self.convs[0].heads, self.convs[0].out_channels
+        side = None
         if csr is None:
-            csr = GraphCSR.build(edge_index, batch, b)
+            cur = torch.cuda.current_stream(x.device)
+            side = self._side_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                csr = GraphCSR.build(edge_index, batch, b, **(csr_hints or {}))
+            for t in (csr.rowptr, csr.col_src, csr.perm, csr.graph_ptr, csr.node_graph, csr.stats):
+                t.record_stream(cur)
         csr_d = csr.as_dict()
         pk = self.packed()
         x = x.contiguous().float()
@@ -299,6 +309,9 @@ class gat_seq(nn.Module):
                 with _strict_fp32_matmul():
                     torch.mm(h, pk["w_h"][i].t(), out=x_l)
                 _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
+            if side is not None:                # the hop is the first consumer of the topology
+                torch.cuda.current_stream(x.device).wait_stream(side)
+                side = None
             last = i == num_hops - 1
             h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
             if self.hop_events is not None:
@@ -325,6 +338,11 @@ class gat_seq(nn.Module):
         if self.projection == "3xf16" and not capturing:
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
+
+    def _side_stream(self, device):
+        if self._side is None or self._side.device != device:
+            self._side = torch.cuda.Stream(device)
+        return self._side
 
     # ---- fp16 range guard of the "3xf16" projection -----------------------------------------------
     # The kernels OR a device flag when an input element does not fit fp16 (|x| >= 65504 or not finite).

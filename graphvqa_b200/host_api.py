@@ -43,8 +43,7 @@ class GatSeqHostRunner:
         self.count = 0
 
     def _forward(self, d):
-        csr = GraphCSR.build(d["edge_index"], d["batch"], d["instr_vectors"].size(1), **self.hints)
-        return self.model(d["x"], d["edge_index"], d["edge_attr"], d["instr_vectors"], d["batch"], csr=csr)
+        return self.model(d["x"], d["edge_index"], d["edge_attr"], d["instr_vectors"], d["batch"], csr_hints=self.hints)
 
     @torch.no_grad()
     def submit(self, host):
