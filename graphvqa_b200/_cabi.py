@@ -60,6 +60,8 @@ SIGNATURES = {
     "gvqa_split_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp]),
     "gvqa_proj_gemm_3xf16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                             _c_i32, _c_vp, _c_vp]),
+    "gvqa_proj_gemm_3xf16_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64,
+                                                    _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "gvqa_gine_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                _c_i32, _c_i32, _c_f32, _c_vp]),
     "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
@@ -329,6 +331,25 @@ def proj_gemm_3xf16(a, b_hi, b_lo, out=None, overflow=None):
         check(lib().gvqa_proj_gemm_3xf16(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
                                          ptr(out), out.stride(0), m, n, k, ptr(overflow), stream_handle(a.device)),
               "gvqa_proj_gemm_3xf16")
+    return out
+
+
+def proj_gemm_3xf16_batched(a, b_hi, b_lo, overflow=None):
+    """out[z] = a[z] @ b[z]^T for a [Z,M,K] float32 (contiguous) and b_hi/b_lo [Z,N,K] float16 views of split_f16
+    output reshaped to [Z, N, ld] (one launch for all z)."""
+    require_cuda(a, b_hi, b_lo, overflow)
+    if a.dtype != torch.float32 or a.dim() != 3 or not a.is_contiguous():
+        raise ValueError("proj_gemm_3xf16_batched: a must be contiguous float32 [Z,M,K]")
+    for t in (b_hi, b_lo):
+        if t.dtype != torch.float16 or t.dim() != 3 or t.stride(2) != 1 or t.stride(1) % 8 or t.stride(0) % 8:
+            raise ValueError("proj_gemm_3xf16_batched: b_hi / b_lo must be [Z,N,K] views of split_f16 output")
+    z, m, k = a.shape
+    n = b_hi.size(1)
+    out = torch.empty(z, m, n, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().gvqa_proj_gemm_3xf16_batched(ptr(a), k, m * k, ptr(b_hi), ptr(b_lo), b_hi.stride(1), b_hi.stride(0),
+                                                 ptr(out), n, m * n, m, n, k, z, ptr(overflow),
+                                                 stream_handle(a.device)), "gvqa_proj_gemm_3xf16_batched")
     return out
 
 

@@ -57,7 +57,8 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
 __global__ void __launch_bounds__(kGemmThreads, 1)
 proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                        const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int M,
-                       int N, int K, int32_t* __restrict__ overflow) {
+                       int N, int K, int batch, int32_t* __restrict__ overflow) {
+  // all four tensor maps are 3-D [batch, rows, K]; a tile index decomposes into (batch z, row tile, column tile)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;
@@ -72,7 +73,8 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + kBN - 1) / kBN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int num_tiles = tiles_per_batch * batch;
   const int kblocks = (K + kBK - 1) / kBK;          // the ragged last k-block is zero-filled by TMA
 
   if (threadIdx.x == 0) {
@@ -107,16 +109,17 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+        const int z = tile / tiles_per_batch, t2 = tile - z * tiles_per_batch;
+        const int m0 = (t2 / n_tiles) * kBM, n0 = (t2 % n_tiles) * kBN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + (size_t)s * kStageBytes;
           mbar_expect_tx(&tma_full[s], kStageBytes);
-          tma_load_2d(st, &map_a, &tma_full[s], kb * kBK, m0);
-          tma_load_2d(st + kAHalfBytes, &map_a, &tma_full[s], kb * kBK + 32, m0);
-          tma_load_2d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0);
-          tma_load_2d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0);
+          tma_load_3d(st, &map_a, &tma_full[s], kb * kBK, m0, z);
+          tma_load_3d(st + kAHalfBytes, &map_a, &tma_full[s], kb * kBK + 32, m0, z);
+          tma_load_3d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0, z);
+          tma_load_3d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0, z);
         }
       }
     }
@@ -128,7 +131,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int half_kb = (kblocks + 1) / 2;              // first k-block of the second K-half
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, M = 128, N = tile width (x16)
-        const int n0 = (tile % n_tiles) * kBN;
+        const int n0 = ((tile % tiles_per_batch) % n_tiles) * kBN;
         const int ncols = min(kBN, (N - n0 + 15) & ~15);
         const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);
@@ -198,7 +201,8 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int chalf = warp >= 10 ? 1 : 0;
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+      const int z = tile / tiles_per_batch, t2 = tile - z * tiles_per_batch;
+      const int m0 = (t2 / n_tiles) * kBM, n0 = (t2 % n_tiles) * kBN;
       mbar_wait(acc_full, tile_it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int col0 = n0 + chalf * 64;
@@ -239,7 +243,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32);
+              tma_store_3d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32, z);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
@@ -290,30 +294,42 @@ extern "C" GVQA_API int gvqa_split_f16(const float* w, int64_t ld_in, void* hi, 
   return GVQA_OK;
 }
 
-extern "C" GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
-                                             float* c, int64_t ldc, int64_t m, int32_t n, int32_t k, int32_t* overflow,
-                                             void* stream_) {
+extern "C" GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
+                                                     const void* b_lo, int64_t ldb, int64_t stride_b, float* c,
+                                                     int64_t ldc, int64_t stride_c, int64_t m, int32_t n, int32_t k,
+                                                     int32_t batch, int32_t* overflow, void* stream_) {
   using namespace f16gemm;
-  if (m < 0 || n <= 0 || k <= 0 || lda < k || ldb < k || ldc < n || m >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (m < 0 || n <= 0 || k <= 0 || batch <= 0 || lda < k || ldb < k || ldc < n || m >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
   if (m == 0) return GVQA_OK;
   if (!a || !b_hi || !b_lo || !c) return GVQA_ERR_NULL_POINTER;
-  if ((k & 3) || (lda & 3) || (ldb & 7) || (ldc & 3)) return GVQA_ERR_UNSUPPORTED;
+  if ((k & 3) || (lda & 3) || (ldb & 7) || (ldc & 3) || (stride_a & 3) || (stride_b & 7) || (stride_c & 3))
+    return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(a) || !aligned16(b_hi) || !aligned16(b_lo) || !aligned16(c)) return GVQA_ERR_MISALIGNED;
+  const int64_t sa = batch > 1 ? stride_a : m * lda, sb = batch > 1 ? stride_b : (int64_t)n * ldb,
+                sc = batch > 1 ? stride_c : m * ldc;
   CUtensorMap map_a, map_bhi, map_blo, map_c;
-  if (!make_map(&map_a, a, m, k, lda, kBM) || !make_map_f16(&map_bhi, b_hi, n, k, ldb, kBN) ||
-      !make_map_f16(&map_blo, b_lo, n, k, ldb, kBN) || !make_map(&map_c, c, m, n, ldc, 32, 32))
+  if (!make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, batch, m, k, lda, sa, kBM, 32) ||
+      !make_map_3d(&map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, batch, n, k, ldb, sb, kBN, 64) ||
+      !make_map_3d(&map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, batch, n, k, ldb, sb, kBN, 64) ||
+      !make_map_3d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c, batch, m, n, ldc, sc, 32, 32))
     return GVQA_ERR_CUDA;
   static const bool attr_ok =
       cudaFuncSetAttribute(proj_gemm_3xf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) ==
       cudaSuccess;
   if (!attr_ok) return GVQA_ERR_CUDA;
-  const int tiles = (int)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
+  const int64_t tiles = ((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * batch;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   if (launch_pdl(1, proj_gemm_3xf16_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, static_cast<cudaStream_t>(stream_),
-                 map_a, map_bhi, map_blo, map_c, (int)m, n, k, overflow) != cudaSuccess) {
+                 map_a, map_bhi, map_blo, map_c, (int)m, n, k, (int)batch, overflow) != cudaSuccess) {
     (void)cudaGetLastError();
     return GVQA_ERR_CUDA;
   }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                                             float* c, int64_t ldc, int64_t m, int32_t n, int32_t k, int32_t* overflow,
+                                             void* stream_) {
+  return gvqa_proj_gemm_3xf16_batched(a, lda, 0, b_hi, b_lo, ldb, 0, c, ldc, 0, m, n, k, 1, overflow, stream_);
 }

@@ -37,6 +37,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // Round-to-nearest (ties away) fp32 -> tf32 kept in an fp32 container: add half an ulp of the
 // 10-bit mantissa, clear the 13 low bits.  Same result as cvt.rna.tf32.f32 for finite values, but
 // on the full-rate integer pipe (the converter warps do this for every element of A).
@@ -70,6 +78,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
                "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 
@@ -168,6 +182,20 @@ inline bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// batched variants: [batch, rows, K] with a batch stride (elements), box [1 x box_rows x box_cols]
+inline bool make_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, int64_t batch,
+                        int64_t rows, int64_t k, int64_t ld, int64_t batch_stride, int box_rows, int box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)batch_stride * elem_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // [rows, K] fp16 row-major (row stride ld halves, multiple of 8) -> 2-D map with a [box_rows x 64] 128B-swizzled box
 inline bool make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {

@@ -284,9 +284,15 @@ class gat_seq(nn.Module):
             # one GEMM for every hop's per-graph terms: rows = (hop, graph), columns = (hop', C + H); only the
             # hop == hop' blocks are used (the cross blocks are wasted flops, ~5 us, cheaper than 5 launches)
             ld = pk["ins_ld"]
-            g_all = gemm(ins.view(num_hops * b, -1), pk["ins_split"]).view(num_hops, b, num_hops, ld)
-            graph_bias_all = [g_all[i, :, i, :c] for i in range(num_hops)]      # [B, C] views, row stride hops*ld
-            a_graph_all = [g_all[i, :, i, c:c + heads] for i in range(num_hops)]
+            if self.projection == "3xf16":      # one batched launch: [hops, B, D] x [hops, C+H(+pad), D]^T
+                bh, bl = (t.unflatten(0, (num_hops, ld)) for t in pk["ins_split"])
+                g_all = _cabi.proj_gemm_3xf16_batched(ins, bh, bl, overflow=flag)            # [hops, B, ld]
+                graph_bias_all = [g_all[i, :, :c] for i in range(num_hops)]      # [B, C] views, row stride ld
+                a_graph_all = [g_all[i, :, c:c + heads] for i in range(num_hops)]
+            else:                               # one plain GEMM incl. the unused cross blocks (hop != hop')
+                g_all = gemm(ins.view(num_hops * b, -1), pk["ins_split"]).view(num_hops, b, num_hops, ld)
+                graph_bias_all = [g_all[i, :, i, :c] for i in range(num_hops)]  # row stride hops*ld
+                a_graph_all = [g_all[i, :, i, c:c + heads] for i in range(num_hops)]
         else:
             with _strict_fp32_matmul():
                 graph_bias_all = torch.bmm(ins, pk["w_ins"])                    # [hops, B, C]

@@ -205,6 +205,13 @@ GVQA_API int gvqa_split_f16(const float* w, int64_t ld_in, void* hi, void* lo, i
 GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
                                   float* c, int64_t ldc, int64_t m, int32_t n, int32_t k, int32_t* overflow,
                                   void* stream);
+/* `batch` independent products C[z] = A[z] @ B[z]^T in one launch (element strides between consecutive z; stride_a
+ * and stride_c multiples of 4, stride_b a multiple of 8): gat_seq's per-hop instruction terms
+ * [hops, B, D] x [hops, C+H, D]^T (gat_skip.py:256-264, split cat). */
+GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
+                                          const void* b_lo, int64_t ldb, int64_t stride_b, float* c, int64_t ldc,
+                                          int64_t stride_c, int64_t m, int32_t n, int32_t k, int32_t batch,
+                                          int32_t* overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GINE message passing: the propagate + self term of torch_geometric's GINEConv as called by

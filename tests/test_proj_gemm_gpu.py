@@ -124,3 +124,16 @@ def test_proj_gemm_3xf16_timing_report():
             fn()
         e1.record(); torch.cuda.synchronize()
         print("%s: %.1f us" % (name, e0.elapsed_time(e1) / 20 * 1e3))
+
+
+def test_proj_gemm_3xf16_batched_matches_fp64():
+    g = torch.Generator().manual_seed(12)
+    z, m, n, k = 5, 256, 528, 512
+    a = torch.randn(z, m, k, generator=g)
+    b = torch.randn(z * n, k, generator=g) * 0.05
+    hi, lo = _cabi.split_f16(b.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = _cabi.proj_gemm_3xf16_batched(a.to(DEV), hi.unflatten(0, (z, n)), lo.unflatten(0, (z, n)), overflow=flag).cpu()
+    want = torch.einsum("zmk,znk->zmn", a.double(), b.view(z, n, k).double())
+    assert int(flag) == 0
+    assert (out.double() - want).abs().max() <= 2e-6 * float(want.abs().max())
