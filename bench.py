@@ -345,14 +345,15 @@ def run_engine(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: %d synthetic GQA-shape scene graphs per GPU (30 nodes/60 edges), F=512, "
                                "D=512, 4 heads, 5-hop GAT-skip (gat_seq.forward: CSR build + edge-logit pre-pass + "
-                               "5 x (fp32 projection + fused hop))" % b,
+                               "5 x (fp32-accurate tcgen05 projection + fused hop))" % b,
                    "graphs_per_gpu": b, "parallelism": "graph-sharded x%d, no data-path collective" % world,
                    "l2_hygiene": "4 distinct input sets (~200 MB > 126 MB L2) rotated step to step",
                    "cuda_graph": graphs is not None},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": n * c * 4},
-        "gpu_launches": args.steps * (5 + 1 + 2 * hops),
+        # per step: 5 CSR kernels + edge-logit GEMM + batched instruction GEMM + hops x (projection GEMM + fused hop)
+        "gpu_launches": args.steps * (5 + 2 + 2 * hops),
         "roofline": {"bound": "hbm", "kernel": "gat_hop_block_kernel (gvqa_gat_hop_f32)",
                      "achieved": primary_achieved, "peak": peak, "unit": "GB/s", "frac": primary_achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,

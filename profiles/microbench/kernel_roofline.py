@@ -1,7 +1,8 @@
 """Every hand-written kernel of SURVEY.md section 8 at the BASELINE.json shapes: duration and algorithmic
 GB/s against the measured HBM peak.  Launches are queued behind a busy stream (no CPU launch gap) and L2 is
-flushed (zero-filled 192 MB) before each timed launch; durations are CUDA-event brackets, so each includes
-the ~2.7 us an event pair reads around nothing (event_overhead.py)."""
+flushed with CLEAN lines (a 256 MB buffer is read, not written: a zero-fill would leave 126 MB of dirty lines
+whose write-back is then billed to the kernel under test) before each timed launch; durations are CUDA-event
+brackets, so each includes the ~2.7 us an event pair reads around nothing (event_overhead.py)."""
 import json, os, sys, torch
 sys.path.insert(0, '/root/repo')
 import bench
@@ -11,11 +12,11 @@ from graphvqa_b200.my_graph_layernorm import LayerNorm
 dev = torch.device('cuda:0')
 peaks = os.path.join('/root/repo', 'MEASURED_PEAKS.json')
 PEAK = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
-flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)      # 256 MB
 def timed(fn, reps=24):
     ts = []
     for _ in range(reps):
-        flush.zero_(); torch.cuda._sleep(150000)
+        flush.sum(); torch.cuda._sleep(150000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
