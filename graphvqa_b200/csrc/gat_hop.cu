@@ -365,9 +365,6 @@ template <int J, int H>
 static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   if (variant == 1) {
     gat_hop_gather_kernel<J, H><<<(unsigned)((p.N + 7) / 8), 256, 0, stream>>>(p);
-  } else if (variant >= 100) {   // experiment: 256-thread CTAs of (variant - 100) nodes
-    const int npc = variant - 100;
-    gat_hop_block_kernel<J, H, 256, 32, 512><<<(unsigned)((p.N + npc - 1) / npc), 256, 0, stream>>>(p, npc);
   } else {
     int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
     npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
@@ -668,7 +665,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->epilogue != GVQA_EPI_NONE && (!a->ep_scale || !a->ep_shift)) return GVQA_ERR_NULL_POINTER;
   if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
-  if (a->variant < 0 || (a->variant > 3 && (a->variant < 104 || a->variant > 132))) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || a->variant > 3) return GVQA_ERR_UNSUPPORTED;
   if ((a->ldx & 3) || (a->ld_graph_bias & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
@@ -699,7 +696,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
       case 8: return launch_staged<8>(p, plan, stream);
     }
   }
-  const int variant = a->variant == 1 ? 1 : (a->variant >= 100 ? a->variant : 3);
+  const int variant = a->variant == 1 ? 1 : 3;
   switch (H) {
     case 1: return dispatch_flat<1>(p, variant, stream);
     case 2: return dispatch_flat<2>(p, variant, stream);
