@@ -338,7 +338,7 @@ def run_engine(args, rank, local_rank, world):
     else:
         primary_us, primary_method = hop_us, "event_bracket"
     primary_achieved = algo / (primary_us * 1e-6) / 1e9
-    base = cpu_baseline(cfg, steps=3, warmup=1) if not args.skip_cpu else None
+    base = cpu_baseline(cfg, steps=3, warmup=1) if (not args.skip_cpu and world == 1) else None   # N=1 only
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -394,6 +394,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner out of stdout: ONE JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
