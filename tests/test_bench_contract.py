@@ -1,0 +1,45 @@
+"""bench.py contract checks that need no GPU: the reference arm prints ONE JSON line with the required keys
+(it times the CPU restatement of the reference dataflow on a bounded sample), and the engine arm refuses to
+run without CUDA instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          env=e, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "questions/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+             env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_engine_arm_fails_loudly_without_cuda():
+    r = _run("--steps", "1", "--warmup", "0", "--skip-cpu")
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stderr + r.stdout)
