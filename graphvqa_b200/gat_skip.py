@@ -321,7 +321,8 @@ class gat_seq(nn.Module):
             last = i == num_hops - 1
             h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
             if self.hop_events is not None:
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ext = capturing       # inside a CUDA-graph capture the pair becomes two event-record nodes
+                ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
                 ev[0].record()
             if not self.skip_hop_launch:
                 _cabi.gat_hop(x_l, a_node, a_edge_all[:, i * heads:], csr_d, heads, c, h_out,
