@@ -368,6 +368,7 @@ static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   } else {
     int npc = (p.N + kNumSMs * 4 - 1) / (kNumSMs * 4);
     npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
+    if (const char* e = getenv("GVQA_HOP_NPC")) { const int v = atoi(e); if (v >= 1 && v <= kBlkNodes) npc = v; }   // experiments
     if (launch_pdl(2, gat_hop_block_kernel<J, H>, dim3((unsigned)((p.N + npc - 1) / npc)), dim3(kBlkThreads), 0, stream, p,
                    npc) != cudaSuccess) {
       (void)cudaGetLastError();
