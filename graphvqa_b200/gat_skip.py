@@ -173,6 +173,7 @@ class gat_seq(nn.Module):
         #   "cublas" torch.mm with TF32 off (fp32 SIMT, ~6x slower)
         self.projection = "3xf16"
         self._overflow, self._overflow_pending = None, []
+        self.overflow_external = False   # True: the caller reads / clears the fp16 range flag itself (host runner)
         self._side = None
         # keep x_l (written by the GEMM, read once by the hop kernel) resident in L2 between the two
         self.l2_persist = False
@@ -261,7 +262,7 @@ class gat_seq(nn.Module):
         # hop-invariant pre-pass: all hops' edge logits in one sweep over edge_attr, and the
         # per-graph instruction terms of x_l and of the logits
         capturing = torch.cuda.is_current_stream_capturing()
-        if not capturing:
+        if not capturing and not self.overflow_external:
             self._poll_overflow()
         tensor_core = self.projection in ("3xtf32", "3xf16")
         if self.projection == "3xf16":
@@ -342,7 +343,7 @@ class gat_seq(nn.Module):
                 hops.append(h)
         if self.l2_persist:
             _cabi.l2_window(None, x.device)
-        if self.projection == "3xf16" and not capturing:
+        if self.projection == "3xf16" and not capturing and not self.overflow_external:
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
 

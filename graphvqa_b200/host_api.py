@@ -40,6 +40,8 @@ class GatSeqHostRunner:
         self.hints = dict(max_nodes_per_graph=max_nodes_per_graph, max_in_edges_per_graph=max_in_edges_per_graph)
         self.s_h2d, self.s_compute, self.s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
         self.slots = [_Slot() for _ in range(depth)]
+        if hasattr(model, "overflow_external"):
+            model.overflow_external = True     # the fp16 range flag travels with each result (see result())
         self.count = 0
 
     def _forward(self, d):

@@ -270,3 +270,20 @@ def test_gat_seq_fp16_projection_flags_out_of_range_inputs():
     with torch.no_grad():
         out = e(*args)
     assert torch.isfinite(out).all()
+
+
+def test_host_runner_redoes_out_of_range_batch_with_full_range_projection():
+    """The fp16-split projection's range flag travels with the result; the runner reruns that batch with the
+    tf32 split, so the caller still gets the oracle's answer."""
+    from graphvqa_b200.host_api import GatSeqHostRunner
+    cfg = dict(in_channels=64, out_channels=64, edge_attr_dim=64, ins_dim=32, num_ins=2, gat_heads=4)
+    o, e = _pair(cfg, seed=61)
+    ei, batch = random_graphs(6, 4, 12, 2.0, seed=8)
+    args = list(_inputs(ei, batch, 6, 64, 64, 32, 2, seed=62))
+    args[0][2, 9] = 9.0e4                                  # outside fp16, fine for fp32
+    with torch.no_grad():
+        want = o(*args)
+    runner = GatSeqHostRunner(e, DEV, depth=2, use_cuda_graph=False)
+    got = runner(*[a.pin_memory() for a in args])
+    scale = float(want.abs().max())
+    assert torch.isfinite(got).all() and (got - want).abs().max() <= 1e-5 * max(scale, 1.0)
