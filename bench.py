@@ -28,8 +28,8 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-hop launch at cfg2 from the committed ncu --set full
 # capture (cold L2; the 15.7 MB output is still dirty in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES = 85604864
-NCU_TRAFFIC_SOURCE = "profiles/r01/hop_full_ncu_raw.csv"
+NCU_TRAFFIC_BYTES = 87152384
+NCU_TRAFFIC_SOURCE = "profiles/r01/hop_final_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
 UNIT = "questions/s"
