@@ -126,8 +126,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 // GVQA_PDL environment variable: bit0 enables the attribute for the projection GEMM, bit1 for the fused hop.
 // Default 1: measured at cfg2 (B200, graph replay) the GEMM gains ~1.6 us per launch, while the hop kernel LOSES
-// ~4 us per launch when its CTAs are scheduled early behind the persistent GEMM (0.504 -> 0.496 ms/step with
-// bit0 only, 0.526 with bit1 only) -- the hop keeps its pdl_wait() calls (no-ops without the attribute).
+// 5-7 us per launch (0.384 -> 0.410 ms/step with the index round trips before the wait, 0.419 with the wait at
+// the top): a plainly stream-ordered launch already overlaps its ramp with the predecessor's drain, and
+// griddepcontrol.wait additionally waits for the predecessor's memory flush.  The hop keeps its pdl_wait() calls
+// (no-ops without the attribute).
 inline int pdl_mask() {
   static const int mask = [] {
     const char* e = getenv("GVQA_PDL");
