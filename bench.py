@@ -256,12 +256,14 @@ def run_engine(args, rank, local_rank, world):
         value = b * world / (ms_per_step / 1e3)
 
         # ---------------- fused-hop kernel time, live, eager launches with events ---------------
-        model.hop_events = []
+        model.hop_events, model.gemm_events = [], []
         for i in range(args.steps):
             step(dev_sets[i % R])
         torch.cuda.synchronize()
         hop_ms = [a.elapsed_time(z) for a, z in model.hop_events]
-        model.hop_events = None
+        gemm_ms = [a.elapsed_time(z) for a, z in model.gemm_events]
+        model.hop_events = model.gemm_events = None
+        gemm_us = 1e3 * sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
         hop_us = 1e3 * sum(hop_ms) / len(hop_ms)
         algo = hop_bytes(n, e, heads, c)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -386,6 +388,20 @@ def run_engine(args, rank, local_rank, world):
                              "launch of K steps; an event pair around an empty stream position already reads ~2.7 us "
                              "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"},
     }
+    if gemm_us:
+        # the other big kernel of the step, tensor-bound: 3 fp16 products (hi*hi, hi*lo', lo'*hi) of [N x F] x
+        # [H*C+16 x F]^T per launch against the measured dense bf16/fp16 matmul peak
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        tpeak = peaks.get("bf16_tflops", 2250.0)
+        nproj = heads * c + 16
+        flops = 3 * 2.0 * n * nproj * cfg["feat"]
+        tf = flops / (gemm_us * 1e-6) / 1e12
+        line["roofline_projection"] = {
+            "bound": "tensor", "kernel": "proj_gemm_3xf16_kernel (gvqa_proj_gemm_3xf16)" if args.projection == "3xf16"
+            else "projection (%s)" % args.projection, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": tf / tpeak, "avg_launch_us": gemm_us, "method": "event_bracket", "launches_bracketed": len(gemm_ms),
+            "tensor_flops_per_launch": flops, "useful_fp32_flops_per_launch": flops / 3,
+            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "nominal"}
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)

@@ -178,6 +178,7 @@ class gat_seq(nn.Module):
         # keep x_l (written by the GEMM, read once by the hop kernel) resident in L2 between the two
         self.l2_persist = False
         self.skip_hop_launch = False  # measurement only (bench.py): omit the fused-hop launches, results are garbage
+        self.gemm_events = None     # same for the projection GEMM launches
         self.hop_events = None      # set to a list to collect (start, end) CUDA events per fused-hop launch
         self._packed = None
 
@@ -311,7 +312,14 @@ class gat_seq(nn.Module):
             _cabi.l2_window(x_l, x.device, 1.0)
         for i in range(num_hops):
             if fused_logits:
+                if self.gemm_events is not None:
+                    gev = (torch.cuda.Event(enable_timing=True, external=capturing),
+                           torch.cuda.Event(enable_timing=True, external=capturing))
+                    gev[0].record()
                 gemm(h, pk["w_split"][i], out=x_l)
+                if self.gemm_events is not None:
+                    gev[1].record()
+                    self.gemm_events.append(gev)
             else:
                 with _strict_fp32_matmul():
                     torch.mm(h, pk["w_h"][i].t(), out=x_l)
