@@ -18,6 +18,7 @@ constexpr int kVarThreads = 128;  // 4 warps, one destination node per warp at a
 //        z[i, F:F+D]  = (1+eps) ins[g] + deg(i) * relu(2 ins[g])      (instruction halves of
 //        x_cat / edge_cat are the same per-graph vector, pipeline_model_gine.py:652-661)
 // ------------------------------------------------------------------------------------------
+template <int J>
 __global__ void __launch_bounds__(kVarThreads) gine_aggregate_kernel(
     const float* __restrict__ h, const float* __restrict__ edge_attr, const float* __restrict__ ins,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src, const int32_t* __restrict__ perm,
@@ -29,21 +30,41 @@ __global__ void __launch_bounds__(kVarThreads) gine_aggregate_kernel(
   const int F4 = F >> 2, D4 = D >> 2;
   const int64_t ldz = (int64_t)F + D;
   const float self_scale = 1.0f + eps;
-  for (int c4 = lane; c4 < F4; c4 += 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int k = e0; k < e1; ++k) {
-      const int src = col_src[k];
-      const int64_t e = perm ? perm[k] : k;
-      const float4 a = ldg_cached(h + (int64_t)src * F + 4 * c4);
-      const float4 b = ldg_stream(edge_attr + e * F + 4 * c4);
-      acc.x += fmaxf(a.x + b.x, 0.f); acc.y += fmaxf(a.y + b.y, 0.f);
-      acc.z += fmaxf(a.z + b.z, 0.f); acc.w += fmaxf(a.w + b.w, 0.f);
+  // lane owns float4 columns lane, lane+32, ... (J of them): the 2 x J loads of an edge are issued together and two
+  // edges are unrolled, instead of one dependent round trip per column group
+  float4 acc[J], self[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    self[j] = acc[j];
+    const int c4 = lane + 32 * j;
+    if (c4 < F4) self[j] = ldg_cached(h + (int64_t)i * F + 4 * c4);
+  }
+#pragma unroll 2
+  for (int k = e0; k < e1; ++k) {
+    const int src = col_src[k];
+    const int64_t e = perm ? perm[k] : k;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < F4) {
+        const float4 a = ldg_cached(h + (int64_t)src * F + 4 * c4);
+        const float4 b = ldg_stream(edge_attr + e * F + 4 * c4);
+        acc[j].x += fmaxf(a.x + b.x, 0.f); acc[j].y += fmaxf(a.y + b.y, 0.f);
+        acc[j].z += fmaxf(a.z + b.z, 0.f); acc[j].w += fmaxf(a.w + b.w, 0.f);
+      }
     }
-    const float4 s = ldg_cached(h + (int64_t)i * F + 4 * c4);
-    // PyG adds (1+eps)*x_i AFTER the aggregation (out += (1 + eps) * x_r)
-    acc.x += self_scale * s.x; acc.y += self_scale * s.y; acc.z += self_scale * s.z; acc.w += self_scale * s.w;
-    stg_stream(z + (int64_t)i * ldz + 4 * c4, acc);
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < F4) {
+      // PyG adds (1+eps)*x_i AFTER the aggregation (out += (1 + eps) * x_r)
+      float4 o = acc[j];
+      o.x += self_scale * self[j].x; o.y += self_scale * self[j].y;
+      o.z += self_scale * self[j].z; o.w += self_scale * self[j].w;
+      stg_stream(z + (int64_t)i * ldz + 4 * c4, o);
+    }
   }
   if (D4 > 0) {
     const float deg = (float)(e1 - e0);
@@ -75,6 +96,7 @@ __global__ void gcn_degree_kernel(const int32_t* __restrict__ rowptr, const int3
 
 //   out[i] = sum_{k: src_k != i} dinv[src_k] dinv[i] (xw[src_k] + P[g]) + dinv[i]^2 (xw[i] + P[g]) + b
 // with xw = h @ W[:F] and P = ins @ W[F:] (x_cat @ W split by rows of W).
+template <int J>
 __global__ void __launch_bounds__(kVarThreads) gcn_aggregate_kernel(
     const float* __restrict__ xw, const float* __restrict__ graph_term, const float* __restrict__ dinv,
     const float* __restrict__ bias, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src,
@@ -86,26 +108,47 @@ __global__ void __launch_bounds__(kVarThreads) gcn_aggregate_kernel(
   const int C4 = C >> 2;
   const float di = dinv[i];
   const float* gt = graph_term ? graph_term + (int64_t)node_graph[i] * C : nullptr;
-  for (int c4 = lane; c4 < C4; c4 += 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gt) p4 = ldg_cached(gt + 4 * c4);
-#pragma unroll 4
-    for (int k = e0; k < e1; ++k) {
-      const int src = col_src[k];
-      if (src == i) continue;                 // pre-existing self-loops are removed by gcn_norm
-      const float w = dinv[src] * di;
-      const float4 v = ldg_cached(xw + (int64_t)src * C + 4 * c4);
-      acc.x += w * (v.x + p4.x); acc.y += w * (v.y + p4.y); acc.z += w * (v.z + p4.z); acc.w += w * (v.w + p4.w);
+  float4 acc[J], p4[J], self[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p4[j] = acc[j];
+    self[j] = acc[j];
+    const int c4 = lane + 32 * j;
+    if (c4 < C4) {
+      if (gt) p4[j] = ldg_cached(gt + 4 * c4);
+      self[j] = ldg_cached(xw + (int64_t)i * C + 4 * c4);
     }
-    const float ws = di * di;                 // the appended loop comes last in PyG's edge list
-    const float4 v = ldg_cached(xw + (int64_t)i * C + 4 * c4);
-    acc.x += ws * (v.x + p4.x); acc.y += ws * (v.y + p4.y); acc.z += ws * (v.z + p4.z); acc.w += ws * (v.w + p4.w);
-    if (bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+#pragma unroll 2
+  for (int k = e0; k < e1; ++k) {
+    const int src = col_src[k];
+    if (src == i) continue;                 // pre-existing self-loops are removed by gcn_norm
+    const float w = dinv[src] * di;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < C4) {
+        const float4 v = ldg_cached(xw + (int64_t)src * C + 4 * c4);
+        acc[j].x += w * (v.x + p4[j].x); acc[j].y += w * (v.y + p4[j].y);
+        acc[j].z += w * (v.z + p4[j].z); acc[j].w += w * (v.w + p4[j].w);
+      }
     }
-    stg_stream(out + (int64_t)i * C + 4 * c4, acc);
+  }
+  const float ws = di * di;                 // the appended loop comes last in PyG's edge list
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < C4) {
+      float4 o = acc[j];
+      o.x += ws * (self[j].x + p4[j].x); o.y += ws * (self[j].y + p4[j].y);
+      o.z += ws * (self[j].z + p4[j].z); o.w += ws * (self[j].w + p4[j].w);
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      }
+      stg_stream(out + (int64_t)i * C + 4 * c4, o);
+    }
   }
 }
 
@@ -200,9 +243,18 @@ extern "C" GVQA_API int gvqa_gine_aggregate_f32(const float* h, const float* edg
     return GVQA_ERR_NULL_POINTER;
   if ((feat & 3) || (ins_dim & 3)) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(h) || !aligned16(edge_attr) || !aligned16(z) || (ins && !aligned16(ins))) return GVQA_ERR_MISALIGNED;
+  if (feat > 1024) return GVQA_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((num_nodes + 3) / 4);
-  gine_aggregate_kernel<<<grid, kVarThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      h, edge_attr, ins, rowptr, col_src, perm, node_graph, z, (int)num_nodes, feat, ins_dim, eps);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int j = (feat / 4 + 31) / 32;
+#define GVQA_GINE(JJ)                                                                                          \
+  gine_aggregate_kernel<JJ><<<grid, kVarThreads, 0, stream>>>(h, edge_attr, ins, rowptr, col_src, perm, node_graph, z, \
+                                                             (int)num_nodes, feat, ins_dim, eps)
+  if (j <= 1) GVQA_GINE(1);
+  else if (j == 2) GVQA_GINE(2);
+  else if (j <= 4) GVQA_GINE(4);
+  else GVQA_GINE(8);
+#undef GVQA_GINE
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
@@ -228,9 +280,18 @@ extern "C" GVQA_API int gvqa_gcn_aggregate_f32(const float* xw, const float* gra
   if (channels & 3) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(xw) || !aligned16(out) || (graph_term && !aligned16(graph_term)) || (bias && !aligned16(bias)))
     return GVQA_ERR_MISALIGNED;
+  if (channels > 1024) return GVQA_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((num_nodes + 3) / 4);
-  gcn_aggregate_kernel<<<grid, kVarThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      xw, graph_term, dinv, bias, rowptr, col_src, node_graph, out, (int)num_nodes, channels);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int j = (channels / 4 + 31) / 32;
+#define GVQA_GCN(JJ)                                                                                        \
+  gcn_aggregate_kernel<JJ><<<grid, kVarThreads, 0, stream>>>(xw, graph_term, dinv, bias, rowptr, col_src, node_graph, \
+                                                            out, (int)num_nodes, channels)
+  if (j <= 1) GVQA_GCN(1);
+  else if (j == 2) GVQA_GCN(2);
+  else if (j <= 4) GVQA_GCN(4);
+  else GVQA_GCN(8);
+#undef GVQA_GCN
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
