@@ -23,6 +23,7 @@ class _Slot:
         self.out_dev = None        # device output (static when graph-captured)
         self.out_host = None       # pinned host output
         self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()   # fp16 range flag of this batch
+        self.flag_dev = None       # device snapshot of the flag, taken on the compute stream after the batch
         self.host_in = None        # the caller's host tensors (for the full-range rerun)
         self.h2d_done = torch.cuda.Event()
         self.compute_done = torch.cuda.Event()
@@ -74,10 +75,18 @@ class GatSeqHostRunner:
                 with torch.cuda.graph(g, stream=self.s_compute):
                     slot.out_dev = self._forward(slot.dev)
                 slot.graph = g
+            flag = getattr(self.model, "_overflow", None)
+            if flag is not None:
+                flag.zero_()                                  # this batch's fp16 range flag starts clear ...
             if slot.graph is not None:
                 slot.graph.replay()
             else:
                 slot.out_dev = self._forward(slot.dev)
+            flag = getattr(self.model, "_overflow", None)     # (created by the first forward)
+            if flag is not None:
+                if slot.flag_dev is None:
+                    slot.flag_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+                slot.flag_dev.copy_(flag)                     # ... and is snapshotted in stream order, per slot
             slot.compute_done.record(self.s_compute)
         if slot.out_host is None or slot.out_host.shape != slot.out_dev.shape:
             slot.out_host = torch.empty(slot.out_dev.shape, dtype=slot.out_dev.dtype).pin_memory()
@@ -85,10 +94,8 @@ class GatSeqHostRunner:
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(slot.compute_done)
             slot.out_host.copy_(slot.out_dev, non_blocking=True)
-            flag = getattr(self.model, "_overflow", None)
-            if flag is not None:       # fp16-split projection: its range flag travels with the result
-                slot.flag_host.copy_(flag, non_blocking=True)
-                flag.zero_()
+            if slot.flag_dev is not None:   # fp16-split projection: the batch's range flag travels with the result
+                slot.flag_host.copy_(slot.flag_dev, non_blocking=True)
             if slot.graph is None:
                 slot.out_dev.record_stream(self.s_d2h)
             slot.d2h_done.record(self.s_d2h)
