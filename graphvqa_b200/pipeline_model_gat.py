@@ -215,6 +215,28 @@ class _NodeModel(nn.Module):
         self.node_mlp_2 = nn.Sequential(nn.Linear(2 * nf, nf), nn.ReLU(), nn.Linear(nf, nf))
 
 
+class _TensorCoreLinear:
+    """y = x @ W^T (+ b) through the tcgen05 tf32-split GEMM (fp32-level accuracy, full fp32 range) instead of
+    cuBLAS' fp32 SIMT kernels; the split weights are cached per parameter version.  Encoder GEMMs only."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def __call__(self, x, weight, bias=None):
+        k = weight.size(1)
+        if not x.is_cuda or k % 4 or x.size(0) == 0:
+            y = x @ weight.t()
+            return y if bias is None else y + bias
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+        split = self._cache.get(key)
+        if split is None:
+            if len(self._cache) > 32:
+                self._cache.clear()
+            split = self._cache[key] = _cabi.split_tf32(weight.detach().contiguous().float())
+        y = _cabi.proj_gemm_3xtf32(x.contiguous().float(), split[0], split[1])
+        return y if bias is None else y.add_(bias)
+
+
 class _MetaLayer(nn.Module):
     """torch_geometric.nn.MetaLayer(EdgeModel, NodeModel) as instantiated by
     get_gt_scene_graph_encoding_layer (pipeline_model_gat.py:63-101):
@@ -225,6 +247,7 @@ class _MetaLayer(nn.Module):
         super().__init__()
         self.edge_model = _EdgeModel(nf, ef)
         self.node_model = _NodeModel(nf, ef)
+        self._lin = _TensorCoreLinear()
 
     def forward(self, x, edge_index, edge_attr, csr):
         """The first Linear of every MLP acts on a concatenation of gathered rows; it is evaluated as a
@@ -233,17 +256,21 @@ class _MetaLayer(nn.Module):
         nf = x.size(1)
         d = csr.as_dict()
         em, nm = self.edge_model.edge_mlp, self.node_model
+        lin = self._lin
         # edge model: e' = W2 relu(W1 [x_src | x_dst | e] + b1) + b2
         w1 = em[0].weight
-        xa, xb = x @ w1[:, :nf].t(), x @ w1[:, nf:2 * nf].t()
-        ec = edge_attr @ w1[:, 2 * nf:].t()
-        e_new = em[2](_cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index))
+        xa, xb = lin(x, w1[:, :nf]), lin(x, w1[:, nf:2 * nf])
+        ec = lin(edge_attr, w1[:, 2 * nf:])
+        e_new = lin(_cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index), em[2].weight, em[2].bias)
         # node model 1 on the UPDATED edges, mean over in-edges, node model 2 on [x | agg]
         w1 = nm.node_mlp_1[0].weight
-        msg = nm.node_mlp_1[2](_cabi.gather_add_relu(x @ w1[:, :nf].t(), None, e_new @ w1[:, nf:].t(),
-                                                     nm.node_mlp_1[0].bias, edge_index))
+        msg = lin(_cabi.gather_add_relu(lin(x, w1[:, :nf]), None, lin(e_new, w1[:, nf:]), nm.node_mlp_1[0].bias,
+                                        edge_index), nm.node_mlp_1[2].weight, nm.node_mlp_1[2].bias)
         agg = _cabi.segment_mean_rows(msg, d, mean=True)
-        return nm.node_mlp_2(torch.cat([x, agg], dim=1)), e_new
+        # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns
+        w1 = nm.node_mlp_2[0].weight
+        hid = torch.relu_(lin(x, w1[:, :nf]).add_(lin(agg, w1[:, nf:])).add_(nm.node_mlp_2[0].bias))
+        return lin(hid, nm.node_mlp_2[2].weight, nm.node_mlp_2[2].bias), e_new
 
 
 class GroundTruth_SceneGraph_Encoder(nn.Module):
