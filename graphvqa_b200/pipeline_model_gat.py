@@ -311,12 +311,17 @@ class MyConditionalGlobalAttention(nn.Module):
         self.gate_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, 1))
         self.node_nn = nn.Sequential(nn.Linear(num_node_features, c), nn.ReLU(), nn.Linear(c, c))
         self.ques_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c))
+        self._lin = _TensorCoreLinear()
 
     def forward(self, x, u, batch, size=None, graph_ptr=None):
         x = x.unsqueeze(-1) if x.dim() == 1 else x
         size = u.size(0) if size is None else size        # the reference syncs on batch[-1].item() (:152)
-        x = self.node_nn(x)
-        gate = self.gate_nn(self.ques_nn(u)[batch] * x)
+        lin = self._lin                                    # node-level Linear layers on the tensor-core GEMM
+        nn_, gn, qn = self.node_nn, self.gate_nn, self.ques_nn
+        x = lin(torch.relu_(lin(x, nn_[0].weight, nn_[0].bias)), nn_[2].weight, nn_[2].bias)
+        q = qn(u)                                          # [B, c]: per graph, tiny
+        hid = torch.relu_(lin(q[batch] * x, gn[0].weight, gn[0].bias))
+        gate = gn[2](hid)                                  # [N, 1]
         if graph_ptr is None:
             counts = torch.bincount(batch, minlength=size)
             graph_ptr = torch.zeros(size + 1, dtype=torch.int32, device=x.device)
