@@ -19,6 +19,7 @@ from torch import nn
 from . import _cabi
 from .gat_skip import _glorot_, _require_inference, _strict_fp32_matmul
 from .graph_batch import GraphCSR
+from .tc_linear import TensorCoreLinear
 
 
 class GCNConv(nn.Module):
@@ -27,6 +28,7 @@ class GCNConv(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        self._lin = TensorCoreLinear()
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -47,9 +49,8 @@ class GCNConv(nn.Module):
             dinv = _cabi.gcn_degree(d, n, x.device)
         x = x.contiguous().float()
         f = x.size(1)
-        with _strict_fp32_matmul():
-            xw = torch.mm(x, self.weight[:f])
-            graph_term = None if ins is None else torch.mm(ins.contiguous().float(), self.weight[f:])
+        xw = self._lin(x, self.weight[:f].t())                          # x @ W[:F]   (weight is [in, out])
+        graph_term = None if ins is None else self._lin(ins.contiguous().float(), self.weight[f:].t())
         return _cabi.gcn_aggregate(xw, graph_term, dinv, self.bias, d)
 
 
@@ -57,6 +58,7 @@ class GINEConv(nn.Module):
     def __init__(self, nn_module, eps=0.0, train_eps=False):
         super().__init__()
         self.nn = nn_module
+        self._lin = TensorCoreLinear()
         self.initial_eps = eps
         if train_eps:
             self.eps = nn.Parameter(torch.Tensor([eps]))
@@ -79,8 +81,17 @@ class GINEConv(nn.Module):
             assert x.size(-1) == edge_attr.size(-1)
         z = _cabi.gine_aggregate(x.contiguous().float(), edge_attr.contiguous().float(),
                                  None if ins is None else ins.contiguous().float(), csr.as_dict(), self._eps_host)
-        with _strict_fp32_matmul():
-            return self.nn(z)
+        return self._apply_nn(z)
+
+    def _apply_nn(self, z):
+        """self.nn(z) with its Linear layers on the tensor-core GEMM (any other layer runs as is)."""
+        for layer in self.nn:
+            if isinstance(layer, nn.Linear):
+                z = self._lin(z, layer.weight, layer.bias)
+            else:
+                with _strict_fp32_matmul():
+                    z = layer(z)
+        return z
 
 
 class _seq_base(nn.Module):

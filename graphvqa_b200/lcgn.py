@@ -17,6 +17,7 @@ from torch import nn
 from . import _cabi
 from .gat_skip import _glorot_, _require_inference, _strict_fp32_matmul
 from .graph_batch import GraphCSR
+from .tc_linear import TensorCoreLinear
 
 
 class gat_lcgn(nn.Module):
@@ -38,6 +39,7 @@ class gat_lcgn(nn.Module):
         else:
             self.register_parameter("bias", None)
         self._packed = None
+        self._lin = TensorCoreLinear()
         self.reset_parameters()
 
     def reset_parameters(self):      # same order as lcgn.py:106-117
@@ -53,8 +55,8 @@ class gat_lcgn(nn.Module):
     def _weights(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed is None or self._packed[0] != key:
-            w_node = torch.cat([self.lin_l.weight, self.lin_r.weight, self.cal_x.weight]).detach().t().contiguous()
-            w_cmd = torch.cat([self.proj_cmd.weight, self.cal_cmd.weight]).detach().t().contiguous()
+            w_node = torch.cat([self.lin_l.weight, self.lin_r.weight, self.cal_x.weight]).detach().contiguous()   # [3C, in]
+            w_cmd = torch.cat([self.proj_cmd.weight, self.cal_cmd.weight]).detach().contiguous()                 # [2C, cmd]
             self._packed = (key, w_node, w_cmd)
         return self._packed[1], self._packed[2]
 
@@ -68,9 +70,8 @@ class gat_lcgn(nn.Module):
         if csr is None:
             csr = GraphCSR.build(edge_index, batch, cmd.size(0))
         w_node, w_cmd = self._weights()
-        with _strict_fp32_matmul():
-            proj = torch.mm(x.contiguous().float(), w_node)          # [N, 3C] = lin_l | lin_r | cal_x
-            cmds = torch.mm(cmd.contiguous().float(), w_cmd)         # [B, 2C] = proj_cmd | cal_cmd
+        proj = self._lin(x.contiguous().float(), w_node)             # [N, 3C] = lin_l | lin_r | cal_x  (tensor cores)
+        cmds = self._lin(cmd.contiguous().float(), w_cmd)            # [B, 2C] = proj_cmd | cal_cmd
         return _cabi.lcgn_hop(proj[:, :c], proj[:, c:2 * c], proj[:, 2 * c:], cmds[:, :c].contiguous(),
                               cmds[:, c:].contiguous(), self.bias, csr.as_dict(), self.negative_slope)
 
@@ -108,15 +109,19 @@ class lcgn_seq(nn.Module):
         _cabi.require_cuda(x, edge_index, batch, q_encoding, lstm_outputs)
         if csr is None:
             csr = GraphCSR.build(edge_index, batch, q_encoding.size(0))
+        lin = self.lcgn._lin       # node-level Linear layers on the tensor-core GEMM (dropout is identity in eval)
+
+        def L(layer, v):
+            return lin(v, layer.weight, layer.bias)
         with _strict_fp32_matmul():
-            x_loc = self.init_sg_emb_input(x)
+            x_loc = L(self.init_sg_emb_input[0], x.contiguous().float())
             x_ctx = (torch.randn(x_loc.size()).to(x_loc.device) if x_ctx_init is None     # lcgn.py:306
                      else x_ctx_init.to(x_loc.device))
             q_emb = F.relu(self.qInput1(q_encoding))
-            proj_x_loc = self.proj_x_loc(x_loc)
+            proj_x_loc = L(self.proj_x_loc[1], x_loc)
             for t in range(self.MAX_ITER_NUM):
                 cmd = self.extract_textual_command(q_emb, lstm_outputs, t)
-                x_joint = torch.cat([x_loc, x_ctx, self.proj_x_ctx(x_ctx) * proj_x_loc], dim=-1)
+                x_joint = torch.cat([x_loc, x_ctx, L(self.proj_x_ctx[1], x_ctx) * proj_x_loc], dim=-1)
                 msg = self.lcgn(x_joint, edge_index, cmd, batch, csr=csr)
-                x_ctx = self.output_layer(torch.cat([x_ctx, msg], dim=-1))
-            return self.fin_layer(torch.cat([x_loc, x_ctx], dim=-1))
+                x_ctx = L(self.output_layer, torch.cat([x_ctx, msg], dim=-1))
+            return L(self.fin_layer, torch.cat([x_loc, x_ctx], dim=-1))

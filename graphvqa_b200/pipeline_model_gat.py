@@ -29,6 +29,7 @@ import torch
 from torch import nn
 
 from . import _cabi
+from .tc_linear import TensorCoreLinear as _TensorCoreLinear
 from .gat_skip import gat_seq
 from .graph_batch import GraphCSR, SceneGraphBatch
 from .my_graph_layernorm import LayerNorm
@@ -213,28 +214,6 @@ class _NodeModel(nn.Module):
         super().__init__()
         self.node_mlp_1 = nn.Sequential(nn.Linear(nf + ef, nf), nn.ReLU(), nn.Linear(nf, nf))
         self.node_mlp_2 = nn.Sequential(nn.Linear(2 * nf, nf), nn.ReLU(), nn.Linear(nf, nf))
-
-
-class _TensorCoreLinear:
-    """y = x @ W^T (+ b) through the tcgen05 tf32-split GEMM (fp32-level accuracy, full fp32 range) instead of
-    cuBLAS' fp32 SIMT kernels; the split weights are cached per parameter version.  Encoder GEMMs only."""
-
-    def __init__(self):
-        self._cache = {}
-
-    def __call__(self, x, weight, bias=None):
-        k = weight.size(1)
-        if not x.is_cuda or k % 4 or x.size(0) == 0:
-            y = x @ weight.t()
-            return y if bias is None else y + bias
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
-        split = self._cache.get(key)
-        if split is None:
-            if len(self._cache) > 32:
-                self._cache.clear()
-            split = self._cache[key] = _cabi.split_tf32(weight.detach().contiguous().float())
-        y = _cabi.proj_gemm_3xtf32(x.contiguous().float(), split[0], split[1])
-        return y if bias is None else y.add_(bias)
 
 
 class _MetaLayer(nn.Module):

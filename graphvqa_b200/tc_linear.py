@@ -1,0 +1,31 @@
+"""Dense layers of the graph side on the hand-written tensor-core GEMM.
+
+``TensorCoreLinear()(x, weight, bias)`` evaluates ``x @ weight^T (+ bias)`` with ``gvqa_proj_gemm_3xtf32``
+(tcgen05, tf32-split operands, fp32 accumulation: fp32-level accuracy over the full fp32 range) instead of
+cuBLAS' fp32 SIMT kernels, which the 1e-4 parity bar would otherwise force (TF32 off).  The split weights are
+cached per parameter version.  Used by the scene-graph encoder, the attention pooling and the GCN / GINE /
+LCGN variants; the Transformer text stack and the answer head stay plain PyTorch.
+"""
+import torch
+
+from . import _cabi
+
+
+class TensorCoreLinear:
+    def __init__(self):
+        self._cache = {}
+
+    def __call__(self, x, weight, bias=None):
+        """x [M, K] float32 CUDA, weight [N, K] (any strides), bias [N] or None -> [M, N]."""
+        k = weight.size(1)
+        if not x.is_cuda or k % 4 or x.size(0) == 0:
+            y = x @ weight.t()
+            return y if bias is None else y + bias
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+        split = self._cache.get(key)
+        if split is None:
+            if len(self._cache) > 64:
+                self._cache.clear()
+            split = self._cache[key] = _cabi.split_tf32(weight.detach().contiguous().float())
+        y = _cabi.proj_gemm_3xtf32(x.contiguous().float(), split[0], split[1])
+        return y if bias is None else y.add_(bias)
