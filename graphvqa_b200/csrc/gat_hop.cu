@@ -264,26 +264,27 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
     return;
   }
 
-  // sources and edge logit terms, edge-parallel
+  // sources, then edge and source logit terms, edge-parallel.  Without the early-start promise both terms are
+  // requested together (round trip 3); with it the edge term is staged first and the source term -- an output of
+  // the previous kernel -- is added after the dependency wait.
   for (int k = tid; k < eC; k += kBlkThreads) {
     const int src = p.col_src[eA + k];
     const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
     src_s[k] = src;
+    const float* an = p.a_node + (int64_t)src * p.lda;
 #pragma unroll
-    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_edge[e * p.lde + h];
+    for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_edge[e * p.lde + h] + (p.early ? 0.f : an[h]);
   }
 
   // ---- everything below reads what the previous kernel wrote (a_node and x_l come out of the GEMM) --------
   if (p.early) {
     pdl_wait();
     pdl_launch_dependents();
-  }
-
-  // round trip 3: source / target logit terms (each thread revisits the edges it staged above)
-  for (int k = tid; k < eC; k += kBlkThreads) {
-    const float* an = p.a_node + (int64_t)src_s[k] * p.lda;
+    for (int k = tid; k < eC; k += kBlkThreads) {   // each thread revisits the edges it staged above
+      const float* an = p.a_node + (int64_t)src_s[k] * p.lda;
 #pragma unroll
-    for (int h = 0; h < H; ++h) alpha_s[k * H + h] += an[h];
+      for (int h = 0; h < H; ++h) alpha_s[k * H + h] += an[h];
+    }
   }
   if (tid < nn * H) {
     tg_reg += p.a_node[(int64_t)(i0 + my_node) * p.lda + H + my_head];
@@ -682,7 +683,8 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.ldgb = a->ld_graph_bias > 0 ? a->ld_graph_bias : C; p.ldag = a->ld_a_graph > 0 ? a->ld_a_graph : H;
   p.N = (int32_t)a->num_nodes; p.E = (int32_t)a->num_edges; p.B = (int32_t)a->num_graphs; p.C = C;
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
-  p.early = (a->flags & GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR) ? 1 : 0;
+  // the early-start layout only pays when the launch carries the PDL attribute (off by default, common.cuh)
+  p.early = ((a->flags & GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR) && (pdl_mask() & 2)) ? 1 : 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   if (a->variant == 2) {
