@@ -1,0 +1,139 @@
+"""Host-side collate of GQA scene graphs: JSON scene graph -> token ids -> one
+``SceneGraphBatch`` in pinned memory, ready for ``.to(device, non_blocking=True)``.
+
+Restates, without torchtext / spaCy / torch_geometric:
+
+* the scene-graph vocabulary of ``GQA_gt_sg_feature_lookup.build_scene_graph_encoding_vocab``
+  (gqa_dataset_entry.py:136-163): one pseudo-sentence made of the name / attribute / relation lists of
+  ``meta_info/`` plus the ontology tables of Constants.py:96-106 plus ``<self>``, fed to a legacy torchtext
+  ``Field(init_token="<start>", eos_token="<end>")`` -- i.e. specials ``<unk> <pad> <start> <end>`` first, then
+  every token by descending frequency, ties alphabetical, lower-casing off, unknown tokens -> id 0;
+* ``convert_one_gqa_scene_graph`` (gqa_dataset_entry.py:190-372): objects sorted by id are the nodes; per
+  node 12 token slots (name + its de-duplicated attributes, ``<pad>`` elsewhere), one ``<self>`` loop edge
+  first, then each outgoing relation in JSON order, each followed by a synthesised reverse edge (same
+  relation token) when the graph has no edge in the opposite direction; the positions of the synthesised
+  edges are recorded graph-locally in ``added_sym_edge``; an empty graph becomes the reference's two-node
+  ``<UNK>`` dummy;
+* ``torch_geometric.data.Batch.from_data_list`` as the reference's collate uses it (gqa_dataset_entry.py:654;
+  SURVEY.md Appendix A): node offsets are added to ``edge_index`` only -- ``added_sym_edge`` stays graph-local,
+  which the encoder reproduces (pipeline_model_gat.py:590).
+
+The attribute order inside a node follows Python's ``set`` iteration order in the reference (:287), which is
+not deterministic across interpreter runs; here attributes keep their first-occurrence order.  The encoder
+sums the 12 slot embeddings (:583-585), so the order does not change any result.
+
+Parity status: the reference's loader cannot run here (torchtext < 0.9, spaCy model and GloVe download are
+absent and there is no network), so this restatement is checked against the structural facts recorded in
+SURVEY.md section 4 (node / edge counts of debug_sceneGraphs.json, vocabulary size 2577, ``<self>`` id) and
+against hand-built graphs (tests/test_collate.py), not against reference outputs.
+"""
+import collections
+import json
+import os
+
+import torch
+
+from .graph_batch import SceneGraphBatch
+
+MAX_OBJ_TOKEN_LEN = 12          # gqa_dataset_entry.py:265 (1 name + up to 11 attributes)
+SPECIALS = ("<unk>", "<pad>", "<start>", "<end>")
+
+
+class SceneGraphVocab:
+    """token -> id with torchtext's unknown-token behaviour (missing -> 0)."""
+
+    def __init__(self, itos):
+        self.itos = list(itos)
+        self.stoi = {t: i for i, t in enumerate(self.itos)}
+        self.pad_id = self.stoi["<pad>"]
+        self.self_id = self.stoi.get("<self>", 0)
+
+    def __len__(self):
+        return len(self.itos)
+
+    def __getitem__(self, token):
+        return self.stoi.get(token, 0)
+
+    @classmethod
+    def from_tokens(cls, tokens):
+        """Legacy torchtext ``Vocab(counter, specials=...)`` order: specials, then by (-frequency, token)."""
+        counter = collections.Counter(tokens)
+        for s in SPECIALS:
+            counter.pop(s, None)
+        words = sorted(counter.items(), key=lambda kv: kv[0])
+        words.sort(key=lambda kv: kv[1], reverse=True)
+        return cls(list(SPECIALS) + [w for w, _ in words])
+
+    @classmethod
+    def from_meta_info(cls, meta_info_dir):
+        """The reference's scene-graph vocabulary from its ``meta_info/`` directory."""
+        def lines(name):
+            with open(os.path.join(meta_info_dir, name)) as f:
+                return f.read().splitlines()
+
+        def table(name):
+            with open(os.path.join(meta_info_dir, name)) as f:
+                return json.load(f)
+
+        tokens = lines("name_gqa.txt") + lines("attr_gqa.txt") + lines("rel_gqa.txt")
+        tokens += table("objects.json") + table("predicates.json") + table("attributes.json")
+        tokens.append("<self>")
+        return cls.from_tokens(tokens)
+
+
+_EMPTY_GRAPH = {"objects": {
+    "0": {"name": "<UNK>", "relations": [{"object": "1", "name": "<UNK>"}], "attributes": ["<UNK>"]},
+    "1": {"name": "<UNK>", "relations": [{"object": "0", "name": "<UNK>"}], "attributes": ["<UNK>"]},
+}}
+
+
+def convert_scene_graph(sg, vocab):
+    """One GQA scene graph (the JSON object with an ``objects`` dict) ->
+    (x [n,12] i64, edge_index [2,e] i64, edge_attr [e,1] i64, added_sym_edge [k] i64)."""
+    if len(sg["objects"]) == 0:
+        sg = _EMPTY_GRAPH
+    objs = sg["objects"]
+    ids = sorted(objs.keys())
+    index = {o: i for i, o in enumerate(ids)}
+    present = {(index[o], index[r["object"]]) for o in ids for r in objs[o]["relations"]}
+    x = torch.full((len(ids), MAX_OBJ_TOKEN_LEN), vocab.pad_id, dtype=torch.int64)
+    src, dst, rel, sym = [], [], [], []
+    for o in ids:
+        i, obj = index[o], objs[o]
+        x[i, 0] = vocab[obj["name"]]
+        for slot, attr in enumerate(dict.fromkeys(obj.get("attributes", []))):
+            if slot + 1 >= MAX_OBJ_TOKEN_LEN:
+                raise ValueError("object %r has more than %d distinct attributes" % (o, MAX_OBJ_TOKEN_LEN - 1))
+            x[i, slot + 1] = vocab[attr]
+        src.append(i); dst.append(i); rel.append(vocab.self_id)          # the self-loop comes first
+        for r in obj["relations"]:
+            j, tok = index[r["object"]], vocab[r["name"]]
+            src.append(i); dst.append(j); rel.append(tok)
+            if (j, i) not in present:                                     # synthesised reverse edge
+                src.append(j); dst.append(i); rel.append(tok)
+                sym.append(len(rel) - 1)
+    return (x, torch.tensor([src, dst], dtype=torch.int64), torch.tensor(rel, dtype=torch.int64).unsqueeze(1),
+            torch.tensor(sym, dtype=torch.int64))
+
+
+def collate_scene_graphs(scene_graphs, vocab, pin_memory=True):
+    """List of GQA scene graphs -> one ``SceneGraphBatch`` of disjoint components (host tensors)."""
+    xs, eis, eas, syms, batch = [], [], [], [], []
+    offset = max_nodes = max_edges = 0
+    for g, sg in enumerate(scene_graphs):
+        x, ei, ea, sym = convert_scene_graph(sg, vocab)
+        xs.append(x); eis.append(ei + offset); eas.append(ea); syms.append(sym)      # sym stays graph-local
+        batch.append(torch.full((x.size(0),), g, dtype=torch.int64))
+        offset += x.size(0)
+        max_nodes, max_edges = max(max_nodes, x.size(0)), max(max_edges, ei.size(1))
+    if not xs:
+        raise ValueError("collate_scene_graphs: empty list")
+    out = SceneGraphBatch(x=torch.cat(xs), edge_index=torch.cat(eis, dim=1), edge_attr=torch.cat(eas),
+                          batch=torch.cat(batch), added_sym_edge=torch.cat(syms), num_graphs=len(xs),
+                          max_nodes_per_graph=max_nodes, max_in_edges_per_graph=max_edges)
+    if pin_memory and torch.cuda.is_available():
+        for name in SceneGraphBatch._TENSOR_FIELDS:
+            t = getattr(out, name)
+            if t is not None:
+                setattr(out, name, t.pin_memory())
+    return out
