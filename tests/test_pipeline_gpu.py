@@ -65,3 +65,21 @@ def test_pipeline_sampling_and_tolerant_load(golden):
     before = m.logit_fc[4].bias.clone()
     m.load_state_dict(sd)
     assert torch.equal(m.logit_fc[4].bias, before)
+
+
+def test_pipeline_runs_on_collated_scene_graphs():
+    """collate.py output (raw GQA-style JSON -> pinned SceneGraphBatch) drives the whole model on the GPU."""
+    from graphvqa_b200.collate import SceneGraphVocab, collate_scene_graphs
+    mod = importlib.import_module("graphvqa_b200.pipeline_model_gat")
+    vocab = SceneGraphVocab.from_tokens(["cat", "dog", "red", "big", "on", "near", "<self>"])
+    sg = {"objects": {"1": {"name": "dog", "attributes": ["red"], "relations": [{"object": "2", "name": "on"}]},
+                      "2": {"name": "cat", "attributes": ["big", "red"], "relations": []},
+                      "3": {"name": "cat", "attributes": [], "relations": [{"object": "1", "name": "near"}]}}}
+    graphs = collate_scene_graphs([sg, {"objects": {}}, sg], vocab)
+    torch.manual_seed(0)
+    m = mod.PipelineModel(VocabSpec(text_vocab_size=50, sg_vocab_size=len(vocab))).eval().to(DEV)
+    q = torch.randint(4, 50, (7, 3))
+    with torch.no_grad():
+        logits = m.answer_logits(q.to(DEV), graphs.to(device=DEV, non_blocking=True))
+    m.gat_seq.check_overflow()
+    assert logits.shape == (3, 1842) and torch.isfinite(logits).all()
