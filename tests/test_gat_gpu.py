@@ -287,3 +287,38 @@ def test_host_runner_redoes_out_of_range_batch_with_full_range_projection():
     got = runner(*[a.pin_memory() for a in args])
     scale = float(want.abs().max())
     assert torch.isfinite(got).all() and (got - want).abs().max() <= 1e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("graphs,nodes,edges", [(256, 30, 60), (128, 200, 800)])
+def test_fused_hop_full_size_properties(graphs, nodes, edges):
+    """Size-independent properties of the fused hop at the full BASELINE sizes (cfg2; cfg4 per GPU), straight
+    through the C ABI: attention weights of every destination sum to one (constant rows in -> the same constant
+    out), the kernel is linear in the projected features for fixed logits, and alpha_out agrees with it."""
+    h, c = 4, 512
+    ei, batch, mx = synthetic_topology(graphs, nodes, edges, seed=77)
+    ei, batch = ei.to(DEV), batch.to(DEV)
+    n, e = batch.numel(), ei.size(1)
+    csr = GraphCSR.build(ei, batch, graphs, max_nodes_per_graph=mx)
+    g = torch.Generator().manual_seed(5)
+    a_node = torch.randn(n, 2 * h, generator=g).to(DEV)
+    a_edge = torch.randn(e, h, generator=g).to(DEV)
+    x1 = torch.randn(n, h * c, generator=g).to(DEV)
+    x2 = torch.randn(n, h * c, generator=g).to(DEV)
+
+    def hop(x_l, alpha=None):
+        out = torch.empty(n, c, device=DEV)
+        _cabi.gat_hop(x_l, a_node, a_edge, csr.as_dict(), h, c, out, alpha_out=alpha, **csr.hints())
+        return out
+    has_in = (csr.rowptr[1:] > csr.rowptr[:-1])
+    alpha = torch.zeros(e, h, device=DEV)
+    ones = hop(torch.full((n, h * c), 3.0, device=DEV), alpha)
+    assert bool(has_in.all())                                   # every node carries its self-loop
+    assert (ones - 3.0).abs().max() <= 1e-5
+    seg = torch.zeros(n, h, device=DEV).index_add_(0, ei[1], alpha)
+    assert (seg - 1.0).abs().max() <= 1e-5 and float(alpha.min()) >= 0.0
+    lin = hop(x1 + 2.0 * x2)
+    assert (lin - (hop(x1) + 2.0 * hop(x2))).abs().max() <= 2e-5
+    # and alpha_out reproduces the output: out[i] = mean_h sum_k alpha[k,h] x_l[src_k, h, :]
+    msg = (x1.view(n, h, c)[ei[0]] * alpha.unsqueeze(-1)).mean(1)
+    want = torch.zeros(n, c, device=DEV).index_add_(0, ei[1], msg)
+    assert (hop(x1) - want).abs().max() <= 2e-5
