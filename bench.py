@@ -401,6 +401,8 @@ def run_engine(args, rank, local_rank, world):
             else "projection (%s)" % args.projection, "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
             "frac": tf / tpeak, "avg_launch_us": gemm_us, "method": "event_bracket", "launches_bracketed": len(gemm_ms),
             "tensor_flops_per_launch": flops, "useful_fp32_flops_per_launch": flops / 3,
+            "peak_sustained": peaks.get("bf16_tflops_sustained"),
+            "frac_of_sustained": (tf / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "nominal"}
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
