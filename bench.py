@@ -374,8 +374,9 @@ def run_engine(args, rank, local_rank, world):
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": n * c * 4},
-        # per step: 5 CSR kernels + edge-logit GEMM + batched instruction GEMM + hops x (projection GEMM + fused hop)
-        "gpu_launches": args.steps * (5 + 2 + 2 * hops),
+        # per step: 5 CSR kernels + hops x (projection GEMM + fused hop); the edge-logit and instruction pre-pass
+        # products ride in hop 0's projection launch (grouped) or cost two launches of their own
+        "gpu_launches": args.steps * (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops),
         "roofline": {"bound": "hbm", "kernel": "gat_hop_block_kernel (gvqa_gat_hop_f32)",
                      "achieved": primary_achieved, "peak": peak, "unit": "GB/s", "frac": primary_achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,

@@ -37,6 +37,17 @@ class GatHopArgs(ctypes.Structure):
     ]
 
 
+class GemmProblem(ctypes.Structure):
+    """Mirror of ``struct gvqa_gemm_problem`` (one product of a grouped launch)."""
+    _fields_ = [
+        ("a", _c_vp), ("lda", _c_i64), ("stride_a", _c_i64), ("b_hi", _c_vp), ("b_lo", _c_vp), ("ldb", _c_i64),
+        ("stride_b", _c_i64), ("c", _c_vp), ("ldc", _c_i64), ("stride_c", _c_i64), ("m", _c_i64),
+        ("n", _c_i32), ("k", _c_i32), ("batch", _c_i32),
+    ]
+
+
+MAX_GROUPED_PROBLEMS = 3
+
 # name -> (restype, argtypes); must list every symbol declared in include/gvqa_b200.h
 SIGNATURES = {
     "gvqa_abi_version": (ctypes.c_int, []),
@@ -62,6 +73,7 @@ SIGNATURES = {
                                             _c_i32, _c_vp, _c_vp]),
     "gvqa_proj_gemm_3xf16_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64,
                                                     _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
+    "gvqa_proj_gemm_3xf16_grouped": (ctypes.c_int, [ctypes.POINTER(GemmProblem), _c_i32, _c_vp, _c_vp]),
     "gvqa_gine_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                _c_i32, _c_i32, _c_f32, _c_vp]),
     "gvqa_gcn_degree_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
@@ -351,6 +363,47 @@ def proj_gemm_3xf16_batched(a, b_hi, b_lo, overflow=None):
                                                  ptr(out), n, m * n, m, n, k, z, ptr(overflow),
                                                  stream_handle(a.device)), "gvqa_proj_gemm_3xf16_batched")
     return out
+
+
+def proj_gemm_3xf16_grouped(problems, overflow=None):
+    """Up to three independent products in ONE persistent launch.  ``problems``: (a, b_hi, b_lo, out) tuples, each
+    either 2-D (a [M,K], b [N,K], out [M,N] or None) or 3-D batched (a [Z,M,K] contiguous, b [Z,N,K] views of
+    split_f16 output, out None or contiguous [Z,M,N]).  Returns the list of outputs."""
+    if not 1 <= len(problems) <= MAX_GROUPED_PROBLEMS:
+        raise ValueError("proj_gemm_3xf16_grouped: 1..%d problems" % MAX_GROUPED_PROBLEMS)
+    arr = (GemmProblem * len(problems))()
+    outs = []
+    device = problems[0][0].device
+    for q, (a, b_hi, b_lo, out) in zip(arr, problems):
+        require_cuda(a, b_hi, b_lo, out, overflow)
+        if a.dtype != torch.float32 or a.dim() not in (2, 3) or a.stride(-1) != 1 or a.device != device:
+            raise ValueError("proj_gemm_3xf16_grouped: a must be float32 [M,K] or [Z,M,K] with unit column stride")
+        for t in (b_hi, b_lo):
+            if t.dtype != torch.float16 or t.dim() != a.dim() or t.stride(-1) != 1 or any(s % 8 for s in t.stride()[:-1]):
+                raise ValueError("proj_gemm_3xf16_grouped: b_hi / b_lo must come from split_f16")
+        if a.dim() == 3:
+            if not a.is_contiguous():
+                raise ValueError("proj_gemm_3xf16_grouped: batched a must be contiguous")
+            z, m, k = a.shape
+            n = b_hi.size(1)
+            if out is None:
+                out = torch.empty(z, m, n, dtype=torch.float32, device=device)
+            elif not out.is_contiguous() or out.shape != (z, m, n):
+                raise ValueError("proj_gemm_3xf16_grouped: batched out must be contiguous [Z,M,N]")
+            q.lda, q.stride_a, q.ldb, q.stride_b, q.ldc, q.stride_c = k, m * k, b_hi.stride(1), b_hi.stride(0), n, m * n
+        else:
+            (m, k), z = a.shape, 1
+            n = b_hi.size(0)
+            if out is None:
+                out = torch.empty(m, n, dtype=torch.float32, device=device)
+            q.lda, q.stride_a, q.ldb, q.stride_b, q.ldc, q.stride_c = (a.stride(0) if m > 1 else k), 0, b_hi.stride(0), 0, \
+                out.stride(0), 0
+        q.a, q.b_hi, q.b_lo, q.c, q.m, q.n, q.k, q.batch = ptr(a), ptr(b_hi), ptr(b_lo), ptr(out), m, n, k, z
+        outs.append(out)
+    with torch.cuda.device(device):
+        check(lib().gvqa_proj_gemm_3xf16_grouped(arr, len(problems), ptr(overflow), stream_handle(device)),
+              "gvqa_proj_gemm_3xf16_grouped")
+    return outs
 
 
 def l2_persist_limit(nbytes, device):

@@ -19,6 +19,7 @@
 // [128 x 64] fp16 (one 128B-swizzled box each) = 64 KB per stage, 3 stages.  Warp roles, TMEM map, the early
 // TMEM release and the TMA-store epilogue are those of proj_gemm.cu.
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "tcgen05_utils.cuh"
 
@@ -54,11 +55,40 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(h);
 }
 
+// Up to kMaxProblems independent products share one persistent launch (tiles of problem 0 first, then 1, ...):
+// gat_seq issues hop 0's projection together with the two small pre-pass products, whose ~170 short tiles then
+// fill the last, partially empty wave instead of costing two more launches.
+constexpr int kMaxProblems = 3;
+
+struct alignas(64) GroupedParams {
+  CUtensorMap map_a[kMaxProblems], map_bhi[kMaxProblems], map_blo[kMaxProblems], map_c[kMaxProblems];
+  int M[kMaxProblems], N[kMaxProblems], K[kMaxProblems];
+  int tiles_per_batch[kMaxProblems], n_tiles[kMaxProblems];
+  int tile_end[kMaxProblems];      // exclusive prefix of tiles
+  int count;
+};
+
+struct TileInfo {
+  int p, z, m0, n0, kblocks;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GroupedParams& g, int tile) {
+  TileInfo t;
+  t.p = tile < g.tile_end[0] ? 0 : (tile < g.tile_end[1] ? 1 : 2);
+  const int local = tile - (t.p == 0 ? 0 : g.tile_end[t.p - 1]);
+  t.z = local / g.tiles_per_batch[t.p];
+  const int t2 = local - t.z * g.tiles_per_batch[t.p];
+  t.m0 = (t2 / g.n_tiles[t.p]) * kBM;
+  t.n0 = (t2 % g.n_tiles[t.p]) * kBN;
+  t.kblocks = (g.K[t.p] + kBK - 1) / kBK;          // the ragged last k-block is zero-filled by TMA
+  return t;
+}
+
+#define GVQA_MAP(field, p) ((p) == 0 ? &g.field[0] : ((p) == 1 ? &g.field[1] : &g.field[2]))
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
-proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                       const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, int M,
-                       int N, int K, int batch, int32_t* __restrict__ overflow) {
-  // all four tensor maps are 3-D [batch, rows, K]; a tile index decomposes into (batch z, row tile, column tile)
+proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restrict__ overflow) {
+  // all tensor maps are 3-D [batch, rows, K]; a tile index decomposes into (problem, batch z, row tile, column tile)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;
@@ -72,10 +102,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + kBN - 1) / kBN;
-  const int tiles_per_batch = m_tiles * n_tiles;
-  const int num_tiles = tiles_per_batch * batch;
-  const int kblocks = (K + kBK - 1) / kBK;          // the ragged last k-block is zero-filled by TMA
+  const int num_tiles = g.tile_end[g.count - 1];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -109,17 +136,17 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_per_batch, t2 = tile - z * tiles_per_batch;
-        const int m0 = (t2 / n_tiles) * kBM, n0 = (t2 % n_tiles) * kBN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const TileInfo t = decode_tile(g, tile);
+        const CUtensorMap *ma = GVQA_MAP(map_a, t.p), *mh = GVQA_MAP(map_bhi, t.p), *ml = GVQA_MAP(map_blo, t.p);
+        for (int kb = 0; kb < t.kblocks; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + (size_t)s * kStageBytes;
           mbar_expect_tx(&tma_full[s], kStageBytes);
-          tma_load_3d(st, &map_a, &tma_full[s], kb * kBK, m0, z);
-          tma_load_3d(st + kAHalfBytes, &map_a, &tma_full[s], kb * kBK + 32, m0, z);
-          tma_load_3d(st + kABytes, &map_bhi, &tma_full[s], kb * kBK, n0, z);
-          tma_load_3d(st + kABytes + kBBytes, &map_blo, &tma_full[s], kb * kBK, n0, z);
+          tma_load_3d(st, ma, &tma_full[s], kb * kBK, t.m0, t.z);
+          tma_load_3d(st + kAHalfBytes, ma, &tma_full[s], kb * kBK + 32, t.m0, t.z);
+          tma_load_3d(st + kABytes, mh, &tma_full[s], kb * kBK, t.n0, t.z);
+          tma_load_3d(st + kABytes + kBBytes, ml, &tma_full[s], kb * kBK, t.n0, t.z);
         }
       }
     }
@@ -128,11 +155,12 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (elect_one()) {
       uint32_t it = 0, tile_it = 0;
       const uint64_t desc0 = umma_desc(smem_u32(smem));   // descriptor of (base + c) == desc0 + (c >> 4)
-      const int half_kb = (kblocks + 1) / 2;              // first k-block of the second K-half
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
         // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, M = 128, N = tile width (x16)
-        const int n0 = ((tile % tiles_per_batch) % n_tiles) * kBN;
-        const int ncols = min(kBN, (N - n0 + 15) & ~15);
+        const TileInfo t = decode_tile(g, tile);
+        const int kblocks = t.kblocks;
+        const int half_kb = (kblocks + 1) / 2;            // first k-block of the second K-half
+        const int ncols = min(kBN, (g.N[t.p] - t.n0 + 15) & ~15);
         const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -165,6 +193,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     uint32_t it = 0;
     float amax = 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int kblocks = decode_tile(g, tile).kblocks;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % kStages, ts = it & 1;
         mbar_wait(&tma_full[s], (it / kStages) & 1);
@@ -201,8 +230,9 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int chalf = warp >= 10 ? 1 : 0;
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const int z = tile / tiles_per_batch, t2 = tile - z * tiles_per_batch;
-      const int m0 = (t2 / n_tiles) * kBM, n0 = (t2 % n_tiles) * kBN;
+      const TileInfo t = decode_tile(g, tile);
+      const int z = t.z, m0 = t.m0, n0 = t.n0, N = g.N[t.p], kblocks = t.kblocks;
+      const CUtensorMap* mc = GVQA_MAP(map_c, t.p);
       mbar_wait(acc_full, tile_it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int col0 = n0 + chalf * 64;
@@ -243,7 +273,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&map_c, stage, col0 + pass * 32, m0 + quarter * 32, z);
+              tma_store_3d(mc, stage, col0 + pass * 32, m0 + quarter * 32, z);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
@@ -294,38 +324,67 @@ extern "C" GVQA_API int gvqa_split_f16(const float* w, int64_t ld_in, void* hi, 
   return GVQA_OK;
 }
 
-extern "C" GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
-                                                     const void* b_lo, int64_t ldb, int64_t stride_b, float* c,
-                                                     int64_t ldc, int64_t stride_c, int64_t m, int32_t n, int32_t k,
-                                                     int32_t batch, int32_t* overflow, void* stream_) {
+extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* problems, int32_t count, int32_t* overflow,
+                                                     void* stream_) {
   using namespace f16gemm;
-  if (m < 0 || n <= 0 || k <= 0 || batch <= 0 || lda < k || ldb < k || ldc < n || m >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
-  if (m == 0) return GVQA_OK;
-  if (!a || !b_hi || !b_lo || !c) return GVQA_ERR_NULL_POINTER;
-  if ((k & 3) || (lda & 3) || (ldb & 7) || (ldc & 3) || (stride_a & 3) || (stride_b & 7) || (stride_c & 3))
-    return GVQA_ERR_UNSUPPORTED;
-  if (!aligned16(a) || !aligned16(b_hi) || !aligned16(b_lo) || !aligned16(c)) return GVQA_ERR_MISALIGNED;
-  const int64_t sa = batch > 1 ? stride_a : m * lda, sb = batch > 1 ? stride_b : (int64_t)n * ldb,
-                sc = batch > 1 ? stride_c : m * ldc;
-  CUtensorMap map_a, map_bhi, map_blo, map_c;
-  if (!make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, batch, m, k, lda, sa, kBM, 32) ||
-      !make_map_3d(&map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_hi, batch, n, k, ldb, sb, kBN, 64) ||
-      !make_map_3d(&map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, b_lo, batch, n, k, ldb, sb, kBN, 64) ||
-      !make_map_3d(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c, batch, m, n, ldc, sc, 32, 32))
-    return GVQA_ERR_CUDA;
+  if (!problems || count < 1 || count > kMaxProblems) return GVQA_ERR_BAD_SHAPE;
+  GroupedParams g;
+  memset(&g, 0, sizeof(g));
+  int64_t tiles = 0;
+  int live = 0;
+  for (int i = 0; i < count; ++i) {
+    const gvqa_gemm_problem& q = problems[i];
+    if (q.m < 0 || q.n <= 0 || q.k <= 0 || q.batch <= 0 || q.lda < q.k || q.ldb < q.k || q.ldc < q.n || q.m >= (1ll << 31))
+      return GVQA_ERR_BAD_SHAPE;
+    if (q.m == 0) continue;
+    if (!q.a || !q.b_hi || !q.b_lo || !q.c) return GVQA_ERR_NULL_POINTER;
+    if ((q.k & 3) || (q.lda & 3) || (q.ldb & 7) || (q.ldc & 3) || (q.stride_a & 3) || (q.stride_b & 7) || (q.stride_c & 3))
+      return GVQA_ERR_UNSUPPORTED;
+    if (!aligned16(q.a) || !aligned16(q.b_hi) || !aligned16(q.b_lo) || !aligned16(q.c)) return GVQA_ERR_MISALIGNED;
+    const int64_t sa = q.batch > 1 ? q.stride_a : q.m * q.lda, sb = q.batch > 1 ? q.stride_b : (int64_t)q.n * q.ldb,
+                  sc = q.batch > 1 ? q.stride_c : q.m * q.ldc;
+    if (!make_map_3d(&g.map_a[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.a, q.batch, q.m, q.k, q.lda, sa, kBM, 32) ||
+        !make_map_3d(&g.map_bhi[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_hi, q.batch, q.n, q.k, q.ldb, sb, kBN, 64) ||
+        !make_map_3d(&g.map_blo[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_lo, q.batch, q.n, q.k, q.ldb, sb, kBN, 64) ||
+        !make_map_3d(&g.map_c[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.c, q.batch, q.m, q.n, q.ldc, sc, 32, 32))
+      return GVQA_ERR_CUDA;
+    g.M[live] = (int)q.m; g.N[live] = q.n; g.K[live] = q.k;
+    g.n_tiles[live] = (q.n + kBN - 1) / kBN;
+    g.tiles_per_batch[live] = (int)((q.m + kBM - 1) / kBM) * g.n_tiles[live];
+    tiles += (int64_t)g.tiles_per_batch[live] * q.batch;
+    if (tiles >= (1ll << 30)) return GVQA_ERR_BAD_SHAPE;
+    g.tile_end[live] = (int)tiles;
+    ++live;
+  }
+  if (live == 0) return GVQA_OK;
+  for (int i = live; i < kMaxProblems; ++i) {     // unused slots: empty ranges, valid divisors
+    g.tile_end[i] = (int)tiles;
+    g.tiles_per_batch[i] = g.n_tiles[i] = 1;
+    g.K[i] = kBK;
+  }
+  g.count = live;
   static const bool attr_ok =
       cudaFuncSetAttribute(proj_gemm_3xf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) ==
       cudaSuccess;
   if (!attr_ok) return GVQA_ERR_CUDA;
-  const int64_t tiles = ((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * batch;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   if (launch_pdl(1, proj_gemm_3xf16_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, static_cast<cudaStream_t>(stream_),
-                 map_a, map_bhi, map_blo, map_c, (int)m, n, k, (int)batch, overflow) != cudaSuccess) {
+                 g, overflow) != cudaSuccess) {
     (void)cudaGetLastError();
     return GVQA_ERR_CUDA;
   }
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
+                                                     const void* b_lo, int64_t ldb, int64_t stride_b, float* c,
+                                                     int64_t ldc, int64_t stride_c, int64_t m, int32_t n, int32_t k,
+                                                     int32_t batch, int32_t* overflow, void* stream_) {
+  gvqa_gemm_problem q;
+  q.a = a; q.lda = lda; q.stride_a = stride_a; q.b_hi = b_hi; q.b_lo = b_lo; q.ldb = ldb; q.stride_b = stride_b;
+  q.c = c; q.ldc = ldc; q.stride_c = stride_c; q.m = m; q.n = n; q.k = k; q.batch = batch;
+  return gvqa_proj_gemm_3xf16_grouped(&q, 1, overflow, stream_);
 }
 
 extern "C" GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,

@@ -21,6 +21,7 @@ and BatchNorm batch statistics, gat_skip.py:190/274, are not part of the engine)
 is no CPU fallback.
 """
 import contextlib
+import os
 
 import torch
 from torch import nn
@@ -172,6 +173,9 @@ class gat_seq(nn.Module):
         #   "3xtf32" the same kernel structure on tf32-split operands (full fp32 range, ~1.4x slower)
         #   "cublas" torch.mm with TF32 off (fp32 SIMT, ~6x slower)
         self.projection = "3xf16"
+        # "3xf16" only: hop 0's projection and the two pre-pass products share ONE persistent launch (their short
+        # tiles fill the projection's last, partially empty wave); False = three launches
+        self.group_prepass = os.environ.get("GVQA_GROUP_PREPASS", "1") != "0"
         self._overflow, self._overflow_pending = None, []
         self.overflow_external = False   # True: the caller reads / clears the fp16 range flag itself (host runner)
         self._side = None
@@ -276,13 +280,31 @@ class gat_seq(nn.Module):
         else:
             def gemm(a, split, out=None):
                 return _cabi.proj_gemm_3xtf32(a, split[0], split[1], out=out)
-        if e == 0:
+        hc = heads * c
+        fused_logits = tensor_core
+        ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
+        x_l = torch.empty(n, ldx, dtype=torch.float32, device=x.device)
+        grouped = self.projection == "3xf16" and self.group_prepass and n > 0 and self.gemm_events is None
+        if grouped:
+            ld = pk["ins_ld"]
+            bh, bl = (t.unflatten(0, (num_hops, ld)) for t in pk["ins_split"])
+            problems = [(x, pk["w_split"][0][0], pk["w_split"][0][1], x_l), (ins, bh, bl, None)]
+            if e > 0:
+                problems.append((edge_attr, pk["edge_split"][0], pk["edge_split"][1], None))
+            outs = _cabi.proj_gemm_3xf16_grouped(problems, overflow=flag)
+            g_all = outs[1]
+            a_edge_all = outs[2] if e > 0 else x.new_zeros(1, num_hops * heads)
+            graph_bias_all = [g_all[i, :, :c] for i in range(num_hops)]
+            a_graph_all = [g_all[i, :, c:c + heads] for i in range(num_hops)]
+        elif e == 0:
             a_edge_all = x.new_zeros(1, num_hops * heads)
         elif tensor_core:
             a_edge_all = gemm(edge_attr, pk["edge_split"])                      # [E, hops*H (+pad)], one sweep
         else:
             a_edge_all = _cabi.skinny_matmul(edge_attr, pk["v_edge"])           # [E, hops*H]
-        if tensor_core:
+        if grouped:
+            pass
+        elif tensor_core:
             # one GEMM for every hop's per-graph terms: rows = (hop, graph), columns = (hop', C + H); only the
             # hop == hop' blocks are used (the cross blocks are wasted flops, ~5 us, cheaper than 5 launches)
             ld = pk["ins_ld"]
@@ -302,10 +324,6 @@ class gat_seq(nn.Module):
 
         h = x
         hops = []
-        fused_logits = tensor_core
-        hc = heads * c
-        ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
-        x_l = torch.empty(n, ldx, dtype=torch.float32, device=x.device)
         a_node = x_l[:, hc:hc + 2 * heads] if fused_logits else \
             torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
         if self.l2_persist:
@@ -316,7 +334,8 @@ class gat_seq(nn.Module):
                     gev = (torch.cuda.Event(enable_timing=True, external=capturing),
                            torch.cuda.Event(enable_timing=True, external=capturing))
                     gev[0].record()
-                gemm(h, pk["w_split"][i], out=x_l)
+                if not (grouped and i == 0):
+                    gemm(h, pk["w_split"][i], out=x_l)
                 if self.gemm_events is not None:
                     gev[1].record()
                     self.gemm_events.append(gev)
@@ -342,7 +361,8 @@ class gat_seq(nn.Module):
                               epilogue=_cabi.EPI_NONE if last else _cabi.EPI_AFFINE_RELU,
                               variant=self.kernel_variant,
                               # topology and pre-pass outputs are older than the projection launched just above
-                              inputs_older_than_predecessor=fused_logits, **csr.hints())
+                              # (except hop 0 of a grouped launch, whose predecessor also wrote the pre-pass outputs)
+                              inputs_older_than_predecessor=fused_logits and not (grouped and i == 0), **csr.hints())
             if self.hop_events is not None:
                 ev[1].record()
                 self.hop_events.append(ev)

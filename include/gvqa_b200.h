@@ -208,6 +208,21 @@ GVQA_API int gvqa_proj_gemm_3xf16(const float* a, int64_t lda, const void* b_hi,
 /* `batch` independent products C[z] = A[z] @ B[z]^T in one launch (element strides between consecutive z; stride_a
  * and stride_c multiples of 4, stride_b a multiple of 8): gat_seq's per-hop instruction terms
  * [hops, B, D] x [hops, C+H, D]^T (gat_skip.py:256-264, split cat). */
+/* Several independent products in ONE persistent launch (at most 3; tiles of problem 0 are scheduled first).
+ * gat_seq issues hop 0's projection together with its two small pre-pass products this way. */
+typedef struct gvqa_gemm_problem {
+  const float* a;          /* [batch, m, k] fp32, row stride lda, batch stride stride_a (elements) */
+  int64_t lda, stride_a;
+  const void* b_hi;        /* [batch, n, k] fp16 from gvqa_split_f16, row stride ldb, batch stride stride_b */
+  const void* b_lo;
+  int64_t ldb, stride_b;
+  float* c;                /* [batch, m, n] fp32, row stride ldc, batch stride stride_c */
+  int64_t ldc, stride_c;
+  int64_t m;
+  int32_t n, k, batch;     /* batch >= 1; the strides are ignored when batch == 1 */
+} gvqa_gemm_problem;
+GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* problems, int32_t count, int32_t* overflow,
+                                          void* stream);
 GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
                                           const void* b_lo, int64_t ldb, int64_t stride_b, float* c, int64_t ldc,
                                           int64_t stride_c, int64_t m, int32_t n, int32_t k, int32_t batch,

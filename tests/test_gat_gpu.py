@@ -255,6 +255,25 @@ def test_gat_seq_projection_paths_agree():
     assert (c - b).abs().max() <= 2e-5
 
 
+@pytest.mark.parametrize("edges", [True, False])
+def test_gat_seq_grouped_prepass_launch_is_bitwise_the_three_launches(edges):
+    """hop 0's projection + the two pre-pass products in one persistent launch (default) vs three launches:
+    identical tiles and k order, so identical bits; also with an edgeless batch (two problems)."""
+    cfg = dict(in_channels=300, out_channels=300, edge_attr_dim=300, ins_dim=512, num_ins=5, gat_heads=4)
+    _, e = _pair(cfg, seed=61)
+    ei, batch = random_graphs(20, 5, 40, 2.0, seed=7)
+    if not edges:
+        ei = ei[:, :0]
+    args = [a.to(DEV) for a in _inputs(ei, batch, 20, 300, 300, 512, 5, seed=62)]
+    with torch.no_grad():
+        e.group_prepass = True; a, ha = e(*args, return_hops=True)
+        e.group_prepass = False; b, hb = e(*args, return_hops=True)
+    e.check_overflow()
+    for x, y in zip(ha, hb):
+        assert torch.equal(x, y)
+    assert torch.equal(a, b)
+
+
 def test_gat_seq_fp16_projection_flags_out_of_range_inputs():
     """The default fp16-split projection refuses to return silently wrong results for |x| >= 65504."""
     cfg = dict(in_channels=64, out_channels=64, edge_attr_dim=64, ins_dim=32, num_ins=2, gat_heads=4)

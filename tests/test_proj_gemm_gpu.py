@@ -137,3 +137,50 @@ def test_proj_gemm_3xf16_batched_matches_fp64():
     want = torch.einsum("zmk,znk->zmn", a.double(), b.view(z, n, k).double())
     assert int(flag) == 0
     assert (out.double() - want).abs().max() <= 2e-6 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("shapes", [
+    [(7680, 2064, 512), (5, 256, 528, 512), (15360, 32, 512)],      # gat_seq at cfg2: hop-0 projection + both pre-pass products
+    [(120, 1216, 300), (5, 4, 320, 512), (236, 32, 300)],           # reference dims, cfg1-sized batch, three different K
+    [(59, 260, 36), (130, 16, 64)],
+])
+def test_proj_gemm_3xf16_grouped_equals_separate_launches(shapes):
+    """One persistent launch over several products returns bit for bit what one launch per product returns
+    (same tile decomposition and k order), and both sit at fp32-level error against float64."""
+    g = torch.Generator().manual_seed(len(shapes) + shapes[0][0])
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    problems, separate, wants = [], [], []
+    for shp in shapes:
+        if len(shp) == 4:
+            z, m, n, k = shp
+            a = (torch.randn(z, m, k, generator=g) * 2.0).to(DEV)
+            b = (torch.randn(z * n, k, generator=g) * 0.05).to(DEV)
+            hi, lo = (t.unflatten(0, (z, n)) for t in _cabi.split_f16(b))
+            separate.append(_cabi.proj_gemm_3xf16_batched(a, hi, lo, overflow=flag))
+            wants.append(torch.einsum("zmk,znk->zmn", a.double(), b.view(z, n, k).double()))
+        else:
+            m, n, k = shp
+            a = (torch.randn(m, k, generator=g) * 2.0).to(DEV)
+            b = (torch.randn(n, k, generator=g) * 0.05).to(DEV)
+            hi, lo = _cabi.split_f16(b)
+            separate.append(_cabi.proj_gemm_3xf16(a, hi, lo, overflow=flag))
+            wants.append(a.double() @ b.double().t())
+        problems.append((a, hi, lo, None))
+    outs = _cabi.proj_gemm_3xf16_grouped(problems, overflow=flag)
+    assert int(flag) == 0
+    for out, sep, want in zip(outs, separate, wants):
+        assert torch.equal(out, sep)
+        assert (out.double() - want).abs().max() <= 2e-6 * float(want.abs().max())
+
+
+def test_proj_gemm_3xf16_grouped_rejects_bad_counts_and_skips_empty():
+    a = torch.randn(64, 64, device=DEV)
+    hi, lo = _cabi.split_f16(torch.randn(32, 64, device=DEV))
+    with pytest.raises(ValueError):
+        _cabi.proj_gemm_3xf16_grouped([], None)
+    with pytest.raises(ValueError):
+        _cabi.proj_gemm_3xf16_grouped([(a, hi, lo, None)] * 4, None)
+    empty = torch.empty(0, 64, device=DEV)
+    outs = _cabi.proj_gemm_3xf16_grouped([(empty, hi, lo, None), (a, hi, lo, None)], None)
+    assert outs[0].shape == (0, 32)
+    assert torch.equal(outs[1], _cabi.proj_gemm_3xf16(a, hi, lo))
