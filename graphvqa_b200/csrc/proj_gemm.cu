@@ -320,6 +320,9 @@ static long long* g_gemm_trace = nullptr;   // debug only: set through gvqa_debu
 static int g_gemm_dbg = 0;                  // debug only: set through gvqa_debug_set_gemm_flags
 extern "C" GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer) { g_gemm_trace = device_buffer; }
 extern "C" GVQA_API void gvqa_debug_set_gemm_flags(int flags) { g_gemm_dbg = flags; }
+namespace gvqa {
+int gemm_debug_flags() { return g_gemm_dbg; }
+}
 
 extern "C" GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream_) {
   if (count < 0) return GVQA_ERR_BAD_SHAPE;

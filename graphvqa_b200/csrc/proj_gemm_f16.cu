@@ -27,21 +27,35 @@ namespace gvqa {
 namespace f16gemm {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;       // tile: rows of A, rows of B, k elements per k-block
-constexpr int kStages = 3;                          // shared-memory ring
-constexpr int kAStages = 2;                         // tensor-memory ring of split A tiles
-constexpr int kGemmThreads = 448;                   // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-13 epilogue
-constexpr int kConvThreads = 128;
+constexpr int kAStages = 4;                         // tensor-memory ring of split A sub-blocks (32 k-elements each)                         // tensor-memory ring of split A tiles
+// warp 0 TMA, warp 1 MMA, then 4 x CH converter warps (CH = 1: a thread converts a whole 64-float row of the
+// k-block; CH = 2: two warps per TMEM lane quarter, one [128 x 32] box each), then 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kAHalfBytes = kBM * 32 * 4;      // one [128 x 32] fp32 box = 16 KB
 constexpr uint32_t kABytes = 2 * kAHalfBytes;       // 32 KB
-constexpr uint32_t kBBytes = kBN * kBK * 2;         // 16 KB
-constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;       // 64 KB
+// PAIR = 1: one CTA per 128 x 128 tile.  PAIR = 2: a two-CTA cluster (the two SMs of a TPC) owns a 256 x 128 tile;
+// each CTA loads and converts its own 128 rows of A but only HALF of the B tile, and the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256), which reads both halves.  That removes 24 of the 144 KB of shared-memory
+// traffic per k-block and a quarter of the L2 -> SM traffic, and the smaller stages allow a 4-deep ring
+// (profiles/r01/gemm_f16_stage_attribution.txt: 49.2 -> 46.9 us at cfg2; step 0.381 -> 0.369 ms).
+template <int PAIR>
+struct Cfg {
+  static constexpr int kBRows = kBN / PAIR;                              // B rows a CTA stages per k-block
+  static constexpr uint32_t kBBytes = kBRows * kBK * 2;                  // 16 KB / 8 KB
+  static constexpr uint32_t kStageBytes = kABytes + 2 * kBBytes;         // 64 KB / 48 KB
+  static constexpr int kStages = PAIR == 2 ? 4 : 3;                      // shared-memory ring (192 KB either way)
+};
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemSmall = 2 * kBN;            // accumulators: [0,128) hi*hi first K-half, [128,256) second, [256,384) lo terms
-constexpr uint32_t kTmemA = 3 * kBN;                // A ring: 2 stages x (32 columns hi | 32 columns lo'), 2 halves per column
-constexpr uint32_t kACols = kBK / 2;                // 32 TMEM columns per 64 fp16
+// A ring: 4 sub-blocks x (16 columns hi | 16 columns lo'), two fp16 per 32-bit column.  A sub-block is one
+// [128 x 32] fp32 box of a stage (the MMAs of a sub-block start as soon as its box is converted).  Measured equal
+// to a ring of two whole k-blocks (46.9 vs 46.8 us at cfg2, profiles/r01/gemm_f16_stage_attribution.txt).
+constexpr uint32_t kTmemA = 3 * kBN;
+constexpr uint32_t kASubCols = 32;                  // TMEM columns per sub-block (hi at +0, lo' at +16)
 constexpr uint32_t kEpiStageBytes = 32 * 32 * 4;
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + (kEpiThreads / 32) * kEpiStageBytes + 1024 + 256;
+constexpr size_t kGemmSmem = (size_t)3 * 65536 + (kEpiThreads / 32) * kEpiStageBytes + 1024 + 256;
+static_assert(Cfg<1>::kStages * Cfg<1>::kStageBytes == 3 * 65536 && Cfg<2>::kStages * Cfg<2>::kStageBytes == 3 * 65536,
+              "both configurations use the same 192 KB operand ring");
 constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {   // a -> low half (lower k), b -> high half
@@ -55,6 +69,64 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(h);
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of both CTAs; also a CTA-wide barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// arrive on the mbarrier that sits at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
+template <int PAIR>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  if constexpr (PAIR == 2) mbar_arrive_cta(bar, 0);
+  else mbar_arrive(bar);
+}
+
+// completion of all MMAs issued so far -> the barrier at this offset (PAIR = 2: in BOTH CTAs of the pair)
+template <int PAIR>
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+  if constexpr (PAIR == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+
+template <int PAIR>
+__device__ __forceinline__ void umma_f16_ts_x(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if constexpr (PAIR == 2) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_f16_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
+  }
+}
+
 // Up to kMaxProblems independent products share one persistent launch (tiles of problem 0 first, then 1, ...):
 // gat_seq issues hop 0's projection together with the two small pre-pass products, whose ~170 short tiles then
 // fill the last, partially empty wave instead of costing two more launches.
@@ -66,19 +138,21 @@ struct alignas(64) GroupedParams {
   int tiles_per_batch[kMaxProblems], n_tiles[kMaxProblems];
   int tile_end[kMaxProblems];      // exclusive prefix of tiles
   int count;
+  int dbg;   // debug only (gvqa_debug_set_gemm_flags): bit0 no TMA loads, bit1 converters idle, bit2 no epilogue, bit3 no MMAs
 };
 
 struct TileInfo {
   int p, z, m0, n0, kblocks;
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const GroupedParams& g, int tile) {
+template <int PAIR>
+__device__ __forceinline__ TileInfo decode_tile(const GroupedParams& g, int tile, int rank) {
   TileInfo t;
   t.p = tile < g.tile_end[0] ? 0 : (tile < g.tile_end[1] ? 1 : 2);
   const int local = tile - (t.p == 0 ? 0 : g.tile_end[t.p - 1]);
   t.z = local / g.tiles_per_batch[t.p];
   const int t2 = local - t.z * g.tiles_per_batch[t.p];
-  t.m0 = (t2 / g.n_tiles[t.p]) * kBM;
+  t.m0 = (t2 / g.n_tiles[t.p]) * (kBM * PAIR) + rank * kBM;   // PAIR = 2: the pair's tile is 256 rows, 128 per CTA
   t.n0 = (t2 % g.n_tiles[t.p]) * kBN;
   t.kblocks = (g.K[t.p] + kBK - 1) / kBK;          // the ragged last k-block is zero-filled by TMA
   return t;
@@ -86,9 +160,12 @@ __device__ __forceinline__ TileInfo decode_tile(const GroupedParams& g, int tile
 
 #define GVQA_MAP(field, p) ((p) == 0 ? &g.field[0] : ((p) == 1 ? &g.field[1] : &g.field[2]))
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int CH, int PAIR>
+__global__ void __launch_bounds__(64 + 128 * CH + kEpiThreads, 1)
 proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restrict__ overflow) {
   // all tensor maps are 3-D [batch, rows, K]; a tile index decomposes into (problem, batch z, row tile, column tile)
+  constexpr int kStages = Cfg<PAIR>::kStages;
+  constexpr uint32_t kStageBytes = Cfg<PAIR>::kStageBytes, kBBytes = Cfg<PAIR>::kBBytes;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;
@@ -101,8 +178,15 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
+  constexpr int kFirstEpiWarp = 2 + 4 * CH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = g.tile_end[g.count - 1];
+  const int dbg = g.dbg;
+  // PAIR = 2: `rank` is the CTA's place in its pair (0 = leader: owns a_ready / acc_empty and issues the MMAs);
+  // tiles are dealt to pairs, not CTAs
+  const int rank = PAIR == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = PAIR == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -110,21 +194,29 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
       mbar_init(&smem_empty[s], 1);
     }
     for (int s = 0; s < kAStages; ++s) {
-      mbar_init(&a_ready[s], kConvThreads);
+      mbar_init(&a_ready[s], 128 * PAIR);             // a sub-block is converted by one warp per lane quarter (per CTA)
       mbar_init(&a_empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kEpiThreads);
+    mbar_init(acc_empty, kEpiThreads * PAIR);
     mbar_fence_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {                                         // PAIR = 2: the same warp of both CTAs allocates collectively
+    if constexpr (PAIR == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (PAIR == 2) cluster_sync_all();             // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -135,109 +227,124 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
     // ===================== TMA producer: one elected lane runs the whole loop =====================
     if (elect_one()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile(g, tile);
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const TileInfo t = decode_tile<PAIR>(g, tile, rank);
         const CUtensorMap *ma = GVQA_MAP(map_a, t.p), *mh = GVQA_MAP(map_bhi, t.p), *ml = GVQA_MAP(map_blo, t.p);
+        // PAIR = 2: this CTA stages rows [rank * ncols / 2, +ncols / 2) of the B tile (the box is 64 rows; the MMA reads
+        // only the first ncols / 2 of them)
+        const int nb0 = PAIR == 2 ? t.n0 + rank * (min(kBN, (g.N[t.p] - t.n0 + 31) & ~31) >> 1) : t.n0;
         for (int kb = 0; kb < t.kblocks; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + (size_t)s * kStageBytes;
+          if (dbg & 1) { mbar_arrive(&tma_full[s]); continue; }
           mbar_expect_tx(&tma_full[s], kStageBytes);
           tma_load_3d(st, ma, &tma_full[s], kb * kBK, t.m0, t.z);
           tma_load_3d(st + kAHalfBytes, ma, &tma_full[s], kb * kBK + 32, t.m0, t.z);
-          tma_load_3d(st + kABytes, mh, &tma_full[s], kb * kBK, t.n0, t.z);
-          tma_load_3d(st + kABytes + kBBytes, ml, &tma_full[s], kb * kBK, t.n0, t.z);
+          tma_load_3d(st + kABytes, mh, &tma_full[s], kb * kBK, nb0, t.z);
+          tma_load_3d(st + kABytes + kBBytes, ml, &tma_full[s], kb * kBK, nb0, t.z);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: one elected lane runs the whole loop =====================
-    if (elect_one()) {
+    if ((PAIR == 1 || rank == 0) && elect_one()) {
       uint32_t it = 0, tile_it = 0;
       const uint64_t desc0 = umma_desc(smem_u32(smem));   // descriptor of (base + c) == desc0 + (c >> 4)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tile_it) {
         // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, M = 128, N = tile width (x16)
-        const TileInfo t = decode_tile(g, tile);
+        const TileInfo t = decode_tile<PAIR>(g, tile, rank);
         const int kblocks = t.kblocks;
         const int half_kb = (kblocks + 1) / 2;            // first k-block of the second K-half
-        const int ncols = min(kBN, (g.N[t.p] - t.n0 + 15) & ~15);
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const int ncols = PAIR == 2 ? min(kBN, (g.N[t.p] - t.n0 + 31) & ~31) : min(kBN, (g.N[t.p] - t.n0 + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)((kBM * PAIR) >> 4) << 24);
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const uint32_t s = it % kStages, ts = it & 1;
-          mbar_wait(&a_ready[ts], (it >> 1) & 1);         // implies tma_full[s]: the converters waited on it
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t s = it % kStages;
           const uint64_t b_hi = desc0 + (uint64_t)((s * kStageBytes + kABytes) >> 4), b_lo = b_hi + (kBBytes >> 4);
-          const uint32_t a_hi = tmem_base + kTmemA + ts * 2 * kACols, a_lo = a_hi + kACols;
           const bool second = kb >= half_kb;
           const bool chunk_first = kb == 0 || kb == half_kb;
           const uint32_t d_big = tmem_base + (second ? (uint32_t)kBN : 0u), d_small = tmem_base + kTmemSmall;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {            // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
-            umma_f16_ts(d_small, a_lo + 8 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
-            umma_f16_ts(d_small, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
-            umma_f16_ts(d_big, a_hi + 8 * k, b_hi + 2 * k, idesc, !(chunk_first && k == 0));
+          for (int half = 0; half < 2; ++half) {          // the two 32-k sub-blocks of the stage
+            const uint32_t sub = 2 * it + half, ss = sub & (kAStages - 1);
+            mbar_wait(&a_ready[ss], (sub / kAStages) & 1);  // implies tma_full[s]: the converters waited on it
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tmem_base + kTmemA + ss * kASubCols, a_lo = a_hi + kASubCols / 2;
+            if (!(dbg & 8)) {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {            // K = 16 per MMA: 8 TMEM columns of A, 32 bytes of B
+                const int k = 2 * half + kk;
+                umma_f16_ts_x<PAIR>(d_small, a_lo + 8 * kk, b_hi + 2 * k, idesc, (kb | k) != 0);
+                umma_f16_ts_x<PAIR>(d_small, a_hi + 8 * kk, b_lo + 2 * k, idesc, 1);
+                umma_f16_ts_x<PAIR>(d_big, a_hi + 8 * kk, b_hi + 2 * k, idesc, !(chunk_first && k == 0));
+              }
+            }
+            umma_commit_to<PAIR>(&a_empty[ss]);
           }
-          umma_commit(&smem_empty[s]);
-          umma_commit(&a_empty[ts]);
-          if (kb == kblocks - 1) umma_commit(acc_full);
+          umma_commit_to<PAIR>(&smem_empty[s]);
+          if (kb == kblocks - 1) umma_commit_to<PAIR>(acc_full);
         }
       }
     }
-  } else if (warp < 6) {
-    // ===================== converters (warps 2..5): thread = one row of the A tile ===============
-    const int quarter = warp & 3;
+  } else if (warp < kFirstEpiWarp) {
+    // ===================== converters: thread = one row of the A tile (CH = 2: of one of its two boxes) =========
+    const int quarter = warp & 3;                          // TMEM lane quarter a warp may touch = warp id % 4
+    const int half0 = CH == 2 ? (warp - 2) >> 2 : 0;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t it = 0;
     float amax = 0.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int kblocks = decode_tile(g, tile).kblocks;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int kblocks = decode_tile<PAIR>(g, tile, rank).kblocks;
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int s = it % kStages, ts = it & 1;
+        const int s = it % kStages;
         mbar_wait(&tma_full[s], (it / kStages) & 1);
-        mbar_wait(&a_empty[ts], ((it >> 1) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t row_addr = smem_u32(smem + (size_t)s * kStageBytes) + (uint32_t)r * 128u;
-        const uint32_t ta = tmem_base + lane_base + kTmemA + (uint32_t)ts * 2 * kACols;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {             // the two [128 x 32] fp32 boxes of the stage
-          uint32_t hi[16], lo[16];
+        for (int half = half0; half < half0 + 2 / CH; ++half) {   // the [128 x 32] fp32 boxes of the stage this warp owns
+          const uint32_t sub = 2 * it + half, ss = sub & (kAStages - 1);
+          mbar_wait(&a_empty[ss], ((sub / kAStages) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (!(dbg & 2)) {
+            const uint32_t ta = tmem_base + lane_base + kTmemA + ss * kASubCols;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int cidx = 0; cidx < 8; ++cidx) {           // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
-            const float4 v = lds128(row_addr + half * kAHalfBytes + (uint32_t)((cidx ^ (r & 7)) * 16));
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-            const uint32_t h01 = pack_half2(v.x, v.y), h23 = pack_half2(v.z, v.w);
-            const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
-            hi[2 * cidx] = h01;
-            hi[2 * cidx + 1] = h23;
-            lo[2 * cidx] = pack_half2((v.x - f01.x) * kLoScale, (v.y - f01.y) * kLoScale);
-            lo[2 * cidx + 1] = pack_half2((v.z - f23.x) * kLoScale, (v.w - f23.y) * kLoScale);
+            for (int cidx = 0; cidx < 8; ++cidx) {         // 128B swizzle: 16-byte chunk c lives at c ^ (row & 7)
+              const float4 v = lds128(row_addr + half * kAHalfBytes + (uint32_t)((cidx ^ (r & 7)) * 16));
+              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+              const uint32_t h01 = pack_half2(v.x, v.y), h23 = pack_half2(v.z, v.w);
+              const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
+              hi[2 * cidx] = h01;
+              hi[2 * cidx + 1] = h23;
+              lo[2 * cidx] = pack_half2((v.x - f01.x) * kLoScale, (v.y - f01.y) * kLoScale);
+              lo[2 * cidx + 1] = pack_half2((v.z - f23.x) * kLoScale, (v.w - f23.y) * kLoScale);
+            }
+            GVQA_TMEM_ST16(ta, hi, 0);
+            GVQA_TMEM_ST16(ta + kASubCols / 2, lo, 0);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           }
-          GVQA_TMEM_ST16(ta + half * 16, hi, 0);
-          GVQA_TMEM_ST16(ta + kACols + half * 16, lo, 0);
+          mbar_arrive_leader<PAIR>(&a_ready[ss]);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(&a_ready[ts]);
       }
     }
     if (overflow != nullptr && !(amax <= 65000.0f)) atomicOr(overflow, 1);   // also catches NaN / inf inputs
   } else {
-    // ===================== epilogue (warps 6..13): TMEM -> registers, release TMEM, then TMA store =============
+    // ===================== epilogue (8 warps): TMEM -> registers, release TMEM, then TMA store =============
     const int quarter = warp & 3;
-    const int chalf = warp >= 10 ? 1 : 0;
+    const int chalf = warp >= kFirstEpiWarp + 4 ? 1 : 0;
     uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const TileInfo t = decode_tile(g, tile);
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++tile_it) {
+      const TileInfo t = decode_tile<PAIR>(g, tile, rank);
       const int z = t.z, m0 = t.m0, n0 = t.n0, N = g.N[t.p], kblocks = t.kblocks;
       const CUtensorMap* mc = GVQA_MAP(map_c, t.p);
       mbar_wait(acc_full, tile_it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int col0 = n0 + chalf * 64;
       float acc[64];
-      const bool live = col0 < N;
+      const bool live = col0 < N && !(dbg & 4);
       const bool two_chunks = kblocks >= 2;                // with a single k-block the second K-half is never written
       if (live) {
 #pragma unroll
@@ -256,9 +363,9 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(acc_empty);                              // TMEM is free: the next tile's MMAs may start
+      mbar_arrive_leader<PAIR>(acc_empty);                 // TMEM is free: the next tile's MMAs may start
       if (live) {
-        const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - 6) * kEpiStageBytes);
+        const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           if (col0 + pass * 32 < N) {
@@ -286,9 +393,14 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  if constexpr (PAIR == 2) {
+    cluster_sync_all();       // neither CTA leaves (or frees tensor memory) while its peer may still signal or read it
+    if (warp == 1)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  } else {
+    __syncthreads();
+    if (warp == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -328,6 +440,14 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* pr
                                                      void* stream_) {
   using namespace f16gemm;
   if (!problems || count < 1 || count > kMaxProblems) return GVQA_ERR_BAD_SHAPE;
+  // two-CTA pairs (default) or one CTA per tile: GVQA_GEMM_PAIR=1 / debug flag 32 select the single-CTA kernel
+  static const int env_pair = [] {
+    const char* e = getenv("GVQA_GEMM_PAIR");
+    return e ? atoi(e) : 2;
+  }();
+  const int flags = gemm_debug_flags();
+  const int pair = (env_pair == 1 || (flags & 32)) ? 1 : 2;
+  const int conv_halves = (flags & 16) ? 2 : 1;       // debug only: eight converter warps instead of four
   GroupedParams g;
   memset(&g, 0, sizeof(g));
   int64_t tiles = 0;
@@ -344,13 +464,13 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* pr
     const int64_t sa = q.batch > 1 ? q.stride_a : q.m * q.lda, sb = q.batch > 1 ? q.stride_b : (int64_t)q.n * q.ldb,
                   sc = q.batch > 1 ? q.stride_c : q.m * q.ldc;
     if (!make_map_3d(&g.map_a[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.a, q.batch, q.m, q.k, q.lda, sa, kBM, 32) ||
-        !make_map_3d(&g.map_bhi[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_hi, q.batch, q.n, q.k, q.ldb, sb, kBN, 64) ||
-        !make_map_3d(&g.map_blo[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_lo, q.batch, q.n, q.k, q.ldb, sb, kBN, 64) ||
+        !make_map_3d(&g.map_bhi[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_hi, q.batch, q.n, q.k, q.ldb, sb, kBN / pair, 64) ||
+        !make_map_3d(&g.map_blo[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, q.b_lo, q.batch, q.n, q.k, q.ldb, sb, kBN / pair, 64) ||
         !make_map_3d(&g.map_c[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.c, q.batch, q.m, q.n, q.ldc, sc, 32, 32))
       return GVQA_ERR_CUDA;
     g.M[live] = (int)q.m; g.N[live] = q.n; g.K[live] = q.k;
     g.n_tiles[live] = (q.n + kBN - 1) / kBN;
-    g.tiles_per_batch[live] = (int)((q.m + kBM - 1) / kBM) * g.n_tiles[live];
+    g.tiles_per_batch[live] = (int)((q.m + kBM * pair - 1) / (kBM * pair)) * g.n_tiles[live];
     tiles += (int64_t)g.tiles_per_batch[live] * q.batch;
     if (tiles >= (1ll << 30)) return GVQA_ERR_BAD_SHAPE;
     g.tile_end[live] = (int)tiles;
@@ -363,13 +483,41 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* pr
     g.K[i] = kBK;
   }
   g.count = live;
-  static const bool attr_ok =
-      cudaFuncSetAttribute(proj_gemm_3xf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) ==
-      cudaSuccess;
-  if (!attr_ok) return GVQA_ERR_CUDA;
-  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  if (launch_pdl(1, proj_gemm_3xf16_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, static_cast<cudaStream_t>(stream_),
-                 g, overflow) != cudaSuccess) {
+  g.dbg = flags & 15;
+  auto kernel = pair == 2 ? (conv_halves == 2 ? proj_gemm_3xf16_kernel<2, 2> : proj_gemm_3xf16_kernel<1, 2>)
+                          : (conv_halves == 2 ? proj_gemm_3xf16_kernel<2, 1> : proj_gemm_3xf16_kernel<1, 1>);
+  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  if (!attr_done[pair - 1][conv_halves - 1]) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return GVQA_ERR_CUDA;
+    }
+    attr_done[pair - 1][conv_halves - 1] = true;
+  }
+  // one persistent CTA per SM; with pairs, one cluster of two per TPC and tiles dealt to clusters
+  const int64_t units = pair == 2 ? kNumSMs / 2 : kNumSMs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((tiles < units ? tiles : units) * pair));
+  cfg.blockDim = dim3(64 + 128 * conv_halves + kEpiThreads);
+  cfg.dynamicSmemBytes = kGemmSmem;
+  cfg.stream = static_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_mask() & 1) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (cudaLaunchKernelEx(&cfg, kernel, g, overflow) != cudaSuccess) {
     (void)cudaGetLastError();
     return GVQA_ERR_CUDA;
   }
