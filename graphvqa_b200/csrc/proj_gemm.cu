@@ -322,6 +322,7 @@ extern "C" GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer) { g
 extern "C" GVQA_API void gvqa_debug_set_gemm_flags(int flags) { g_gemm_dbg = flags; }
 namespace gvqa {
 int gemm_debug_flags() { return g_gemm_dbg; }
+long long* gemm_debug_trace() { return g_gemm_trace; }
 }
 
 extern "C" GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream_) {

@@ -138,6 +138,7 @@ struct alignas(64) GroupedParams {
   int tiles_per_batch[kMaxProblems], n_tiles[kMaxProblems];
   int tile_end[kMaxProblems];      // exclusive prefix of tiles
   int count;
+  long long* trace;   // debug only (gvqa_debug_set_gemm_trace): CTA 0 records clock64() per k-block and role
   int dbg;   // debug only (gvqa_debug_set_gemm_flags): bit0 no TMA loads, bit1 converters idle, bit2 no epilogue, bit3 no MMAs
 };
 
@@ -164,6 +165,12 @@ template <int CH, int PAIR>
 __global__ void __launch_bounds__(64 + 128 * CH + kEpiThreads, 1)
 proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restrict__ overflow) {
   // all tensor maps are 3-D [batch, rows, K]; a tile index decomposes into (problem, batch z, row tile, column tile)
+  // trace rows: [it][0] producer past smem_empty, [1] converter past tma_full, [2] past a_empty (first box), [3] done,
+  // [4] MMA loop top, [5] past a_ready (first box), [6] past a_ready (second box), [7] committed;
+  // [1024 + tile][0] MMA before acc_empty, [1] after, [2] epilogue past acc_full, [3] TMEM released, [4] stores issued
+  // (profiles/microbench/trace_gemm_f16.py)
+#define GVQA_F16_TRACE(slot, col) \
+  do { if (g.trace && blockIdx.x == 0 && (slot) < 1100) g.trace[(slot) * 8 + (col)] = clock64(); } while (0)
   constexpr int kStages = Cfg<PAIR>::kStages;
   constexpr uint32_t kStageBytes = Cfg<PAIR>::kStageBytes, kBBytes = Cfg<PAIR>::kBBytes;
   extern __shared__ unsigned char smem_raw[];
@@ -237,6 +244,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
           const int s = it % kStages;
           mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + (size_t)s * kStageBytes;
+          GVQA_F16_TRACE(it, 0);
           if (dbg & 1) { mbar_arrive(&tma_full[s]); continue; }
           mbar_expect_tx(&tma_full[s], kStageBytes);
           tma_load_3d(st, ma, &tma_full[s], kb * kBK, t.m0, t.z);
@@ -258,10 +266,13 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
         const int half_kb = (kblocks + 1) / 2;            // first k-block of the second K-half
         const int ncols = PAIR == 2 ? min(kBN, (g.N[t.p] - t.n0 + 31) & ~31) : min(kBN, (g.N[t.p] - t.n0 + 15) & ~15);
         const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)((kBM * PAIR) >> 4) << 24);
+        GVQA_F16_TRACE(1024 + tile_it, 0);
         mbar_wait(acc_empty, (tile_it & 1) ^ 1);
+        GVQA_F16_TRACE(1024 + tile_it, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const uint32_t s = it % kStages;
+          GVQA_F16_TRACE(it, 4);
           const uint64_t b_hi = desc0 + (uint64_t)((s * kStageBytes + kABytes) >> 4), b_lo = b_hi + (kBBytes >> 4);
           const bool second = kb >= half_kb;
           const bool chunk_first = kb == 0 || kb == half_kb;
@@ -270,6 +281,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
           for (int half = 0; half < 2; ++half) {          // the two 32-k sub-blocks of the stage
             const uint32_t sub = 2 * it + half, ss = sub & (kAStages - 1);
             mbar_wait(&a_ready[ss], (sub / kAStages) & 1);  // implies tma_full[s]: the converters waited on it
+            GVQA_F16_TRACE(it, 5 + half);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = tmem_base + kTmemA + ss * kASubCols, a_lo = a_hi + kASubCols / 2;
             if (!(dbg & 8)) {
@@ -285,6 +297,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
           }
           umma_commit_to<PAIR>(&smem_empty[s]);
           if (kb == kblocks - 1) umma_commit_to<PAIR>(acc_full);
+          GVQA_F16_TRACE(it, 7);
         }
       }
     }
@@ -301,11 +314,13 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % kStages;
         mbar_wait(&tma_full[s], (it / kStages) & 1);
+        if (threadIdx.x == 64) GVQA_F16_TRACE(it, 1);
         const uint32_t row_addr = smem_u32(smem + (size_t)s * kStageBytes) + (uint32_t)r * 128u;
 #pragma unroll
         for (int half = half0; half < half0 + 2 / CH; ++half) {   // the [128 x 32] fp32 boxes of the stage this warp owns
           const uint32_t sub = 2 * it + half, ss = sub & (kAStages - 1);
           mbar_wait(&a_empty[ss], ((sub / kAStages) & 1) ^ 1);
+          if (threadIdx.x == 64 && half == 0) GVQA_F16_TRACE(it, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (!(dbg & 2)) {
             const uint32_t ta = tmem_base + lane_base + kTmemA + ss * kASubCols;
@@ -328,6 +343,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
           }
           mbar_arrive_leader<PAIR>(&a_ready[ss]);
         }
+        if (threadIdx.x == 64) GVQA_F16_TRACE(it, 3);
       }
     }
     if (overflow != nullptr && !(amax <= 65000.0f)) atomicOr(overflow, 1);   // also catches NaN / inf inputs
@@ -341,6 +357,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
       const int z = t.z, m0 = t.m0, n0 = t.n0, N = g.N[t.p], kblocks = t.kblocks;
       const CUtensorMap* mc = GVQA_MAP(map_c, t.p);
       mbar_wait(acc_full, tile_it & 1);
+      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_F16_TRACE(1024 + tile_it, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int col0 = n0 + chalf * 64;
       float acc[64];
@@ -364,6 +381,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive_leader<PAIR>(acc_empty);                 // TMEM is free: the next tile's MMAs may start
+      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_F16_TRACE(1024 + tile_it, 3);
       if (live) {
         const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
 #pragma unroll
@@ -388,6 +406,7 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
+      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_F16_TRACE(1024 + tile_it, 4);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -484,6 +503,7 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* pr
   }
   g.count = live;
   g.dbg = flags & 15;
+  g.trace = gemm_debug_trace();
   auto kernel = pair == 2 ? (conv_halves == 2 ? proj_gemm_3xf16_kernel<2, 2> : proj_gemm_3xf16_kernel<1, 2>)
                           : (conv_halves == 2 ? proj_gemm_3xf16_kernel<2, 1> : proj_gemm_3xf16_kernel<1, 1>);
   static bool attr_done[2][2] = {{false, false}, {false, false}};

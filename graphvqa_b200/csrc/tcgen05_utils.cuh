@@ -7,7 +7,8 @@
 
 namespace gvqa {
 
-int gemm_debug_flags();   // proj_gemm.cu: value of gvqa_debug_set_gemm_flags (0 in production)
+int gemm_debug_flags();          // proj_gemm.cu: value of gvqa_debug_set_gemm_flags (0 in production)
+long long* gemm_debug_trace();   // proj_gemm.cu: buffer of gvqa_debug_set_gemm_trace (null in production)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
