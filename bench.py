@@ -278,7 +278,7 @@ def run_engine(args, rank, local_rank, world):
         # position already reads ~2.7 us on this hardware (profiles/microbench/event_overhead.py).  Second
         # view: replay the step graphs with and without the hop launches (the GEMMs' time does not depend on
         # the data) and attribute the difference to the hops, launch gaps as they really are in the graph.
-        hop_in_graph_us = None
+        hop_in_graph_us, hop_in_graph_spread = None, None
         if graphs is not None:
             model.skip_hop_launch = True
             for r in range(R):
@@ -301,9 +301,10 @@ def run_engine(args, rank, local_rank, world):
                 return a.elapsed_time(z) / args.steps
             for gs in (graphs, graphs_nohop):
                 timed(gs)
-            full = min(timed(graphs) for _ in range(3))
-            nohop = min(timed(graphs_nohop) for _ in range(3))
-            hop_in_graph_us = 1e3 * (full - nohop) / hops
+            # interleaved rounds (both graphs see the same clock / power state), median of the per-round differences
+            diffs = sorted(timed(graphs) - timed(graphs_nohop) for _ in range(7))
+            hop_in_graph_us = 1e3 * diffs[len(diffs) // 2] / hops
+            hop_in_graph_spread = [1e3 * diffs[0] / hops, 1e3 * diffs[-1] / hops]
             del graphs_nohop
 
         # ---------------- third view: the event pairs as nodes of the replayed graph ------------------
@@ -382,10 +383,12 @@ def run_engine(args, rank, local_rank, world):
                      "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo, "avg_launch_us": primary_us, "method": primary_method,
                      "bracketed_us": hop_us, "bracketed_frac": achieved / peak, "launches_bracketed": len(hop_ms),
-                     "in_graph_us": hop_in_graph_us, "in_graph_bracketed_us": hop_graph_bracket_us,
-                     "note": "in_graph_differential: CUDA events around K replays of the step graph minus K replays of the "
-                             "same graph captured without the 5 fused-hop launches, per hop (the launch as it runs in "
-                             "the timed region).  bracketed_*: eager launches with an event pair around every hop "
+                     "in_graph_us": hop_in_graph_us, "in_graph_us_min_max": hop_in_graph_spread,
+                     "in_graph_bracketed_us": hop_graph_bracket_us,
+                     "note": "in_graph_differential: median over 7 interleaved rounds of (CUDA events around K replays of "
+                             "the step graph minus K replays of the same graph captured without the 5 fused-hop "
+                             "launches), per hop (the launch as it runs in the timed region); in_graph_us_min_max = "
+                             "smallest and largest round.  bracketed_*: eager launches with an event pair around every hop "
                              "launch of K steps; an event pair around an empty stream position already reads ~2.7 us "
                              "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"},
     }
