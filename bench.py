@@ -301,8 +301,8 @@ def run_engine(args, rank, local_rank, world):
                 return a.elapsed_time(z) / args.steps
             for gs in (graphs, graphs_nohop):
                 timed(gs)
-            # interleaved rounds (both graphs see the same clock / power state), median of the per-round differences
-            diffs = sorted(timed(graphs) - timed(graphs_nohop) for _ in range(7))
+            # 15 interleaved rounds (both graphs see the same clock / power state), median of the per-round differences
+            diffs = sorted(timed(graphs) - timed(graphs_nohop) for _ in range(15))
             hop_in_graph_us = 1e3 * diffs[len(diffs) // 2] / hops
             hop_in_graph_spread = [1e3 * diffs[0] / hops, 1e3 * diffs[-1] / hops]
             del graphs_nohop
@@ -385,7 +385,7 @@ def run_engine(args, rank, local_rank, world):
                      "bracketed_us": hop_us, "bracketed_frac": achieved / peak, "launches_bracketed": len(hop_ms),
                      "in_graph_us": hop_in_graph_us, "in_graph_us_min_max": hop_in_graph_spread,
                      "in_graph_bracketed_us": hop_graph_bracket_us,
-                     "note": "in_graph_differential: median over 7 interleaved rounds of (CUDA events around K replays of "
+                     "note": "in_graph_differential: median over 15 interleaved rounds of (CUDA events around K replays of "
                              "the step graph minus K replays of the same graph captured without the 5 fused-hop "
                              "launches), per hop (the launch as it runs in the timed region); in_graph_us_min_max = "
                              "smallest and largest round.  bracketed_*: eager launches with an event pair around every hop "
