@@ -73,3 +73,53 @@ def test_product_fails_loudly_on_cpu_tensors():
     m.train()
     with pytest.raises(NotImplementedError):
         m(torch.randn(2, 8), ei, torch.randn(2, 8), torch.randn(2, 1, 4), torch.zeros(2, dtype=torch.long))
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/gvqa_b200.h compiles as C (gcc, no CUDA headers) and the two argument structs have the size and
+    field offsets the ctypes mirrors assume."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields = {"gvqa_gat_hop_args": [n for n, _ in _cabi.GatHopArgs._fields_],
+              "gvqa_gemm_problem": [n for n, _ in _cabi.GemmProblem._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "gvqa_b200.h"', 'int main(void) {']
+    for struct, names in fields.items():
+        src.append('  printf("%s %%zu", sizeof(struct %s));' % (struct, struct))
+        for n in names:
+            src.append('  printf(" %%zu", offsetof(struct %s, %s));' % (struct, n))
+        src.append('  printf("\\n");')
+    src += ['  return 0;', '}']
+    c_file = tmp_path / "layout.c"
+    c_file.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line, (struct, cls) in zip(out, (("gvqa_gat_hop_args", _cabi.GatHopArgs), ("gvqa_gemm_problem", _cabi.GemmProblem))):
+        got = line.split()
+        assert got[0] == struct
+        want = [ctypes.sizeof(cls)] + [getattr(cls, n).offset for n, _ in cls._fields_]
+        assert [int(v) for v in got[1:]] == want, struct
+
+
+def test_grouped_gemm_argument_errors_are_reported_before_any_launch():
+    lib = _cabi.lib()
+    q = (_cabi.GemmProblem * 4)()
+    assert lib.gvqa_proj_gemm_3xf16_grouped(None, 1, None, None) == -2
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 0, None, None) == -2
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 4, None, None) == -2
+    q[0].m, q[0].n, q[0].k, q[0].batch, q[0].lda, q[0].ldb, q[0].ldc = 128, 128, 64, 1, 64, 64, 128
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 1, None, None) == -1          # NULL operands
+    q[0].a = q[0].b_hi = q[0].b_lo = q[0].c = 256
+    q[0].k, q[0].lda, q[0].ldb = 62, 62, 62                                  # k not a multiple of 4
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 1, None, None) == -3
+    q[0].k, q[0].lda, q[0].ldb = 64, 64, 64
+    q[0].a = 260                                                             # not 16-byte aligned
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 1, None, None) == -4
+    q[0].a, q[0].ldc = 256, 64                                               # ldc < n
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 1, None, None) == -2
+    q[0].ldc, q[0].m = 128, 0                                                # nothing to do
+    assert lib.gvqa_proj_gemm_3xf16_grouped(q, 1, None, None) == 0
