@@ -8,7 +8,7 @@ a = torch.randn(7680, 512, generator=g).to(DEV); b = (torch.randn(2064, 512, gen
 hi, lo = _cabi.split_f16(b); out = torch.empty(7680, 2064, device=DEV)
 for _ in range(3): _cabi.proj_gemm_3xf16(a, hi, lo, out=out)
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-_cabi.lib().gvqa_debug_set_gemm_flags(flags & ~64)
+_cabi.lib().gvqa_debug_set_gemm_flags(flags)
 tr = torch.zeros(1100 * 8, dtype=torch.int64, device=DEV)
 _cabi.lib().gvqa_debug_set_gemm_trace(tr.data_ptr())
 _cabi.proj_gemm_3xf16(a, hi, lo, out=out); torch.cuda.synchronize()

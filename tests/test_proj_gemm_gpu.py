@@ -184,3 +184,24 @@ def test_proj_gemm_3xf16_grouped_rejects_bad_counts_and_skips_empty():
     outs = _cabi.proj_gemm_3xf16_grouped([(empty, hi, lo, None), (a, hi, lo, None)], None)
     assert outs[0].shape == (0, 32)
     assert torch.equal(outs[1], _cabi.proj_gemm_3xf16(a, hi, lo))
+
+
+@pytest.mark.parametrize("m,n,k", [(7680, 2064, 512), (1000, 2048, 512), (59, 1200, 300), (300, 32, 64)])
+def test_proj_gemm_3xf16_double_buffered_accumulator_variant(m, n, k):
+    """Opt-in variant (GVQA_GEMM_DB=1 / debug flag 64): the two hi*hi accumulators hold consecutive tiles instead of
+    the two K-halves of one tile.  Same accuracy bar as the default at K <= 512."""
+    g = torch.Generator().manual_seed(m + n + k + 7)
+    a = torch.randn(m, k, generator=g) * 3.0
+    b = torch.randn(n, k, generator=g) * 0.05
+    hi, lo = _cabi.split_f16(b.to(DEV))
+    want = a.double() @ b.double().t()
+    err32 = ((a @ b.t()).double() - want).abs().max()
+    scale = float(want.abs().max())
+    base = _cabi.proj_gemm_3xf16(a.to(DEV), hi, lo).cpu()
+    try:
+        _cabi.lib().gvqa_debug_set_gemm_flags(64)
+        out = _cabi.proj_gemm_3xf16(a.to(DEV), hi, lo).cpu()
+    finally:
+        _cabi.lib().gvqa_debug_set_gemm_flags(0)
+    assert (out.double() - want).abs().max() <= max(4 * float(err32), 2e-6 * scale)
+    assert (out - base).abs().max() <= 4e-6 * scale
