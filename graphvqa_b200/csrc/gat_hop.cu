@@ -54,6 +54,7 @@ struct HopParams {
   float slope;
   int32_t epilogue;
   int32_t early;   // GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR: topology / a_edge / a_graph may be read before pdl_wait()
+  int32_t prefetch;   // GVQA_HOP_PREFETCH (experiments): 1 = the CTA's h_prev rows are pulled into L2 during the index prologue
 };
 
 // Softmax weights of the in-edges [e0,e1) of node `i` for all H heads, computed by one warp.
@@ -232,6 +233,14 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
   const int C4 = p.C >> 2;
 #define GVQA_HOP_TRACE(col) do { if (p.trace && tid == 0) p.trace[(size_t)blockIdx.x * 8 + (col)] = gtime_ns(); } while (0)
   GVQA_HOP_TRACE(0);
+  if (p.prefetch && p.h_prev) {
+    // the skip rows of the CTA's own nodes are contiguous, older than the predecessor kernel and known without any
+    // index: request them while the three dependent index round trips keep the memory system idle
+    const char* base = reinterpret_cast<const char*>(p.h_prev + (int64_t)i0 * p.C);
+    const int bytes = nn * p.C * 4;
+    for (int off = tid * 128; off < bytes; off += kBlkThreads * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+  }
 
   // ---- round trips 1+2 touch only the per-batch topology and the pre-pass outputs, none of which the
   // projection GEMM right before this kernel writes: under programmatic dependent launch they run while that
@@ -685,6 +694,11 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   p.slope = a->negative_slope; p.epilogue = a->epilogue;
   // the early-start layout only pays when the launch carries the PDL attribute (off by default, common.cuh)
   p.early = ((a->flags & GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR) && (pdl_mask() & 2)) ? 1 : 0;
+  static const int env_prefetch = [] {
+    const char* e = getenv("GVQA_HOP_PREFETCH");
+    return e ? atoi(e) : 0;
+  }();
+  p.prefetch = env_prefetch;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   if (a->variant == 2) {
