@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK = 0, 1, 2, 3
@@ -98,12 +98,13 @@ def lib():
                 "graphvqa_b200: CUDA library %s not found. Build it with "
                 "`python -m graphvqa_b200.build` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
+        handle.gvqa_abi_version.restype, handle.gvqa_abi_version.argtypes = ctypes.c_int, []
+        if handle.gvqa_abi_version() != ABI_VERSION:      # checked first: a stale library may lack newer symbols
+            raise RuntimeError("graphvqa_b200: ABI version mismatch (library %d, binding %d); rebuild with "
+                               "`python -m graphvqa_b200.build`" % (handle.gvqa_abi_version(), ABI_VERSION))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.gvqa_abi_version() != ABI_VERSION:
-            raise RuntimeError("graphvqa_b200: ABI version mismatch (library %d, binding %d); rebuild"
-                               % (handle.gvqa_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 

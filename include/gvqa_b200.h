@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GVQA_ABI_VERSION 2
+#define GVQA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define GVQA_API __attribute__((visibility("default")))
