@@ -43,3 +43,18 @@ def test_engine_arm_fails_loudly_without_cuda():
     r = _run("--steps", "1", "--warmup", "0", "--skip-cpu")
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under graphvqa_b200/ may import, load or mention it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "graphvqa_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|oracle\.", text, re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
