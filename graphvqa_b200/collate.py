@@ -22,10 +22,12 @@ The attribute order inside a node follows Python's ``set`` iteration order in th
 not deterministic across interpreter runs; here attributes keep their first-occurrence order.  The encoder
 sums the 12 slot embeddings (:583-585), so the order does not change any result.
 
-Parity status: the reference's loader cannot run here (torchtext < 0.9, spaCy model and GloVe download are
-absent and there is no network), so this restatement is checked against the structural facts recorded in
-SURVEY.md section 4 (node / edge counts of debug_sceneGraphs.json, vocabulary size 2577, ``<self>`` id) and
-against hand-built graphs (tests/test_collate.py), not against reference outputs.
+Parity status: pinned against the reference's own loader.  The unmodified ``gqa_dataset_entry.py`` runs in the
+build container on minimal ``torchtext`` / ``torch_geometric`` stand-ins (the absent third-party wheels; their
+vocabulary-ordering and batching rules are restated from the published behaviour), and its
+``GQA_gt_sg_feature_lookup('debug')`` output for the four graphs of debug_sceneGraphs.json -- vocabulary (all
+2577 tokens, same order), per-graph tensors, the empty-graph dummy and the collated batch -- is committed as
+``tests/golden/collate_debug.pt``; tests/test_collate.py compares bit for bit (attribute slots as sorted sets).
 """
 import collections
 import json

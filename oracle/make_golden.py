@@ -1,6 +1,7 @@
 """Generate tests/golden/*.pt by running the UNMODIFIED reference modules (over oracle/pyg_shim).
 
-TEST INFRASTRUCTURE, build-container only:   python -m oracle.make_golden
+TEST INFRASTRUCTURE, build-container only:   python -m oracle.make_golden            (all model fixtures)
+                                             python -m oracle.make_golden collate    (collate_debug.pt only)
 
 Each fixture holds the inputs, the module ``state_dict`` and the outputs the reference's own code
 produced on CPU (fp32).  Topologies come from the reference's ``debug_sceneGraphs.json`` (4 graphs:
@@ -86,7 +87,48 @@ def _state_hash(sd):
     return h.hexdigest()
 
 
+def canonical_tokens(x):
+    """Node token rows with the attribute slots (1..11) sorted: the reference fills them in ``set`` iteration
+    order (gqa_dataset_entry.py:287), which depends on the interpreter's string hash seed; the encoder sums the
+    slot embeddings, so the order carries no information."""
+    return torch.cat([x[:, :1], x[:, 1:].sort(dim=1).values], dim=1)
+
+
+def make_collate_fixture():
+    """tests/golden/collate_debug.pt: what the reference's OWN loader (``GQA_gt_sg_feature_lookup('debug')`` of the
+    unmodified gqa_dataset_entry.py, on oracle/torchtext_shim + oracle/pyg_shim) produces for the four graphs of
+    debug_sceneGraphs.json: its scene-graph vocabulary, every graph's tensors and the collated ``Batch``."""
+    os.makedirs(OUT, exist_ok=True)
+    _, lookup = rr.load_scene_graph_lookup("debug")      # puts the shims on sys.path
+    import torch_geometric
+    vocab = lookup.SG_ENCODING_TEXT.vocab
+    graphs, data = [], []
+    for key, sg in lookup.sg_json_data.items():
+        d = lookup.convert_one_gqa_scene_graph(sg)
+        data.append(d)
+        graphs.append(dict(key=key, x=canonical_tokens(d.x), edge_index=d.edge_index, edge_attr=d.edge_attr,
+                           added_sym_edge=d.added_sym_edge))
+    empty = lookup.convert_one_gqa_scene_graph({"objects": {}})
+    b = torch_geometric.data.Batch.from_data_list(data)
+    fx = dict(meta=dict(generator="oracle/make_golden.py collate", reference=rr.REFERENCE_ROOT, torch=torch.__version__),
+              scene_graphs=lookup.sg_json_data, itos=list(vocab.itos),
+              itos_sha256=hashlib.sha256("\n".join(vocab.itos).encode()).hexdigest(),
+              self_id=int(vocab.stoi["<self>"]), pad_id=int(vocab.stoi[lookup.SG_ENCODING_TEXT.pad_token]),
+              graphs=graphs,
+              empty=dict(x=canonical_tokens(empty.x), edge_index=empty.edge_index, edge_attr=empty.edge_attr,
+                         added_sym_edge=empty.added_sym_edge),
+              batch=dict(x=canonical_tokens(b.x), edge_index=b.edge_index, edge_attr=b.edge_attr, batch=b.batch,
+                         added_sym_edge=b.added_sym_edge))
+    path = os.path.join(OUT, "collate_debug.pt")
+    torch.save(fx, path)
+    print(os.path.basename(path), os.path.getsize(path))
+
+
 def main():
+    import sys
+    if sys.argv[1:] == ["collate"]:
+        make_collate_fixture()
+        return
     os.makedirs(OUT, exist_ok=True)
     ei, batch = debug_topology()
     n, e, b = batch.numel(), ei.size(1), int(batch.max()) + 1

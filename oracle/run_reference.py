@@ -13,6 +13,7 @@ What is stubbed, and why:
 Nothing from the reference is copied: its files are executed where they lie.
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -66,6 +67,61 @@ def _dataset_stub():
 
 
 _loaded = {}
+_TT_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "torchtext_shim")
+_HARD_CODED_ROOT = "/home/weixin/neuralPoolTest/GraphVQA"     # Constants.py:13 + 'GraphVQA' (gqa_dataset_entry.py:28-30)
+
+
+class _redirect_reference_paths:
+    """While active, ``open()`` of a path under the reference's hard-coded checkout location reads the same file
+    under REFERENCE_ROOT instead (Constants.py and gqa_dataset_entry.py open their meta_info files at import)."""
+
+    def __enter__(self):
+        import builtins
+        self._builtins, self._open = builtins, builtins.open
+
+        def redirected(file, *args, **kwargs):
+            try:
+                path = os.fspath(file)
+            except TypeError:
+                return self._open(file, *args, **kwargs)
+            if isinstance(path, str) and path.startswith(_HARD_CODED_ROOT):
+                path = REFERENCE_ROOT + path[len(_HARD_CODED_ROOT):]
+            return self._open(path, *args, **kwargs)
+
+        builtins.open = redirected
+        return self
+
+    def __exit__(self, *exc):
+        self._builtins.open = self._open
+        return False
+
+
+def load_scene_graph_lookup(split="debug"):
+    """The reference's own ``GQA_gt_sg_feature_lookup(split)`` (gqa_dataset_entry.py:52-372), built from the
+    UNMODIFIED file on top of oracle/torchtext_shim + oracle/pyg_shim: its scene-graph vocabulary and its
+    ``convert_one_gqa_scene_graph``.  matplotlib (imported by Constants.py for plotting helpers) is stubbed."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    if "scene_graph_lookup" in _loaded:
+        return _loaded["scene_graph_lookup"]
+    for p in (_SHIM, _TT_SHIM):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.append(REFERENCE_ROOT)
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            sys.modules[name] = types.ModuleType(name)
+    with _redirect_reference_paths():
+        spec = importlib.util.spec_from_file_location("gqa_dataset_entry_reference",
+                                                      os.path.join(REFERENCE_ROOT, "gqa_dataset_entry.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)              # imports the reference's Constants.py under the redirect, too
+        lookup = mod.GQA_gt_sg_feature_lookup(split)
+    _loaded["scene_graph_lookup"] = (mod, lookup)
+    return mod, lookup
 
 
 def load(name):
