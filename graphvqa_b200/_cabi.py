@@ -12,10 +12,10 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
-EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU = 0, 1, 2
-VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK = 0, 1, 2, 3
+EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU, EPI_GRAPH_LN = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK, VARIANT_WS = 0, 1, 2, 3, 4
 HOP_INPUTS_OLDER_THAN_PREDECESSOR = 1
 
 _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
@@ -33,7 +33,8 @@ class GatHopArgs(ctypes.Structure):
         ("num_nodes", _c_i64), ("num_edges", _c_i64), ("num_graphs", _c_i64),
         ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
         ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
-        ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64), ("flags", _c_i32),
+        ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64), ("flags", _c_i32), ("ln_eps", _c_f32),
+        ("ln_weight", _c_vp), ("ln_bias", _c_vp), ("sched", _c_vp),
     ]
 
 
@@ -80,6 +81,13 @@ SIGNATURES = {
     "gvqa_gcn_aggregate_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                               _c_i32, _c_vp]),
     "gvqa_gather_add_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_gather_add_relu_i32_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_affine_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_graph_scale_rows_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp]),
+    "gvqa_attention_pool_gate_f32": (ctypes.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
+                                                    _c_i32, _c_vp]),
+    "gvqa_build_csr_host": (ctypes.c_int, [_c_vp, _c_i32, _c_i64, _c_vp, _c_i32, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp,
+                                           _c_vp, _c_vp, _c_vp]),
     "gvqa_segment_mean_rows_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_attention_pool_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp]),
     "gvqa_lcgn_hop_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp,
@@ -188,8 +196,12 @@ def skinny_matmul(x, v, out=None):
 def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=None, graph_bias=None,
             a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
-            max_in_edges_per_graph=0, variant=VARIANT_AUTO, inputs_older_than_predecessor=False):
-    require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out)
+            max_in_edges_per_graph=0, variant=VARIANT_AUTO, inputs_older_than_predecessor=False,
+            ln_weight=None, ln_bias=None, ln_eps=1e-5, sched=None):
+    require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out,
+                 ln_weight, ln_bias, sched)
+    if variant == VARIANT_WS and sched is None:
+        sched = hop_sched(h_out.device)
     require_f32c(h_out=h_out, h_prev=h_prev, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift, alpha_out=alpha_out)
     for name, t in (("graph_bias", graph_bias), ("a_graph", a_graph)):    # [B, .] row-strided views are fine
         if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
@@ -213,9 +225,24 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.ld_graph_bias = graph_bias.stride(0) if graph_bias is not None and graph_bias.size(0) > 1 else 0
     a.ld_a_graph = a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else 0
     a.flags = HOP_INPUTS_OLDER_THAN_PREDECESSOR if inputs_older_than_predecessor else 0
+    a.ln_eps, a.ln_weight, a.ln_bias, a.sched = ln_eps, ptr(ln_weight), ptr(ln_bias), ptr(sched)
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
     return h_out
+
+
+_hop_sched = {}
+
+
+def hop_sched(device):
+    """Scheduler words of the warp-specialised hop kernel (variant 4): one zeroed int32[2] per device, shared by
+    all launches of a stream-ordered sequence (the kernel leaves it zero)."""
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _hop_sched.get(key)
+    if t is None:
+        t = _hop_sched[key] = torch.zeros(2, dtype=torch.int32, device=device)
+    return t
 
 
 def graph_layernorm(x, graph_ptr, num_graphs, weight, bias, eps, out=None, max_nodes_per_graph=0):
@@ -423,15 +450,84 @@ def l2_window(tensor, device, hit_ratio=1.0):
 
 
 def gather_add_relu(a, b, c, bias, edge_index, relu=True):
-    """out[k] = act(a[src_k] + b[dst_k] + c[k] + bias); edge_index int64 [2,E] (reference layout)."""
+    """out[k] = act(a[src_k] + b[dst_k] + c[k] + bias); edge_index [2,E] int64 (reference layout) or int32 (the
+    loader-side wire format)."""
     require_cuda(a, b, c, bias, edge_index)
     require_f32c(a=a, b=b, c=c, bias=bias)
+    if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("gather_add_relu: edge_index must be int64 or int32 [2, E]")
     e, f = edge_index.size(1), a.size(1)
     out = torch.empty(e, f, dtype=torch.float32, device=a.device)
+    fn = lib().gvqa_gather_add_relu_f32 if edge_index.dtype == torch.int64 else lib().gvqa_gather_add_relu_i32_f32
     with torch.cuda.device(a.device):
-        check(lib().gvqa_gather_add_relu_f32(ptr(a), ptr(b), ptr(c), ptr(bias), ptr(edge_index.contiguous()), ptr(out),
-                                             e, f, 1 if relu else 0, stream_handle(a.device)),
-              "gvqa_gather_add_relu_f32")
+        check(fn(ptr(a), ptr(b), ptr(c), ptr(bias), ptr(edge_index.contiguous()), ptr(out), e, f, 1 if relu else 0,
+                 stream_handle(a.device)), "gvqa_gather_add_relu_f32")
+    return out
+
+
+def affine_relu(x, scale, shift, relu=True, out=None):
+    """out = act(x * scale[c] + shift[c]) for x [N,C] float32 contiguous (BatchNorm1d eval folded + ReLU)."""
+    require_cuda(x, scale, shift)
+    require_f32c(x=x, scale=scale, shift=shift, out=out)
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_affine_relu_f32(ptr(x), ptr(scale), ptr(shift), ptr(out), x.size(0), x.size(1),
+                                         1 if relu else 0, stream_handle(x.device)), "gvqa_affine_relu_f32")
+    return out
+
+
+def graph_scale_rows(x, q, node_graph, out=None):
+    """out[n] = x[n] * q[node_graph[n]]  (x [N,C], q [B,C] float32 contiguous, node_graph int32 [N])."""
+    require_cuda(x, q, node_graph)
+    require_f32c(x=x, q=q, out=out)
+    if node_graph.dtype != torch.int32:
+        raise TypeError("graph_scale_rows: node_graph must be int32 (GraphCSR.node_graph)")
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_graph_scale_rows_f32(ptr(x), ptr(q), ptr(node_graph), ptr(out), x.size(0), x.size(1),
+                                              stream_handle(x.device)), "gvqa_graph_scale_rows_f32")
+    return out
+
+
+def attention_pool_gate(hid, w_gate, b_gate, x, graph_ptr, num_graphs):
+    """out[g] = sum_n softmax_g(<hid[n], w_gate> + b_gate)[n] * x[n]: gate Linear(C,1) + per-graph softmax + pooling
+    in one kernel.  Returns (out [B,C], gate [N])."""
+    require_cuda(hid, w_gate, b_gate, x, graph_ptr)
+    w_gate = w_gate.reshape(-1).contiguous().float()
+    require_f32c(hid=hid, x=x)
+    gate = torch.empty(max(x.size(0), 1), dtype=torch.float32, device=x.device)
+    out = torch.empty(num_graphs, x.size(1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().gvqa_attention_pool_gate_f32(ptr(hid), hid.size(1), ptr(w_gate), ptr(b_gate), ptr(gate), ptr(x),
+                                                 ptr(graph_ptr), ptr(out), num_graphs, x.size(1),
+                                                 stream_handle(x.device)), "gvqa_attention_pool_gate_f32")
+    return out, gate[:x.size(0)]
+
+
+def build_csr_host(edge_index, batch, num_graphs, pin=True):
+    """Loader-side CSR build on HOST tensors (int32 or int64 inputs): dict(rowptr, col_src, perm, graph_ptr,
+    node_graph, stats) of int32 CPU tensors (pinned when a CUDA runtime is present and ``pin``), identical to what
+    ``build_csr`` produces on the device.  Needs no GPU."""
+    for t in (edge_index, batch):
+        if t.is_cuda or t.dtype not in (torch.int32, torch.int64):
+            raise TypeError("build_csr_host: CPU int32 / int64 tensors expected")
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must be [2, E]")
+    edge_index, batch = edge_index.contiguous(), batch.contiguous()
+    n, e = batch.numel(), edge_index.size(1)
+    pin = bool(pin) and torch.cuda.is_available()
+
+    def buf(count):
+        t = torch.empty(count, dtype=torch.int32)
+        return t.pin_memory() if pin else t
+    out = dict(rowptr=buf(n + 1), col_src=buf(max(e, 1)), perm=buf(max(e, 1)), graph_ptr=buf(num_graphs + 1),
+               node_graph=buf(max(n, 1)), stats=buf(8))
+    check(lib().gvqa_build_csr_host(ptr(edge_index), edge_index.element_size(), e, ptr(batch), batch.element_size(), n,
+                                    num_graphs, ptr(out["rowptr"]), ptr(out["col_src"]), ptr(out["perm"]),
+                                    ptr(out["graph_ptr"]), ptr(out["node_graph"]), ptr(out["stats"])),
+          "gvqa_build_csr_host")
     return out
 
 

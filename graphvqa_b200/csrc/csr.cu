@@ -24,9 +24,14 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ edge_index, int64_t
     }
   }
   if (t < N) {
-    // graph boundaries from the non-decreasing batch vector (empty graphs get empty ranges)
-    const int64_t b = batch[t];
-    const int64_t prev = t > 0 ? batch[t - 1] : -1;
+    // graph boundaries from the non-decreasing batch vector (empty graphs get empty ranges).  Ids outside
+    // [0, B) or a decreasing step would make the hop kernels index graph_bias / a_graph out of bounds: they are
+    // clamped here and counted with the bad edges (stats[3]), which GraphCSR.read_stats() exposes.
+    int64_t b = batch[t];
+    int64_t prev = t > 0 ? batch[t - 1] : -1;
+    if (b < 0 || b >= B || b < prev) atomicAdd(&stats[3], 1);
+    b = b < 0 ? 0 : (b >= B ? (B > 0 ? B - 1 : 0) : b);
+    prev = prev < -1 ? -1 : (prev >= B ? B - 1 : prev);
     node_graph[t] = (int32_t)b;
     for (int64_t g = prev + 1; g <= b && g <= B; ++g) graph_ptr[g] = (int32_t)t;
     if (t == N - 1)

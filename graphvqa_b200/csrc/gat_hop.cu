@@ -14,6 +14,14 @@
 //    memory, then every warp streams its nodes' source rows with 32 independent 128-bit loads in
 //    flight per lane.  The whole grid is resident in ONE wave (no tail), so the kernel behaves
 //    like a streaming copy.  Default.
+//  4 gat_hop_ws_kernel     -- persistent, warp-specialised: one producer warp per CTA claims chunks of 8 destination
+//    nodes from a device counter and prepares them (index round trips + softmax) into a 3-slot shared-memory ring
+//    while 4 consumer warps stream the previous chunks; only the first chunk's index latency is exposed and fast
+//    SMs take more chunks than slow ones (the block kernel's per-CTA stream phase spreads 7.9-17.2 us for equal
+//    work, profiles/r01/hop_timeline_block_kernel.txt).
+//  5 gat_hop_graphln_kernel -- epilogue GVQA_EPI_GRAPH_LN: one CTA per graph keeps the graph's output rows in shared
+//    memory, so the per-graph LayerNorm of my_graph_layernorm.py:52-78 (two-pass variance) runs before the single
+//    HBM write.  Selected by the epilogue mode, not by `variant`.
 //  2 gat_hop_staged_kernel -- one CTA per (graph, channel-window): softmax once for all heads,
 //    then one stage per head (the window of every node row of the graph) streamed by the TMA
 //    engine (cp.async.bulk + mbarrier) through a 3-deep shared-memory ring, accumulators in
@@ -55,6 +63,10 @@ struct HopParams {
   int32_t epilogue;
   int32_t early;   // GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR: topology / a_edge / a_graph may be read before pdl_wait()
   int32_t prefetch;   // GVQA_HOP_PREFETCH (experiments): 1 = the CTA's h_prev rows are pulled into L2 during the index prologue
+  int32_t* sched;     // variant 4: {next chunk, finished CTAs}, zero before the first launch, self-resetting
+  const float* ln_weight;   // GVQA_EPI_GRAPH_LN: one float each (or NULL), my_graph_layernorm.py:40-41
+  const float* ln_bias;
+  float ln_eps;
 };
 
 // Softmax weights of the in-edges [e0,e1) of node `i` for all H heads, computed by one warp.
@@ -107,9 +119,20 @@ struct WarpSoftmax {
 // Epilogue for one float4 column (absolute float4 index c4) of output row i: head mean,
 // + per-graph instruction term (rows with in-edges only), +bias, +skip, BatchNorm(eval) affine,
 // ReLU; 128-bit streaming store.
+__device__ __forceinline__ float4 epilogue_value4(const HopParams& p, int c4, float4 o, float inv_heads, bool add_gb,
+                                                  const float4& gb, bool have_skip, const float4& skip,
+                                                  int epilogue);
+
 __device__ __forceinline__ void epilogue_store4(const HopParams& p, int i, int c4, float4 o, float inv_heads,
                                                 bool add_gb, const float4& gb, bool have_skip,
                                                 const float4& skip) {
+  stg_stream(p.h_out + (int64_t)i * p.C + 4 * c4,
+             epilogue_value4(p, c4, o, inv_heads, add_gb, gb, have_skip, skip, p.epilogue));
+}
+
+__device__ __forceinline__ float4 epilogue_value4(const HopParams& p, int c4, float4 o, float inv_heads, bool add_gb,
+                                                  const float4& gb, bool have_skip, const float4& skip,
+                                                  int epilogue) {
   o.x *= inv_heads; o.y *= inv_heads; o.z *= inv_heads; o.w *= inv_heads;
   if (add_gb) { o.x += gb.x; o.y += gb.y; o.z += gb.z; o.w += gb.w; }
   if (p.bias) {
@@ -117,16 +140,16 @@ __device__ __forceinline__ void epilogue_store4(const HopParams& p, int i, int c
     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
   }
   if (have_skip) { o.x += skip.x; o.y += skip.y; o.z += skip.z; o.w += skip.w; }
-  if (p.epilogue != GVQA_EPI_NONE) {
+  if (epilogue == GVQA_EPI_AFFINE || epilogue == GVQA_EPI_AFFINE_RELU) {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ep_scale) + c4);
     const float4 sh = __ldg(reinterpret_cast<const float4*>(p.ep_shift) + c4);
     o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y);
     o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
-    if (p.epilogue == GVQA_EPI_AFFINE_RELU) {
+    if (epilogue == GVQA_EPI_AFFINE_RELU) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
   }
-  stg_stream(p.h_out + (int64_t)i * p.C + 4 * c4, o);
+  return o;     // GVQA_EPI_GRAPH_LN: the per-graph normalisation follows in gat_hop_graphln_kernel
 }
 
 // One warp computes output row i for the float4 column window [c4_lo, c4_lo + c4_n), gathering
@@ -371,6 +394,330 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_block_
   if (p.trace && lane == 0 && wid < 4) p.trace[(size_t)blockIdx.x * 8 + 4 + wid] = gtime_ns();   // per-warp finish
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Shared streaming step of kernels 4 and 5: output row i from staged (src, alpha) lists in shared
+// memory.  2 edges x H x J independent 128-bit loads in flight per lane; the epilogue value goes to
+// `sink(c4, value)`.
+// ------------------------------------------------------------------------------------------
+template <int J, int H, typename Sink>
+__device__ __forceinline__ void stream_node(const HopParams& p, int i, int lane, int C4, const int32_t* src_s,
+                                            const float* alpha_s, int r0, int r1, int gid, int epilogue, Sink&& sink) {
+  float4 acc[J], skip[J], gb[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    skip[j] = acc[j];
+    gb[j] = acc[j];
+    const int c4 = lane + 32 * j;
+    if (c4 < C4) {
+      if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * c4);
+      if (p.graph_bias && r1 > r0) gb[j] = ldg_cached(p.graph_bias + (int64_t)gid * p.ldgb + 4 * c4);
+    }
+  }
+#pragma unroll 2
+  for (int k = r0; k < r1; ++k) {
+    const float* row = p.x_l + (int64_t)src_s[k] * p.ldx;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float a = alpha_s[k * H + h];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < C4) fma4(acc[j], a, ldg_cached(row + h * p.C + 4 * c4));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < C4)
+      sink(c4, epilogue_value4(p, c4, acc[j], 1.0f / H, p.graph_bias != nullptr && r1 > r0, gb[j], p.h_prev != nullptr,
+                               skip[j], epilogue));
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 4: persistent warp-specialised hop.  Warp 0 = producer (claims chunks, index round trips,
+// softmax into a ring slot), warps 1..4 = consumers (weighted gather + epilogue).
+// ------------------------------------------------------------------------------------------
+constexpr int kWsConsumers = 4;
+constexpr int kWsThreads = 32 * (kWsConsumers + 1);
+constexpr int kWsSlots = 3;
+constexpr int kWsEdgeCap = 128;   // in-edges of one chunk staged in a slot; larger chunks take the per-warp path
+
+template <int H>
+struct WsGeom {
+  static constexpr int kChunk = H >= 8 ? 4 : 8;   // kChunk * H <= 32: one producer lane per (node, head)
+};
+
+template <int H>
+struct __align__(16) WsSlot {
+  float alpha[kWsEdgeCap * H];
+  int32_t src[kWsEdgeCap];
+  int32_t rp[WsGeom<H>::kChunk + 1];
+  int32_t gid[WsGeom<H>::kChunk];
+  int32_t i0, nn, overflow, pad;
+};
+
+template <int J, int H>
+__global__ void __launch_bounds__(kWsThreads, 3) gat_hop_ws_kernel(const HopParams p, const int nchunks) {
+  constexpr int kChunk = WsGeom<H>::kChunk;
+  __shared__ WsSlot<H> slots[kWsSlots];
+  __shared__ __align__(8) uint64_t full_bar[kWsSlots], empty_bar[kWsSlots];
+  __shared__ float gather_alpha[kWsConsumers][kEdgeChunk * H];   // scratch of the oversize-chunk path
+  __shared__ int32_t gather_src[kWsConsumers][kEdgeChunk];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int C4 = p.C >> 2;
+  if (p.trace && tid == 0) {
+    p.trace[(size_t)blockIdx.x * 8 + 0] = gtime_ns();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[(size_t)blockIdx.x * 8 + 3] = smid;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kWsSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kWsConsumers);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (wid == 0) {
+    // ---------------- producer ----------------
+    const int node = lane / H, head = lane - node * H;
+#pragma unroll 1
+    for (int it = 0;; ++it) {
+      const int s = it % kWsSlots;
+      int c = 0;
+      if (lane == 0) c = atomicAdd(p.sched, 1);
+      c = __shfl_sync(kFull, c, 0);
+      mbar_wait(&empty_bar[s], (uint32_t)(((it / kWsSlots) & 1) ^ 1));     // consumers have left the slot
+      WsSlot<H>& sl = slots[s];
+      if (c >= nchunks) {
+        if (lane == 0) {
+          sl.nn = 0;
+          // the CTA whose final claim is the last one resets the scheduler words for the next launch
+          if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+        if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 8 + 2] = (unsigned long long)it;
+        break;
+      }
+      const int i0 = c * kChunk;
+      const int nn = min(kChunk, p.N - i0);
+      // round trip 1: row pointers, graph ids, target-side logit terms
+      const int rpv = lane <= nn ? p.rowptr[i0 + lane] : 0;
+      float tg = 0.f;
+      int g = 0;
+      const bool owner = lane < nn * H;
+      if (owner) {
+        g = p.node_graph[i0 + node];
+        if (p.a_graph) tg = p.a_graph[(int64_t)g * p.ldag + head];
+        tg += p.a_node[(int64_t)(i0 + node) * p.lda + H + head];
+      }
+      const int eA = __shfl_sync(kFull, rpv, 0);
+      const int eC = __shfl_sync(kFull, rpv, nn) - eA;
+      if (lane <= nn) sl.rp[lane] = rpv - eA;
+      if (owner && head == 0) sl.gid[node] = g;
+      const bool over = eC > kWsEdgeCap;
+      if (!over) {
+        // round trips 2 + 3: sources / edge ids, then the edge and source logit terms
+        for (int k = lane; k < eC; k += 32) {
+          const int src = p.col_src[eA + k];
+          const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+          sl.src[k] = src;
+          const float* an = p.a_node + (int64_t)src * p.lda;
+#pragma unroll
+          for (int h = 0; h < H; ++h) sl.alpha[k * H + h] = p.a_edge[e * p.lde + h] + an[h];
+        }
+      }
+      __syncwarp();
+      if (!over && owner) {
+        const int r0 = sl.rp[node], r1 = sl.rp[node + 1];
+        float mx = -INFINITY;
+#pragma unroll 4
+        for (int k = r0; k < r1; ++k) mx = fmaxf(mx, leaky_relu(sl.alpha[k * H + head] + tg, p.slope));
+        float sum = 0.f;
+#pragma unroll 4
+        for (int k = r0; k < r1; ++k) sum += expf(leaky_relu(sl.alpha[k * H + head] + tg, p.slope) - mx);
+        const float inv = 1.0f / (sum + 1e-16f);
+#pragma unroll 4
+        for (int k = r0; k < r1; ++k) {
+          const float a = expf(leaky_relu(sl.alpha[k * H + head] + tg, p.slope) - mx) * inv;
+          sl.alpha[k * H + head] = a;
+          if (p.alpha_out) {
+            const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+            p.alpha_out[e * H + head] = a;
+          }
+        }
+      }
+      if (lane == 0) {
+        sl.i0 = i0;
+        sl.nn = nn;
+        sl.overflow = over ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (p.trace && lane == 0 && it == 0) p.trace[(size_t)blockIdx.x * 8 + 1] = gtime_ns();
+    }
+  } else {
+    // ---------------- consumers ----------------
+    const int cw = wid - 1;
+#pragma unroll 1
+    for (int it = 0;; ++it) {
+      const int s = it % kWsSlots;
+      mbar_wait(&full_bar[s], (uint32_t)((it / kWsSlots) & 1));
+      const WsSlot<H>& sl = slots[s];
+      const int nn = sl.nn;
+      if (nn == 0) break;
+      const int i0 = sl.i0;
+      if (sl.overflow) {
+        for (int node = cw; node < nn; node += kWsConsumers)
+          gather_node<J, H>(p, i0 + node, lane, 0, C4, gather_alpha[cw], gather_src[cw], true);
+      } else {
+#pragma unroll 1
+        for (int node = cw; node < nn; node += kWsConsumers) {
+          const int i = i0 + node;
+          stream_node<J, H>(p, i, lane, C4, sl.src, sl.alpha, sl.rp[node], sl.rp[node + 1], sl.gid[node], p.epilogue,
+                            [&](int c4, const float4& v) { stg_stream(p.h_out + (int64_t)i * p.C + 4 * c4, v); });
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    if (p.trace && lane == 0) p.trace[(size_t)blockIdx.x * 8 + 4 + cw] = gtime_ns();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel 5: graph-LayerNorm epilogue (my_graph_layernorm.py:52-78 applied to conv + skip).  One CTA per
+// graph; the graph's pre-normalisation rows live in shared memory when they fit (n <= n_cap rows), else
+// they make one trip through h_out (written, then re-read by the same CTA).  Two-pass variance like the
+// reference: mean first, then the centred second moment; eps is added to the standard deviation.
+// ------------------------------------------------------------------------------------------
+constexpr int kLnHopThreads = 256;
+constexpr int kLnHopEdgeCap = 512;     // staged in-edges per graph; larger graphs take the per-warp path
+
+__device__ __forceinline__ float block_sum_256(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float t = lane < kLnHopThreads / 32 ? scratch[lane] : 0.f;
+  return warp_sum(t);
+}
+
+template <int J, int H>
+__global__ void __launch_bounds__(kLnHopThreads) gat_hop_graphln_kernel(const HopParams p, const int n_cap) {
+  extern __shared__ __align__(16) float rows_s[];                 // [n_cap][C]
+  __shared__ __align__(16) float alpha_s[kLnHopEdgeCap * H];
+  __shared__ int32_t src_s[kLnHopEdgeCap];
+  __shared__ float scratch[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int kWarps = kLnHopThreads / 32;
+  const int g = blockIdx.x;
+  const int n0 = p.graph_ptr[g], n1 = p.graph_ptr[g + 1], n = n1 - n0;
+  if (n <= 0) return;
+  const int C = p.C, C4 = C >> 2;
+  const int eA = p.rowptr[n0], eC = p.rowptr[n1] - eA;
+  const bool rows_fit = n <= n_cap;
+  const bool edges_fit = eC <= kLnHopEdgeCap;
+  float* rows = rows_fit ? rows_s : p.h_out + (int64_t)n0 * C;
+
+  float local = 0.f;     // sum of this thread's output elements
+  if (edges_fit) {
+    for (int k = tid; k < eC; k += kLnHopThreads) {
+      const int src = p.col_src[eA + k];
+      const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+      src_s[k] = src;
+      const float* an = p.a_node + (int64_t)src * p.lda;
+#pragma unroll
+      for (int h = 0; h < H; ++h) alpha_s[k * H + h] = p.a_edge[e * p.lde + h] + an[h];
+    }
+    __syncthreads();
+    for (int t = tid; t < n * H; t += kLnHopThreads) {
+      const int node = t / H, h = t - node * H;
+      const int r0 = p.rowptr[n0 + node] - eA, r1 = p.rowptr[n0 + node + 1] - eA;
+      float tg = p.a_node[(int64_t)(n0 + node) * p.lda + H + h];
+      if (p.a_graph) tg = p.a_graph[(int64_t)g * p.ldag + h] + tg;
+      float mx = -INFINITY;
+      for (int k = r0; k < r1; ++k) mx = fmaxf(mx, leaky_relu(alpha_s[k * H + h] + tg, p.slope));
+      float sum = 0.f;
+      for (int k = r0; k < r1; ++k) sum += expf(leaky_relu(alpha_s[k * H + h] + tg, p.slope) - mx);
+      const float inv = 1.0f / (sum + 1e-16f);
+      for (int k = r0; k < r1; ++k) {
+        const float a = expf(leaky_relu(alpha_s[k * H + h] + tg, p.slope) - mx) * inv;
+        alpha_s[k * H + h] = a;
+        if (p.alpha_out) {
+          const int64_t e = p.perm ? p.perm[eA + k] : (eA + k);
+          p.alpha_out[e * H + h] = a;
+        }
+      }
+    }
+    __syncthreads();
+    for (int node = wid; node < n; node += kWarps) {
+      const int i = n0 + node;
+      const int r0 = p.rowptr[i] - eA, r1 = p.rowptr[i + 1] - eA;
+      float* dst = rows + (int64_t)node * C;
+      stream_node<J, H>(p, i, lane, C4, src_s, alpha_s, r0, r1, g, GVQA_EPI_NONE, [&](int c4, const float4& v) {
+        *reinterpret_cast<float4*>(dst + 4 * c4) = v;
+        local += (v.x + v.y) + (v.z + v.w);
+      });
+    }
+  } else {
+    // oversize graph: per-warp gather straight to h_out without the normalisation, then normalise in place
+    HopParams q = p;
+    q.epilogue = GVQA_EPI_NONE;
+    rows = p.h_out + (int64_t)n0 * C;
+    float* alpha_w = alpha_s + wid * (kEdgeChunk * H);
+    int32_t* src_w = src_s + wid * kEdgeChunk;
+    for (int node = wid; node < n; node += kWarps) gather_node<J, H>(q, n0 + node, lane, 0, C4, alpha_w, src_w, true);
+    __syncthreads();
+    const int64_t cnt4 = (int64_t)n * C4;
+    for (int64_t t = tid; t < cnt4; t += kLnHopThreads) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(rows) + t);
+      local += (v.x + v.y) + (v.z + v.w);
+    }
+  }
+  const float norm = (float)n * (float)C;
+  const float mean = block_sum_256(local, scratch) / norm;
+  const int64_t cnt4 = (int64_t)n * C4;
+  const bool in_smem = rows == rows_s;
+  float q2 = 0.f;
+  for (int64_t t = tid; t < cnt4; t += kLnHopThreads) {
+    const float4 v = in_smem ? reinterpret_cast<const float4*>(rows)[t] : __ldcg(reinterpret_cast<const float4*>(rows) + t);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q2 += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = block_sum_256(q2, scratch) / norm;
+  const float denom = sqrtf(var) + p.ln_eps;
+  const bool affine = p.ln_weight != nullptr && p.ln_bias != nullptr;
+  const float w = affine ? __ldg(p.ln_weight) : 1.f;
+  const float b0 = affine ? __ldg(p.ln_bias) : 0.f;
+  float* out = p.h_out + (int64_t)n0 * C;
+  for (int64_t t = tid; t < cnt4; t += kLnHopThreads) {
+    const float4 v = in_smem ? reinterpret_cast<const float4*>(rows)[t] : __ldcg(reinterpret_cast<const float4*>(rows) + t);
+    float4 o;
+    o.x = (v.x - mean) / denom; o.y = (v.y - mean) / denom; o.z = (v.z - mean) / denom; o.w = (v.w - mean) / denom;
+    if (affine) { o.x = o.x * w + b0; o.y = o.y * w + b0; o.z = o.z * w + b0; o.w = o.w * w + b0; }
+    stg_stream(out + 4 * t, o);
+  }
+}
+
 template <int J, int H>
 static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   if (variant == 1) {
@@ -389,10 +736,76 @@ static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   return GVQA_OK;
 }
 
+template <int J, int H>
+static int launch_ws(const HopParams& p, cudaStream_t stream) {
+  static const int per_sm = [] {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gat_hop_ws_kernel<J, H>, kWsThreads, 0) != cudaSuccess || nb < 1) {
+      (void)cudaGetLastError();
+      nb = 1;
+    }
+    if (const char* e = getenv("GVQA_HOP_WS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= nb) nb = v; }   // experiments
+    return nb;
+  }();
+  const int chunk = WsGeom<H>::kChunk;
+  const int nchunks = (p.N + chunk - 1) / chunk;
+  const int grid = nchunks < kNumSMs * per_sm ? nchunks : kNumSMs * per_sm;
+  if (launch_pdl(2, gat_hop_ws_kernel<J, H>, dim3((unsigned)grid), dim3(kWsThreads), 0, stream, p, nchunks) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return GVQA_ERR_CUDA;
+  }
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+template <int J, int H>
+static int launch_graphln(const HopParams& p, int max_nodes_hint, cudaStream_t stream) {
+  // shared-memory rows for the hinted largest graph (unknown: 64 rows), capped so that two CTAs fit per SM when
+  // the graphs are small and one CTA can still stage ~200 KB
+  const size_t row = (size_t)p.C * 4;
+  size_t want = (size_t)(max_nodes_hint > 0 ? max_nodes_hint : 64) * row;
+  const size_t cap = 200 * 1024;
+  if (want > cap) want = cap - cap % row;
+  const int n_cap = (int)(want / row);
+  static size_t configured = 0;     // largest dynamic shared-memory size the attribute was raised to for this instance
+  if (want > 48 * 1024 && want > configured) {
+    if (cudaFuncSetAttribute(gat_hop_graphln_kernel<J, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return GVQA_ERR_CUDA;
+    }
+    configured = cap;
+  }
+  gat_hop_graphln_kernel<J, H><<<(unsigned)p.B, kLnHopThreads, want, stream>>>(p, n_cap);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
 template <int H>
-static int dispatch_flat(const HopParams& p, int variant, cudaStream_t stream) {
-  const int j = (p.C / 4 + 31) / 32;
-  switch (j) {
+static int dispatch_flat(const HopParams& p, int variant, cudaStream_t stream, int max_nodes_hint = 0) {
+  const int jj = (p.C / 4 + 31) / 32;
+  if (p.epilogue == GVQA_EPI_GRAPH_LN) {
+    switch (jj) {
+      case 1: return launch_graphln<1, H>(p, max_nodes_hint, stream);
+      case 2: return launch_graphln<2, H>(p, max_nodes_hint, stream);
+      case 3: return launch_graphln<3, H>(p, max_nodes_hint, stream);
+      case 4: return launch_graphln<4, H>(p, max_nodes_hint, stream);
+      case 5: case 6: return launch_graphln<6, H>(p, max_nodes_hint, stream);
+      case 7: case 8: return launch_graphln<8, H>(p, max_nodes_hint, stream);
+      default: return GVQA_ERR_UNSUPPORTED;
+    }
+  }
+  if (variant == 4) {
+    switch (jj) {
+      case 1: return launch_ws<1, H>(p, stream);
+      case 2: return launch_ws<2, H>(p, stream);
+      case 3: return launch_ws<3, H>(p, stream);
+      case 4: return launch_ws<4, H>(p, stream);
+      case 5: case 6: return launch_ws<6, H>(p, stream);
+      case 7: case 8: return launch_ws<8, H>(p, stream);
+      default: return GVQA_ERR_UNSUPPORTED;
+    }
+  }
+  switch (jj) {
     case 1: return launch_flat<1, H>(p, variant, stream);
     case 2: return launch_flat<2, H>(p, variant, stream);
     case 3: return launch_flat<3, H>(p, variant, stream);
@@ -673,10 +1086,13 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->num_nodes == 0) return GVQA_OK;
   if (!a->x_l || !a->a_node || !a->rowptr || !a->node_graph || !a->h_out) return GVQA_ERR_NULL_POINTER;
   if (a->num_edges > 0 && (!a->a_edge || !a->col_src)) return GVQA_ERR_NULL_POINTER;
-  if (a->epilogue != GVQA_EPI_NONE && (!a->ep_scale || !a->ep_shift)) return GVQA_ERR_NULL_POINTER;
-  if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_AFFINE_RELU) return GVQA_ERR_UNSUPPORTED;
+  if (a->epilogue < GVQA_EPI_NONE || a->epilogue > GVQA_EPI_GRAPH_LN) return GVQA_ERR_UNSUPPORTED;
+  if ((a->epilogue == GVQA_EPI_AFFINE || a->epilogue == GVQA_EPI_AFFINE_RELU) && (!a->ep_scale || !a->ep_shift))
+    return GVQA_ERR_NULL_POINTER;
+  if (a->epilogue == GVQA_EPI_GRAPH_LN && (!a->graph_ptr || a->num_graphs <= 0)) return GVQA_ERR_NULL_POINTER;
+  if (a->variant == 4 && !a->sched) return GVQA_ERR_NULL_POINTER;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
-  if (a->variant < 0 || a->variant > 3) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || a->variant > 4) return GVQA_ERR_UNSUPPORTED;
   if ((a->ldx & 3) || (a->ld_graph_bias & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
@@ -699,9 +1115,10 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
     return e ? atoi(e) : 0;
   }();
   p.prefetch = env_prefetch;
+  p.sched = a->sched; p.ln_weight = a->ln_weight; p.ln_bias = a->ln_bias; p.ln_eps = a->ln_eps;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-  if (a->variant == 2) {
+  if (a->variant == 2 && a->epilogue != GVQA_EPI_GRAPH_LN) {
     StagedPlan plan;
     if (!a->graph_ptr || a->num_graphs <= 0 ||
         !plan_staged(C, H, a->max_nodes_per_graph, a->max_in_edges_per_graph, &plan))
@@ -713,12 +1130,12 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
       case 8: return launch_staged<8>(p, plan, stream);
     }
   }
-  const int variant = a->variant == 1 ? 1 : 3;
+  const int variant = a->variant == 1 ? 1 : (a->variant == 4 ? 4 : 3);
   switch (H) {
-    case 1: return dispatch_flat<1>(p, variant, stream);
-    case 2: return dispatch_flat<2>(p, variant, stream);
-    case 4: return dispatch_flat<4>(p, variant, stream);
-    case 8: return dispatch_flat<8>(p, variant, stream);
+    case 1: return dispatch_flat<1>(p, variant, stream, a->max_nodes_per_graph);
+    case 2: return dispatch_flat<2>(p, variant, stream, a->max_nodes_per_graph);
+    case 4: return dispatch_flat<4>(p, variant, stream, a->max_nodes_per_graph);
+    case 8: return dispatch_flat<8>(p, variant, stream, a->max_nodes_per_graph);
   }
   return GVQA_ERR_UNSUPPORTED;
 }

@@ -12,9 +12,10 @@
 
 namespace gvqa {
 
+template <typename Index>
 __global__ void __launch_bounds__(256) gather_add_relu_kernel(
     const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-    const float* __restrict__ bias, const int64_t* __restrict__ edge_index, float* __restrict__ out, int64_t E,
+    const float* __restrict__ bias, const Index* __restrict__ edge_index, float* __restrict__ out, int64_t E,
     int F, int relu) {
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -64,8 +65,47 @@ __global__ void __launch_bounds__(256) segment_mean_rows_kernel(
   }
 }
 
-// One CTA per graph: softmax of the per-node gate over the graph's nodes, then sum_n w_n x[n,:]
-__global__ void __launch_bounds__(256) attention_pool_kernel(const float* __restrict__ gate,
+// out[n,:] = x[n,:] * q[g(n),:]  -- the `ques_nn(u)[batch] * node_nn(x)` product of MyConditionalGlobalAttention
+// (pipeline_model_gat.py:166-167) without materialising q[batch]
+__global__ void __launch_bounds__(256) graph_scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ q,
+                                                               const int32_t* __restrict__ node_graph,
+                                                               float* __restrict__ out, int64_t N, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const float* qr = q + (int64_t)node_graph[i] * C;
+  for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+    float4 v = ldg_stream(x + i * C + 4 * c4);
+    const float4 u = ldg_cached(qr + 4 * c4);
+    v.x *= u.x; v.y *= u.y; v.z *= u.z; v.w *= u.w;
+    stg_stream(out + i * C + 4 * c4, v);
+  }
+}
+
+// out[n,c] = act(x[n,c] * scale[c] + shift[c])  -- BatchNorm1d(eval) folded to an affine map + ReLU, the whole
+// bug-faithful GCN / GINE hop (the conv result is discarded by the reference, pipeline_model_gcn.py:660-668)
+__global__ void __launch_bounds__(256) affine_relu_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float* __restrict__ out,
+                                                          int64_t total4, int C4, int relu) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += stride) {
+    const int c4 = (int)(t % C4);
+    float4 v = ldg_stream(x + 4 * t);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    stg_stream(out + 4 * t, v);
+  }
+}
+
+// One CTA per graph: softmax of the per-node gate over the graph's nodes, then sum_n w_n x[n,:].
+// With `hid` given, the gate itself is computed here first: gate[n] = <hid[n,:], w_gate> + b_gate (the last Linear
+// of gate_nn, pipeline_model_gat.py:128 / :168), one warp per node, and parked in `gate` (scratch, [N]).
+__global__ void __launch_bounds__(256) attention_pool_kernel(float* __restrict__ gate,
+                                                             const float* __restrict__ hid, int Ch,
+                                                             const float* __restrict__ w_gate,
+                                                             const float* __restrict__ b_gate,
                                                              const float* __restrict__ x,
                                                              const int32_t* __restrict__ graph_ptr,
                                                              float* __restrict__ out, int C) {
@@ -73,9 +113,24 @@ __global__ void __launch_bounds__(256) attention_pool_kernel(const float* __rest
   __shared__ float w_s[256];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n0 = graph_ptr[g], n1 = graph_ptr[g + 1], n = n1 - n0;
+  if (hid != nullptr) {
+    const float b0 = b_gate ? __ldg(b_gate) : 0.f;
+    for (int i = wid; i < n; i += 8) {
+      const float* hr = hid + (int64_t)(n0 + i) * Ch;
+      float acc = 0.f;
+      for (int c4 = lane; c4 < (Ch >> 2); c4 += 32) {
+        const float4 v = ldg_stream(hr + 4 * c4);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w_gate) + c4);
+        acc = fmaf(v.x, w.x, acc); acc = fmaf(v.y, w.y, acc); acc = fmaf(v.z, w.z, acc); acc = fmaf(v.w, w.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) gate[n0 + i] = acc + b0;
+    }
+    __syncthreads();     // the CTA's own global writes are visible to its threads after the barrier
+  }
   // pass 1: segment max (empty segment -> 0, and the output row is 0)
   float mx = -INFINITY;
-  for (int i = tid; i < n; i += 256) mx = fmaxf(mx, gate[n0 + i]);
+  for (int i = tid; i < n; i += 256) mx = fmaxf(mx, __ldcg(gate + n0 + i));
   mx = warp_max(mx);
   if (lane == 0) red[wid] = mx;
   __syncthreads();
@@ -84,7 +139,7 @@ __global__ void __launch_bounds__(256) attention_pool_kernel(const float* __rest
   if (n == 0) mx = 0.f;
   __syncthreads();
   float sum = 0.f;
-  for (int i = tid; i < n; i += 256) sum += expf(gate[n0 + i] - mx);
+  for (int i = tid; i < n; i += 256) sum += expf(__ldcg(gate + n0 + i) - mx);
   sum = warp_sum(sum);
   if (lane == 0) red[wid] = sum;
   __syncthreads();
@@ -98,7 +153,7 @@ __global__ void __launch_bounds__(256) attention_pool_kernel(const float* __rest
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = 0; base < n; base += 256) {
       __syncthreads();
-      if (base + tid < n) w_s[tid] = expf(gate[n0 + base + tid] - mx) / denom;
+      if (base + tid < n) w_s[tid] = expf(__ldcg(gate + n0 + base + tid) - mx) / denom;
       __syncthreads();
       if (c4 < C4) {
         const int lim = min(256, n - base);
@@ -123,8 +178,52 @@ extern "C" GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b,
   if (feat & 3) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)))
     return GVQA_ERR_MISALIGNED;
-  gather_add_relu_kernel<<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  gather_add_relu_kernel<int64_t><<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       a, b, c, bias, edge_index, out, num_edges, feat, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float* b, const float* c, const float* bias,
+                                                     const int32_t* edge_index, float* out, int64_t num_edges,
+                                                     int32_t feat, int32_t relu, void* stream_) {
+  if (num_edges < 0 || feat <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_edges == 0) return GVQA_OK;
+  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
+  if (feat & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)))
+    return GVQA_ERR_MISALIGNED;
+  gather_add_relu_kernel<int32_t><<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      a, b, c, bias, edge_index, out, num_edges, feat, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_affine_relu_f32(const float* x, const float* scale, const float* shift, float* out,
+                                             int64_t num_rows, int32_t channels, int32_t relu, void* stream_) {
+  if (num_rows < 0 || channels <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_rows == 0) return GVQA_OK;
+  if (!x || !scale || !shift || !out) return GVQA_ERR_NULL_POINTER;
+  if (channels & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(out) || !aligned16(scale) || !aligned16(shift)) return GVQA_ERR_MISALIGNED;
+  const int64_t total4 = num_rows * (channels >> 2);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;     // grid-stride over a resident grid
+  affine_relu_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, scale, shift, out, total4,
+                                                                                        channels >> 2, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_graph_scale_rows_f32(const float* x, const float* q, const int32_t* node_graph, float* out,
+                                                  int64_t num_nodes, int32_t channels, void* stream_) {
+  if (num_nodes < 0 || channels <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!x || !q || !node_graph || !out) return GVQA_ERR_NULL_POINTER;
+  if (channels & 3) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(q) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
+  graph_scale_rows_kernel<<<(unsigned)((num_nodes + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      x, q, node_graph, out, num_nodes, channels);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
@@ -150,8 +249,23 @@ extern "C" GVQA_API int gvqa_attention_pool_f32(const float* gate, const float* 
   if (!gate || !x || !graph_ptr || !out) return GVQA_ERR_NULL_POINTER;
   if (channels & 3) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
-  attention_pool_kernel<<<(unsigned)num_graphs, 256, 0, static_cast<cudaStream_t>(stream_)>>>(gate, x, graph_ptr, out,
-                                                                                                channels);
+  attention_pool_kernel<<<(unsigned)num_graphs, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      const_cast<float*>(gate), nullptr, 0, nullptr, nullptr, x, graph_ptr, out, channels);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_attention_pool_gate_f32(const float* hid, int32_t hid_channels, const float* w_gate,
+                                                     const float* b_gate, float* gate_scratch, const float* x,
+                                                     const int32_t* graph_ptr, float* out, int64_t num_graphs,
+                                                     int32_t channels, void* stream_) {
+  if (num_graphs < 0 || channels <= 0 || hid_channels <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_graphs == 0) return GVQA_OK;
+  if (!hid || !w_gate || !gate_scratch || !x || !graph_ptr || !out) return GVQA_ERR_NULL_POINTER;
+  if ((channels & 3) || (hid_channels & 3)) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(out) || !aligned16(hid) || !aligned16(w_gate)) return GVQA_ERR_MISALIGNED;
+  attention_pool_kernel<<<(unsigned)num_graphs, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      gate_scratch, hid, hid_channels, w_gate, b_gate, x, graph_ptr, out, channels);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }

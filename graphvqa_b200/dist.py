@@ -6,7 +6,8 @@ no collective at all (each rank even writes its own result dump, :938-942).  The
 shape: a batch of disjoint graphs is split into contiguous graph ranges (``shard_scene_graphs``),
 each rank runs the unchanged single-GPU path on its range, and ONE collective assembles the
 answer logits (``all_gather_logits``: NCCL all-gather of [B/G, 1842] fp32, < 1 MB per rank).
-Every op on the path is per-graph, so the G-GPU result equals the 1-GPU result row for row.
+Every op on the path is per-graph, so the G-GPU result equals the 1-GPU result row for row (including the
+reference's un-offset ``added_sym_edge`` negation, see ``shard_scene_graphs``).
 """
 import os
 
@@ -45,8 +46,14 @@ def graph_range(num_graphs, rank, world):
 def shard_scene_graphs(graphs, rank, world, num_graphs=None):
     """The sub-batch of graphs [lo, hi) of ``graphs`` (any object with the SceneGraphBatch fields) with
     node ids re-based to start at 0.  Works on CPU or GPU tensors; ``batch`` must be sorted.
-    ``added_sym_edge`` keeps the reference's (un-offset, graph-local) convention: the entries that
-    belong to graphs of this shard are kept as they are."""
+    ``added_sym_edge``: the reference applies these indices to rows of the BATCHED edge array although
+    they are graph-local (Batch.from_data_list does not offset them; pipeline_model_gat.py:590), so the
+    single-GPU run negates the embedding of edge rows ``added_sym_edge`` of the full batch.  To make the
+    sharded result equal the single-GPU result row for row, the shard carries exactly those rows that
+    fall inside its edge slice, re-based to shard-local edge positions (out-of-range entries, which the
+    reference would fault on, are dropped).  This is NOT what per-rank collation under
+    DistributedSampler produces (each rank would then negate the low-numbered rows of its own batch);
+    ``collate_scene_graphs`` on the rank's own graphs reproduces that behaviour."""
     b = num_graphs if num_graphs is not None else getattr(graphs, "num_graphs", None)
     if b is None:
         b = int(graphs.batch.max()) + 1
@@ -64,7 +71,13 @@ def shard_scene_graphs(graphs, rank, world, num_graphs=None):
     out.batch = batch[n0:n1] - lo
     out.edge_index = ei[:, keep] - n0
     out.edge_attr = None if getattr(graphs, "edge_attr", None) is None else graphs.edge_attr[keep]
-    out.added_sym_edge = getattr(graphs, "added_sym_edge", None)
+    sym = getattr(graphs, "added_sym_edge", None)
+    if sym is not None:
+        mask = torch.zeros(ei.size(1), dtype=torch.bool, device=ei.device)
+        sym = sym[(sym >= 0) & (sym < ei.size(1))]
+        mask[sym] = True
+        sym = mask[keep].nonzero().flatten()
+    out.added_sym_edge = sym
     out.node_range, out.edge_mask = (n0, n1), keep
     return out
 

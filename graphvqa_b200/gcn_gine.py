@@ -95,11 +95,24 @@ class GINEConv(nn.Module):
 
 
 class _seq_base(nn.Module):
+    _folded = None
+
     def _bn_relu(self, h, i):
+        """eval-mode BatchNorm1d + ReLU (+ Dropout = identity) as ONE kernel: the statistics fold into a per-channel
+        scale / shift (cached per parameter version), ``gvqa_affine_relu_f32`` applies them."""
         bn = self.bns[i]
-        # eval-mode BatchNorm1d + ReLU (+ Dropout = identity), plain elementwise torch ops
-        return torch.relu(torch.nn.functional.batch_norm(h, bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                                                         False, 0.0, bn.eps))
+        key = tuple((t.data_ptr(), t._version) for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+                    if t is not None)
+        if self._folded is None:
+            self._folded = {}
+        hit = self._folded.get(i)
+        if hit is None or hit[0] != key:
+            inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+            g = bn.weight.detach().double() if bn.affine else torch.ones_like(inv)
+            b = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
+            hit = self._folded[i] = (key, (g * inv).float().contiguous(),
+                                     (b - bn.running_mean.detach().double() * g * inv).float().contiguous())
+        return _cabi.affine_relu(h.contiguous(), hit[1], hit[2], relu=True)
 
 
 class gcn_seq(_seq_base):

@@ -41,6 +41,27 @@ class GraphCSR:
         return dict(max_nodes=s[0], max_in_edges=s[1], max_in_degree=s[2], bad_edges=s[3])
 
     @staticmethod
+    def from_host(parts, device, non_blocking=True):
+        """Device CSR from the loader-side build (``_cabi.build_csr_host`` / ``collate.collate_wire``): the int32
+        arrays are copied as they are, no CSR kernel runs on the GPU.  The hints come from the host stats."""
+        st = parts["stats"]
+        dev = {k: parts[k].to(device=device, non_blocking=non_blocking)
+               for k in ("rowptr", "col_src", "perm", "graph_ptr", "node_graph", "stats")}
+        n, b = parts["rowptr"].numel() - 1, parts["graph_ptr"].numel() - 1
+        e = int(parts["rowptr"][n]) if n >= 0 else 0
+        return GraphCSR(dev, n, e, b, int(st[0]), int(st[1]))
+
+    def check(self):
+        """Synchronising sanity check (debug / first batch of a new data source): raises when the build counted
+        edges whose endpoints are out of range or lie in different graphs, or batch ids that are out of range or
+        not sorted -- inputs for which the per-graph folding of the instruction terms is not valid."""
+        st = self.read_stats()
+        if st["bad_edges"]:
+            raise ValueError("GraphCSR: %d invalid edges / batch ids (endpoints out of range or in different "
+                             "graphs, graph ids outside [0, num_graphs) or unsorted)" % st["bad_edges"])
+        return st
+
+    @staticmethod
     def build(edge_index, batch, num_graphs, max_nodes_per_graph=0, max_in_edges_per_graph=0,
               read_hints=False):
         """read_hints=True fills missing hints from the device stats (one host sync)."""

@@ -69,13 +69,19 @@ def _batch_csr(graphs, num_graphs):
         if graphs.num_graphs is None:
             graphs.num_graphs = num_graphs
         return graphs.csr()
-    csr = getattr(graphs, "_gvqa_csr", None)
-    if csr is None or csr.num_graphs != num_graphs or csr.rowptr.device != graphs.edge_index.device:
-        csr = GraphCSR.build(graphs.edge_index, graphs.batch, num_graphs)
-        try:
-            graphs._gvqa_csr = csr
-        except Exception:
-            pass
+    ei, bt = graphs.edge_index, graphs.batch
+    # the cache is only valid for the very tensors it was built from (foreign batch objects may be reused with
+    # new contents): storage, in-place version, shape and device all enter the key
+    key = (num_graphs, ei.device, ei.data_ptr(), ei._version, tuple(ei.shape), bt.data_ptr(), bt._version,
+           tuple(bt.shape))
+    cached = getattr(graphs, "_gvqa_csr", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    csr = GraphCSR.build(ei, bt, num_graphs)
+    try:
+        graphs._gvqa_csr = (key, csr)
+    except Exception:
+        pass
     return csr
 
 
@@ -292,21 +298,28 @@ class MyConditionalGlobalAttention(nn.Module):
         self.ques_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c))
         self._lin = _TensorCoreLinear()
 
-    def forward(self, x, u, batch, size=None, graph_ptr=None):
+    def forward(self, x, u, batch, size=None, graph_ptr=None, node_graph=None):
+        """x [N,F], u [B,c] (question summary), batch [N] -> [B,c].  ``graph_ptr`` / ``node_graph`` (int32, from the
+        batch's GraphCSR) avoid the reference's ``batch[-1].item()`` host sync (:152) and the bincount."""
         x = x.unsqueeze(-1) if x.dim() == 1 else x
-        size = u.size(0) if size is None else size        # the reference syncs on batch[-1].item() (:152)
+        size = u.size(0) if size is None else size
         lin = self._lin                                    # node-level Linear layers on the tensor-core GEMM
         nn_, gn, qn = self.node_nn, self.gate_nn, self.ques_nn
         x = lin(torch.relu_(lin(x, nn_[0].weight, nn_[0].bias)), nn_[2].weight, nn_[2].bias)
-        q = qn(u)                                          # [B, c]: per graph, tiny
-        hid = torch.relu_(lin(q[batch] * x, gn[0].weight, gn[0].bias))
-        gate = gn[2](hid)                                  # [N, 1]
+        q = qn(u).contiguous()                             # [B, c]: per graph, tiny
         if graph_ptr is None:
             counts = torch.bincount(batch, minlength=size)
             graph_ptr = torch.zeros(size + 1, dtype=torch.int32, device=x.device)
             graph_ptr[1:] = counts.cumsum(0).to(torch.int32)
-        # per-graph softmax + weighted sum in one kernel (replaces scatter_max / exp / scatter_add / gathers)
-        return _cabi.attention_pool(gate, x.contiguous(), graph_ptr.to(torch.int32), size)
+        if node_graph is None:
+            node_graph = batch.to(torch.int32)
+        # q[batch] * x without materialising q[batch]; then gate_nn's hidden layer on the tensor-core GEMM
+        hid = torch.relu_(lin(_cabi.graph_scale_rows(x.contiguous(), q, node_graph), gn[0].weight, gn[0].bias))
+        # gate_nn's Linear(c,1) + per-graph softmax (PyG semantics) + weighted sum in ONE kernel
+        # (replaces a GEMV launch, scatter_max / exp / scatter_add / gathers)
+        pooled, _ = _cabi.attention_pool_gate(hid, gn[2].weight, gn[2].bias, x.contiguous(),
+                                              graph_ptr.to(torch.int32), size)
+        return pooled
 
 
 class PipelineModel(nn.Module):
@@ -354,39 +367,94 @@ class PipelineModel(nn.Module):
                             instr_vectors=instr_vectors, batch=graphs.batch, csr=csr)
 
     # -------------------------------------------------------------------------------------------
-    def forward(self, questions, gt_scene_graphs, programs_input, full_answers_input, SAMPLE_FLAG=False):
-        _cabi.require_cuda(questions, gt_scene_graphs.edge_index)
-        if self.training or torch.is_grad_enabled():
-            raise NotImplementedError("PipelineModel (B200 engine) is inference-only: call .eval() and run under "
-                                      "torch.no_grad(); training stays on the reference path")
-        num_graphs = questions.size(1)
-        csr = _batch_csr(gt_scene_graphs, num_graphs)
-        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+    # strict_range: the default fp16-split projection of gat_seq flags inputs outside fp16's range on the device.
+    # True (default): every eager call synchronises on that flag before returning and redoes the graph side with the
+    # tf32 split when it is set -- the caller never sees an invalid result (the reference's validate() synchronises
+    # per batch anyway, mainExplain_gat.py:782).  False: no sync; call ``model.gat_seq.check_overflow()`` yourself.
+    strict_range = True
+    # overlap_text: the Transformer text side (question encoder + program decoder) runs on a second CUDA stream
+    # beside the scene-graph encoder and the CSR build; they join before the hop stack.
+    overlap_text = True
+    _text_stream = None
+
+    def _text_side(self, questions, programs_input, mode):
+        """mode: "coarse" (instruction vectors only), "teacher" (forward), "sample" (greedy)."""
         questions_encoded = self.question_encoder(questions)
-        if not SAMPLE_FLAG:
-            programs_output, instr_vectors = self.program_decoder(memory=questions_encoded, tgt=programs_input)
+        if mode == "coarse":
+            return questions_encoded, None, self.program_decoder.instruction_vectors(questions_encoded)[0]
+        if mode == "teacher":
+            programs_output, instr = self.program_decoder(memory=questions_encoded, tgt=programs_input)
         else:
-            programs_output, instr_vectors = self.program_decoder.sample(memory=questions_encoded, tgt=programs_input)
+            programs_output, instr = self.program_decoder.sample(memory=questions_encoded, tgt=programs_input)
+        return questions_encoded, programs_output, instr
+
+    def graph_side(self, gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr=None, encoded=None):
+        """Everything between the text stack and the answer: scene-graph encoder -> hop stack -> conditional
+        attention pooling -> logit_fc (pipeline_model_gat.py:751, 791-816).  ``questions_encoded`` [L,B,D] (only
+        row 0 is used by the GAT / GCN / GINE variants).  Returns short_answer_logits [B, 1842]."""
+        if csr is None:
+            csr = _batch_csr(gt_scene_graphs, num_graphs)
+        if encoded is None:
+            encoded = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+        x_encoded, edge_attr_encoded = encoded[0], encoded[1]
+        seq = getattr(self, "gat_seq", None)
+        guarded = (self.strict_range and seq is not None and seq.projection == "3xf16"
+                   and not torch.cuda.is_current_stream_capturing())
+        if seq is not None:
+            seq.overflow_external = guarded or seq.overflow_external
         x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
+        if guarded and seq._overflow is not None and int(seq._overflow) != 0:      # one host sync per call
+            seq._overflow.zero_()
+            seq.projection = "3xtf32"
+            try:
+                x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors,
+                                           questions_encoded, csr)
+            finally:
+                seq.projection = "3xf16"
         q0 = questions_encoded[0]
-        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch,
-                                                     size=num_graphs, graph_ptr=csr.graph_ptr)
-        short_answer_logits = self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
-        return programs_output, short_answer_logits
+        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch, size=num_graphs,
+                                                     graph_ptr=csr.graph_ptr, node_graph=csr.node_graph)
+        return self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
+
+    def _run(self, questions, gt_scene_graphs, programs_input, mode):
+        _cabi.require_cuda(questions, gt_scene_graphs.edge_index)
+        num_graphs = questions.size(1)
+        dev = questions.device
+        if self.overlap_text:
+            cur = torch.cuda.current_stream(dev)
+            if self._text_stream is None or self._text_stream.device != dev:
+                self._text_stream = torch.cuda.Stream(dev)
+            side = self._text_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                questions_encoded, programs_output, instr_vectors = self._text_side(questions, programs_input, mode)
+            csr = _batch_csr(gt_scene_graphs, num_graphs)                      # graph side, concurrently
+            encoded = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+            cur.wait_stream(side)
+            for t in (questions_encoded, programs_output, instr_vectors):
+                if t is not None:
+                    t.record_stream(cur)
+        else:
+            csr = _batch_csr(gt_scene_graphs, num_graphs)
+            encoded = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
+            questions_encoded, programs_output, instr_vectors = self._text_side(questions, programs_input, mode)
+        logits = self.graph_side(gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr=csr, encoded=encoded)
+        return programs_output, logits
+
+    def forward(self, questions, gt_scene_graphs, programs_input, full_answers_input, SAMPLE_FLAG=False):
+        if self.training:
+            raise NotImplementedError("PipelineModel (B200 engine) is inference-only: call .eval(); training stays "
+                                      "on the reference path")
+        # the reference's validate() wraps the call in torch.no_grad() (mainExplain_gat.py:701); a drop-in caller in
+        # eval mode without it must not break: nothing here is differentiable anyway
+        with torch.no_grad():
+            return self._run(questions, gt_scene_graphs, programs_input, "sample" if SAMPLE_FLAG else "teacher")
 
     def answer_logits(self, questions, gt_scene_graphs):
         """Inference fast path: the short-answer logits do not depend on the fine program decoder
         (SURVEY.md section 0, fact 10), so only the coarse decoder runs."""
-        num_graphs = questions.size(1)
-        csr = _batch_csr(gt_scene_graphs, num_graphs)
-        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
-        questions_encoded = self.question_encoder(questions)
-        instr_vectors = self.program_decoder.instruction_vectors(questions_encoded)[0]
-        x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
-        q0 = questions_encoded[0]
-        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch,
-                                                     size=num_graphs, graph_ptr=csr.graph_ptr)
-        return self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
+        with torch.no_grad():
+            return self._run(questions, gt_scene_graphs, None, "coarse")[1]
 
     def load_state_dict(self, state_dict, strict=True):
         """Size-tolerant load (pipeline_model_gat.py:823-836): keys that are missing here or whose

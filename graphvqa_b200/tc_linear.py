@@ -18,9 +18,12 @@ class TensorCoreLinear:
     def __call__(self, x, weight, bias=None):
         """x [M, K] float32 CUDA, weight [N, K] (any strides), bias [N] or None -> [M, N]."""
         k = weight.size(1)
-        if not x.is_cuda or k % 4 or x.size(0) == 0:
-            y = x @ weight.t()
-            return y if bias is None else y + bias
+        _cabi.require_cuda(x, weight, bias)              # raises: there is no CPU fallback
+        if k % 4:
+            raise ValueError("TensorCoreLinear: the input width must be a multiple of 4 (got %d); pad the weight "
+                             "columns or call torch.nn.functional.linear explicitly" % k)
+        if x.size(0) == 0:                               # nothing to compute, nothing to launch
+            return x.new_zeros(0, weight.size(0))
         key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
         split = self._cache.get(key)
         if split is None:

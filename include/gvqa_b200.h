@@ -16,7 +16,12 @@
  *    gvqa_build_csr from the reference's int64 COO `edge_index` ([0]=source j, [1]=target i).
  *  - Return value: GVQA_OK (0) or a negative gvqa_status; gvqa_error_string() describes it.
  *    Argument errors are detected on the host before anything is enqueued.
- *  - Thread-safe: no global mutable state (a one-time cudaFuncSetAttribute per kernel aside).
+ *  - Threading: the entry points keep no per-call state; concurrent calls from several host threads on
+ *    different streams are safe.  Process-wide state exists in three places, all write-once or debug-only:
+ *    (1) one-time cudaFuncSetAttribute / occupancy queries cached in function-local statics (thread-safe
+ *    initialisation), (2) environment switches for experiments (GVQA_PDL, GVQA_HOP_NPC, ...) latched at first
+ *    use, (3) the debug hooks declared in gvqa_b200_debug.h (trace buffers, stage-skipping flags), which are
+ *    plain globals: set them only while no other thread is launching.
  */
 #ifndef GVQA_B200_H_
 #define GVQA_B200_H_
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GVQA_ABI_VERSION 3
+#define GVQA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define GVQA_API __attribute__((visibility("default")))
@@ -50,7 +55,11 @@ typedef enum gvqa_status {
 typedef enum gvqa_epilogue {
   GVQA_EPI_NONE = 0,         /* last hop of gat_seq (gat_skip.py:273: no BN after the final conv) */
   GVQA_EPI_AFFINE = 1,       /* y = out*scale[c] + shift[c]            (BatchNorm1d in eval mode)  */
-  GVQA_EPI_AFFINE_RELU = 2   /* y = relu(out*scale[c] + shift[c])      (gat_skip.py:274-275)       */
+  GVQA_EPI_AFFINE_RELU = 2,  /* y = relu(out*scale[c] + shift[c])      (gat_skip.py:274-275)       */
+  GVQA_EPI_GRAPH_LN = 3      /* y = my_graph_layernorm.LayerNorm(out, batch): per-graph statistics over all
+                                nodes x channels, two-pass variance, eps added to the std, scalar affine
+                                (graph_utils/my_graph_layernorm.py:52-78); one CTA per graph keeps the rows in
+                                shared memory, so the normalisation costs no extra HBM pass                 */
 } gvqa_epilogue;
 
 GVQA_API int gvqa_abi_version(void);
@@ -86,6 +95,17 @@ GVQA_API int gvqa_build_csr(const int64_t* edge_index, int64_t num_edges, const 
                    int64_t num_nodes, int64_t num_graphs, int32_t* rowptr, int32_t* col_src,
                    int32_t* perm, int32_t* graph_ptr, int32_t* node_graph, int32_t* stats,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same build on the HOST, for the data-loader side (the reference collates with
+ * torch_geometric's Batch.from_data_list and ships int64 COO, gqa_dataset_entry.py:631-675): every pointer is a
+ * HOST pointer (ideally pinned), `index_bytes` / `batch_bytes` give the width of the inputs (4 = int32, 8 = int64).
+ * Outputs equal gvqa_build_csr's bit for bit (stable counting sort, same clamping, same stats); the device then
+ * receives rowptr / col_src / perm / graph_ptr / node_graph in their final int32 form and runs no CSR kernel.
+ * No workspace argument: scratch of N int32 is allocated internally (host code). */
+GVQA_API int gvqa_build_csr_host(const void* edge_index_host, int32_t index_bytes, int64_t num_edges,
+                                 const void* batch_host, int32_t batch_bytes, int64_t num_nodes, int64_t num_graphs,
+                                 int32_t* rowptr_host, int32_t* col_src_host, int32_t* perm_host,
+                                 int32_t* graph_ptr_host, int32_t* node_graph_host, int32_t* stats_host);
 
 /* ------------------------------------------------------------------------------------------
  * Skinny projection  out[M,K] = x[M,F] @ v[K,F]^T,  K <= 32, F % 4 == 0  (v laid out like an
@@ -144,11 +164,18 @@ typedef struct gvqa_gat_hop_args {
   int32_t epilogue;        /* gvqa_epilogue                                                   */
   int32_t max_nodes_per_graph;    /* loader hints (0 = unknown) that size the shared-memory staged  */
   int32_t max_in_edges_per_graph; /* kernel; never a correctness input (oversize graphs fall back)   */
-  int32_t variant;         /* 0 = auto, 1 = warp-per-node gather, 2 = TMA smem-staged, 3 = block-phase gather */
+  int32_t variant;         /* 0 = auto, 1 = warp-per-node gather, 2 = TMA smem-staged, 3 = block-phase gather,
+                              4 = persistent warp-specialised (producer warp prepares chunks, needs `sched`) */
   int64_t ld_graph_bias;   /* row stride of graph_bias in floats; 0 = dense (C); multiple of 4            */
   int64_t ld_a_graph;      /* row stride of a_graph in floats; 0 = dense (H).  Both terms may be column
                               blocks of one pre-pass GEMM output                                          */
   int32_t flags;           /* GVQA_HOP_* bits                                                             */
+  float ln_eps;            /* GVQA_EPI_GRAPH_LN: eps (added to the standard deviation)                            */
+  const float* ln_weight;  /* GVQA_EPI_GRAPH_LN: ONE float each on the device (the reference's parameters have    */
+  const float* ln_bias;    /*   shape [1]), or both NULL for no affine                                            */
+  int32_t* sched;          /* variant 4: two int32 of device scratch, zero before the first launch; the kernel
+                              leaves them zero again (dynamic chunk scheduler); may be NULL otherwise.  Two
+                              launches that may run concurrently need separate words                              */
 } gvqa_gat_hop_args;
 
 /* The block kernel is launched with programmatic stream serialization: its CTAs may start while the previous
@@ -180,14 +207,6 @@ GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, 
  * A_hi*B_hi is accumulated in fp32 in tensor memory.  B must be pre-split with gvqa_split_tf32
  * (weights: once per checkpoint); A is split on the fly.  k, lda, ldb, ldc multiples of 4.
  */
-/* debug: device buffer of 1100*8 int64 that CTA 0 fills with clock64() pipeline timestamps; NULL = off */
-GVQA_API void gvqa_debug_set_gemm_trace(long long* device_buffer);
-/* Debug only: bit0 skip TMA loads, bit1 skip the A converters, bit2 skip the epilogue (results are then wrong;
- * used to attribute kernel time in profiles/microbench/gemm_dbg.py).  0 = production behaviour. */
-GVQA_API void gvqa_debug_set_gemm_flags(int flags);
-/* Debug only: per-CTA %globaltimer stamps of the block hop kernel ([grid][8] uint64: start, row pointers loaded,
- * logit terms loaded, softmax done, finish time of warps 0..3); NULL disables.  profiles/microbench/hop_trace.py */
-GVQA_API void gvqa_debug_set_hop_trace(unsigned long long* device_buffer);
 GVQA_API int gvqa_split_tf32(const float* w, float* hi, float* lo, int64_t count, void* stream);
 GVQA_API int gvqa_proj_gemm_3xtf32(const float* a, int64_t lda, const float* b_hi, const float* b_lo,
                                    int64_t ldb, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
@@ -284,11 +303,32 @@ GVQA_API int gvqa_lcgn_hop_f32(const float* xl, const float* xr, const float* xv
 GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b, const float* c, const float* bias,
                                       const int64_t* edge_index, float* out, int64_t num_edges,
                                       int32_t feat, int32_t relu, void* stream);
+/* the same with the loader-side int32 wire format: edge_index int32 [2,E] */
+GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float* b, const float* c, const float* bias,
+                                          const int32_t* edge_index, float* out, int64_t num_edges,
+                                          int32_t feat, int32_t relu, void* stream);
 GVQA_API int gvqa_segment_mean_rows_f32(const float* values, const int32_t* perm, const int32_t* rowptr,
                                         float* out, int64_t num_segments, int32_t feat, int32_t mean,
                                         void* stream);
 GVQA_API int gvqa_attention_pool_f32(const float* gate, const float* x, const int32_t* graph_ptr, float* out,
                                      int64_t num_graphs, int32_t channels, void* stream);
+
+/* MyConditionalGlobalAttention's tail in two launches instead of six (pipeline_model_gat.py:166-179):
+ *  gvqa_graph_scale_rows_f32: out[n,:] = x[n,:] * q[node_graph[n],:]   (ques_nn(u)[batch] * node_nn(x), q[batch]
+ *     never materialised);
+ *  gvqa_attention_pool_gate_f32: gate[n] = <hid[n,:], w_gate> + *b_gate (gate_nn's last Linear(C,1)), then the
+ *     per-graph softmax and the weighted sum of gvqa_attention_pool_f32 in the same kernel.  gate_scratch: [N]
+ *     floats of device scratch (holds the gates afterwards); b_gate: ONE device float or NULL. */
+/* out[n,c] = x[n,c]*scale[c] + shift[c], then ReLU when relu != 0: BatchNorm1d(eval)+ReLU of the GCN / GINE
+ * sequences (pipeline_model_gcn.py:666-668), whose conv results the reference discards.  In-place allowed. */
+GVQA_API int gvqa_affine_relu_f32(const float* x, const float* scale, const float* shift, float* out,
+                                  int64_t num_rows, int32_t channels, int32_t relu, void* stream);
+GVQA_API int gvqa_graph_scale_rows_f32(const float* x, const float* q, const int32_t* node_graph, float* out,
+                                       int64_t num_nodes, int32_t channels, void* stream);
+GVQA_API int gvqa_attention_pool_gate_f32(const float* hid, int32_t hid_channels, const float* w_gate,
+                                          const float* b_gate, float* gate_scratch, const float* x,
+                                          const int32_t* graph_ptr, float* out, int64_t num_graphs,
+                                          int32_t channels, void* stream);
 
 #ifdef __cplusplus
 }

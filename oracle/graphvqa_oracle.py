@@ -100,7 +100,10 @@ class gat_seq(nn.Module):
         self.bns = nn.ModuleList([nn.BatchNorm1d(out_channels) for _ in range(num_ins - 1)])
         self.dropout = dropout
 
-    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, return_hops=False):
+    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, return_hops=False, interleaved_ln=None):
+        """``interleaved_ln`` (a LayerNorm of this file, default None = the reference's behaviour): apply that per-graph
+        LayerNorm between the hops INSTEAD of BatchNorm1d+ReLU -- the north star's "interleaved with
+        my_graph_layernorm" option, which the reference itself does not use (SURVEY.md section 0, fact 4)."""
         h = x
         hops = []
         last = len(self.convs) - 1
@@ -109,7 +112,10 @@ class gat_seq(nn.Module):
             edge_cat = torch.cat((edge_attr, ins[batch[edge_index[0]]]), dim=-1)   # :257-260
             x_cat = torch.cat((h, ins[batch]), dim=-1)                      # :263-264
             h = conv(x_cat, edge_index, edge_cat) + h                       # :269-270
-            if i != last:                                                   # :273-276
+            if i != last and interleaved_ln is not None:
+                h = graph_layernorm(h, batch, instr_vectors.size(1), interleaved_ln.weight, interleaved_ln.bias,
+                                    interleaved_ln.eps)
+            elif i != last:                                                 # :273-276
                 h = F.dropout(F.relu(self.bns[i](h)), p=self.dropout, training=self.training)
             hops.append(h)
         return (h, hops) if return_hops else h
@@ -341,3 +347,128 @@ class lcgn_seq(nn.Module):
             msg = self.lcgn(x_joint, edge_index=edge_index, cmd=cmd, batch=batch)
             x_ctx = self.output_layer(torch.cat([x_ctx, msg], dim=-1))
         return self.fin_layer(torch.cat([x_loc, x_ctx], dim=-1))
+
+
+# --------------------------------------------------------------------------------------
+# Scene-graph encoder (the step before the hop stack)      (reference: pipeline_model_gat.py)
+# --------------------------------------------------------------------------------------
+class _EdgeModel(nn.Module):
+    """get_gt_scene_graph_encoding_layer.EdgeModel (pipeline_model_gat.py:65-77)."""
+
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.edge_mlp = nn.Sequential(nn.Linear(2 * nf + ef, ef), nn.ReLU(), nn.Linear(ef, ef))
+
+    def forward(self, src, dest, edge_attr, u=None, batch=None):
+        return self.edge_mlp(torch.cat([src, dest, edge_attr], 1))                 # :76-77
+
+
+class _NodeModel(nn.Module):
+    """get_gt_scene_graph_encoding_layer.NodeModel (pipeline_model_gat.py:79-98)."""
+
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.node_mlp_1 = nn.Sequential(nn.Linear(nf + ef, nf), nn.ReLU(), nn.Linear(nf, nf))
+        self.node_mlp_2 = nn.Sequential(nn.Linear(2 * nf, nf), nn.ReLU(), nn.Linear(nf, nf))
+
+    def forward(self, x, edge_index, edge_attr, u=None, batch=None):
+        row, col = edge_index[0], edge_index[1]                                    # :93
+        out = torch.cat([x[row], edge_attr], dim=1)                                # :94
+        out = self.node_mlp_1(out)                                                 # :95
+        out = pyg.scatter_mean(out, col, x.size(0))                                # :96 (count clamped to >= 1)
+        out = torch.cat([x, out], dim=1)                                           # :97
+        return self.node_mlp_2(out)                                                # :98
+
+
+class MetaLayer(nn.Module):
+    """torch_geometric.nn.MetaLayer(EdgeModel(), NodeModel()) (pipeline_model_gat.py:100):
+    edges first, then nodes on the UPDATED edge features."""
+
+    def __init__(self, nf, ef):
+        super().__init__()
+        self.edge_model = _EdgeModel(nf, ef)
+        self.node_model = _NodeModel(nf, ef)
+
+    def forward(self, x, edge_index, edge_attr, u=None, batch=None):
+        row, col = edge_index[0], edge_index[1]
+        edge_attr = self.edge_model(x[row], x[col], edge_attr, u, None if batch is None else batch[row])
+        x = self.node_model(x, edge_index, edge_attr, u, batch)
+        return x, edge_attr, u
+
+
+class GroundTruth_SceneGraph_Encoder(nn.Module):
+    """pipeline_model_gat.py:553-610 with the vocabulary size / pad id passed in (the reference reads them from
+    gqa_dataset_entry class attributes, :556-562).  ``sg_emb_dim`` is 300 in the reference (:560)."""
+
+    def __init__(self, sg_vocab_size, sg_pad_idx=1, sg_emb_dim=300):
+        super().__init__()
+        self.sg_emb_dim = sg_emb_dim
+        self.sg_vocab_embedding = nn.Embedding(sg_vocab_size, sg_emb_dim, padding_idx=sg_pad_idx)
+        self.scene_graph_encoding_layer = MetaLayer(sg_emb_dim, sg_emb_dim)
+        self.graph_layer_norm = LayerNorm(sg_emb_dim)
+
+    def forward(self, gt_scene_graphs):
+        g = gt_scene_graphs
+        x_embed_sum = self.sg_vocab_embedding(g.x).sum(dim=-2)                     # :583-585
+        edge_attr_embed = self.sg_vocab_embedding(g.edge_attr)                     # :587
+        # :590 -- rows `added_sym_edge` of the BATCHED edge array (the indices are graph-local and un-offset)
+        sym = getattr(g, "added_sym_edge", None)
+        if sym is not None and sym.numel() > 0:
+            edge_attr_embed = edge_attr_embed.clone()
+            edge_attr_embed[sym, :, :] *= -1
+        edge_attr_embed_sum = edge_attr_embed.sum(dim=-2)                          # :594
+        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoding_layer(
+            x=x_embed_sum, edge_index=g.edge_index, edge_attr=edge_attr_embed_sum, u=None, batch=g.batch)   # :600-606
+        x_encoded = self.graph_layer_norm(x_encoded, g.batch)                      # :608
+        return x_encoded, edge_attr_encoded, None
+
+
+# --------------------------------------------------------------------------------------
+# Question-conditioned attention pooling (the step after the hop stack)
+# --------------------------------------------------------------------------------------
+class MyConditionalGlobalAttention(nn.Module):
+    """pipeline_model_gat.py:108-185."""
+
+    def __init__(self, num_node_features, num_out_features):
+        super().__init__()
+        c = num_out_features
+        self.gate_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, 1))                 # :126
+        self.node_nn = nn.Sequential(nn.Linear(num_node_features, c), nn.ReLU(), nn.Linear(c, c))  # :127
+        self.ques_nn = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c))                 # :128
+
+    def forward(self, x, u, batch, size=None):
+        x = x.unsqueeze(-1) if x.dim() == 1 else x                                 # :150
+        size = int(batch[-1]) + 1 if size is None else size                        # :152
+        x = self.node_nn(x)                                                        # :161
+        gate = self.gate_nn(self.ques_nn(u)[batch] * x)                            # :171
+        assert gate.dim() == x.dim() and gate.size(0) == x.size(0)                 # :172
+        gate = pyg.segment_softmax(gate, batch, size)                              # :177
+        return pyg.scatter_sum(gate * x, batch, size)                              # :178
+
+
+class GraphSide(nn.Module):
+    """The graph side of PipelineModel.forward (pipeline_model_gat.py:751, 791-816) with the reference's
+    sub-module names: scene_graph_encoder -> gat_seq -> graph_global_attention_pooling -> logit_fc.  The text
+    side's outputs (``instr_vectors`` [5,B,D], ``questions_encoded[0]`` [B,D]) are inputs."""
+
+    def __init__(self, sg_vocab_size, sg_pad_idx=1, sg_emb_dim=300, question_hidden_dim=512, num_answers=1842):
+        super().__init__()
+        f, d = sg_emb_dim, question_hidden_dim
+        self.scene_graph_encoder = GroundTruth_SceneGraph_Encoder(sg_vocab_size, sg_pad_idx, f)
+        self.gat_seq = gat_seq(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d, num_ins=5, dropout=0.1,
+                               gat_heads=4, gat_negative_slope=0.2, gat_bias=True)            # :683-687
+        self.graph_global_attention_pooling = MyConditionalGlobalAttention(num_node_features=f, num_out_features=d)
+        self.logit_fc = nn.Sequential(nn.Dropout(p=0.2), nn.Linear(3 * d, d), nn.ELU(), nn.Dropout(p=0.2),
+                                      nn.Linear(d, num_answers))                               # :722-728
+
+    def forward(self, gt_scene_graphs, instr_vectors, q0, return_parts=False):
+        g = gt_scene_graphs
+        x_encoded, edge_attr_encoded, _ = self.scene_graph_encoder(g)              # :751
+        x_executed = self.gat_seq(x=x_encoded, edge_index=g.edge_index, edge_attr=edge_attr_encoded,
+                                  instr_vectors=instr_vectors, batch=g.batch)      # :791
+        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=g.batch, size=None)   # :800-805
+        logits = self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))       # :814-816
+        if return_parts:
+            return dict(x_encoded=x_encoded, edge_attr_encoded=edge_attr_encoded, x_executed=x_executed,
+                        pooled=pooled, short_answer_logits=logits)
+        return logits

@@ -124,10 +124,88 @@ def make_collate_fixture():
     print(os.path.basename(path), os.path.getsize(path))
 
 
+def make_graph_side_fixtures():
+    """tests/golden/graph_side_gat.pt + encoder_pool_edge.pt.
+
+    graph_side_gat: intermediates of the UNMODIFIED reference PipelineModel on the pipeline_gat.pt inputs, captured
+    with forward hooks: what the text side hands to the graph side (``instr_vectors``, ``questions_encoded[0]``) and
+    what the graph side produces after the hop stack (``x_executed``), after the conditional attention pooling
+    (``pooled``) and after ``logit_fc``.
+    encoder_pool_edge: the reference's GroundTruth_SceneGraph_Encoder on a 7-graph batch with single-node graphs,
+    nodes without in-edges (scatter_mean's clamp, pipeline_model_gat.py:96) and un-offset ``added_sym_edge`` entries
+    of more than 4 graphs (:590); and the reference's MyConditionalGlobalAttention with an EMPTY graph in the middle
+    of the batch and ``size`` larger than ``batch.max() + 1``."""
+    from .golden_utils import deterministic_fill, state_hash
+    os.makedirs(OUT, exist_ok=True)
+    meta = dict(generator="oracle/make_golden.py graph_side", reference=rr.REFERENCE_ROOT, torch=torch.__version__)
+    mod = rr.load("pipeline_model_gat")
+    import torch_geometric
+    with torch.no_grad():
+        base = torch.load(os.path.join(OUT, "pipeline_gat.pt"), weights_only=False)
+        torch.manual_seed(0)
+        model = deterministic_fill(mod.PipelineModel().eval(), seed=base["fill_seed"])
+        assert state_hash(model.state_dict()) == base["state_sha256"]
+        batch_obj = debug_token_batch(seed=606)
+        assert torch.equal(batch_obj.x, base["x"])
+        cap = {}
+        hooks = [
+            model.gat_seq.register_forward_hook(
+                lambda m, a, kw, out: cap.update(instr_vectors=kw["instr_vectors"].clone(), x_executed=out.clone()),
+                with_kwargs=True),
+            model.graph_global_attention_pooling.register_forward_hook(
+                lambda m, a, kw, out: cap.update(q0=kw["u"].clone(), pooled=out.clone()), with_kwargs=True)]
+        _, logits = model(base["questions"], batch_obj, base["programs_input"], None, SAMPLE_FLAG=False)
+        for hk in hooks:
+            hk.remove()
+        assert torch.equal(logits, base["short_answer_logits"])
+        torch.save(dict(meta=meta, inputs="pipeline_gat.pt", fill_seed=base["fill_seed"],
+                        state_sha256=base["state_sha256"], **cap), os.path.join(OUT, "graph_side_gat.pt"))
+
+        # ---- edge cases -------------------------------------------------------------------------
+        gen = torch.Generator().manual_seed(808)
+        sizes = [1, 5, 1, 9, 3, 7, 2]
+        data = []
+        for n in sizes:
+            src = list(range(1, n))          # node 0 of every graph has NO self-loop and no in-edge
+            dst = list(range(1, n))
+            m_extra = 2 * n if n > 1 else 0
+            s_ = torch.randint(0, n, (m_extra,), generator=gen).tolist()
+            d_ = (torch.randint(1, n, (m_extra,), generator=gen).tolist() if n > 1 else [])
+            ei = torch.tensor([src + s_, dst + d_], dtype=torch.long).reshape(2, -1)
+            x = torch.randint(4, rr.SG_VOCAB_SIZE, (n, 12), generator=gen)
+            x[torch.rand(n, 12, generator=gen) < 0.5] = 1
+            ea = torch.randint(4, rr.SG_VOCAB_SIZE, (ei.size(1), 1), generator=gen)
+            d = torch_geometric.data.Data(x=x, edge_index=ei, edge_attr=ea)
+            k = min(3, ei.size(1))
+            d.added_sym_edge = torch.randperm(max(ei.size(1), 1), generator=gen)[:k] if ei.size(1) else torch.zeros(0, dtype=torch.long)
+            data.append(d)
+        b = torch_geometric.data.Batch.from_data_list(data)
+        enc = model.scene_graph_encoder
+        x_enc, e_enc, _ = enc(b)
+        fx = dict(meta=meta, fill_seed=base["fill_seed"], state_sha256=base["state_sha256"],
+                  enc=dict(x=b.x, edge_index=b.edge_index, edge_attr=b.edge_attr, batch=b.batch,
+                           added_sym_edge=b.added_sym_edge, num_graphs=len(sizes), x_encoded=x_enc,
+                           edge_attr_encoded=e_enc))
+        # pooling: 6 graph slots, graph 2 empty, graph 5 (the last slot, beyond batch.max()) empty too
+        torch.manual_seed(809)
+        pool = mod.MyConditionalGlobalAttention(num_node_features=20, num_out_features=16).eval()
+        pb = torch.tensor([0] * 4 + [1] * 1 + [3] * 6 + [4] * 2, dtype=torch.long)
+        px = torch.randn(pb.numel(), 20, generator=gen)
+        pu = torch.randn(6, 16, generator=gen)
+        fx["pool"] = dict(state=pool.state_dict(), x=px, u=pu, batch=pb, size=6, out=pool(px, pu, pb, size=6),
+                          out_default_size=pool(px, pu[:5], pb))
+        torch.save(fx, os.path.join(OUT, "encoder_pool_edge.pt"))
+    for fn in ("graph_side_gat.pt", "encoder_pool_edge.pt"):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
 def main():
     import sys
     if sys.argv[1:] == ["collate"]:
         make_collate_fixture()
+        return
+    if sys.argv[1:] == ["graph_side"]:
+        make_graph_side_fixtures()
         return
     os.makedirs(OUT, exist_ok=True)
     ei, batch = debug_topology()

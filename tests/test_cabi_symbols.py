@@ -11,9 +11,13 @@ from graphvqa_b200 import _cabi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "gvqa_b200.h")).read()
+def declared_symbols(header="gvqa_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(r"GVQA_API\s+[\w\s\*]+?\b(gvqa_\w+)\s*\(", text)))
+
+
+def all_declared_symbols():
+    return sorted(set(sum((declared_symbols(h) for h in os.listdir(os.path.join(ROOT, "include")) if h.endswith(".h")), [])))
 
 
 @pytest.fixture(scope="module")
@@ -30,12 +34,15 @@ def test_header_declares_symbols():
 
 
 def test_library_exports_every_declared_symbol(handle):
-    for name in declared_symbols():
+    for name in all_declared_symbols():
         assert hasattr(handle, name), "libgvqa_b200.so does not export %s" % name
 
 
 def test_binding_covers_header_exactly():
-    assert sorted(_cabi.SIGNATURES) == declared_symbols()
+    assert sorted(_cabi.SIGNATURES) == all_declared_symbols()
+    # the production header carries no debug hooks; they live in gvqa_b200_debug.h
+    assert not [n for n in declared_symbols() if "debug" in n]
+    assert sorted(n for n in _cabi.SIGNATURES if "debug" in n) == declared_symbols("gvqa_b200_debug.h")
 
 
 def test_abi_version_and_error_strings(handle):

@@ -27,8 +27,13 @@ def _per_graph_feature(graphs, num_graphs, width=5):
     deg = torch.zeros(graphs.batch.numel()).index_add_(0, graphs.edge_index[1],
                                                       torch.ones(graphs.edge_index.size(1)))
     node = graphs.x.float().sum(1) * (1 + deg) + graphs.x.float()[graphs.edge_index[0]].sum(1).new_zeros(1)
-    src_sum = torch.zeros(graphs.batch.numel()).index_add_(0, graphs.edge_index[1],
-                                                          graphs.x.float().sum(1)[graphs.edge_index[0]])
+    # like the encoder (pipeline_model_gat.py:590): rows `added_sym_edge` of the BATCHED edge array change sign
+    sign = torch.ones(graphs.edge_index.size(1))
+    sym = getattr(graphs, "added_sym_edge", None)
+    if sym is not None and sym.numel():
+        sign[sym] = -1.0
+    src_sum = torch.zeros(graphs.batch.numel()).index_add_(
+        0, graphs.edge_index[1], sign * (graphs.x.float().sum(1)[graphs.edge_index[0]] + graphs.edge_attr.float()[:, 0]))
     out = torch.zeros(num_graphs, width)
     for k in range(width):
         out[:, k].index_add_(0, graphs.batch, (node + (k + 1) * src_sum) * (k + 1))
@@ -40,7 +45,10 @@ def _make_batch(num_graphs, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.randint(0, 50, (batch.numel(), 3), generator=g)
     ea = torch.randint(0, 50, (ei.size(1), 1), generator=g)
-    return SceneGraphBatch(x=x, edge_index=ei, edge_attr=ea, batch=batch, num_graphs=num_graphs)
+    # graph-local, un-offset positions of synthesized reverse edges, concatenated over the graphs (what
+    # Batch.from_data_list yields): small numbers with repeats, all pointing into the first rows of the batch
+    sym = torch.randint(0, max(2, ei.size(1) // 3), (2 * num_graphs,), generator=g)
+    return SceneGraphBatch(x=x, edge_index=ei, edge_attr=ea, batch=batch, added_sym_edge=sym, num_graphs=num_graphs)
 
 
 def test_graph_range_partitions_exactly():
@@ -68,6 +76,27 @@ def test_shards_rebase_indices_and_cover_the_batch():
         parts.append(_per_graph_feature(s, hi - lo))
     assert n_seen == graphs.batch.numel() and e_seen == graphs.edge_index.size(1)
     assert torch.equal(torch.cat(parts), full)        # graphs are independent: bitwise identical
+
+
+def test_shards_keep_the_sym_edge_rows_of_the_single_batch():
+    """`added_sym_edge` indexes rows of the batched edge array (un-offset, pipeline_model_gat.py:590): every shard
+    must negate exactly the rows of its own slice that the single-GPU run negates -- not the full list."""
+    graphs = _make_batch(9, seed=11)
+    assert graphs.added_sym_edge.numel() > 0
+    negated = torch.zeros(graphs.edge_index.size(1), dtype=torch.bool)
+    negated[graphs.added_sym_edge] = True
+    seen = 0
+    for r in range(4):
+        s = shard_scene_graphs(graphs, r, 4)
+        assert s.added_sym_edge.numel() == 0 or int(s.added_sym_edge.max()) < s.edge_index.size(1)
+        local = torch.zeros(s.edge_index.size(1), dtype=torch.bool)
+        local[s.added_sym_edge] = True
+        assert torch.equal(local, negated[s.edge_mask])
+        seen += int(local.sum())
+    assert seen == int(negated.sum())
+    # a stale index beyond the edge array (the reference would fault) is dropped, not propagated
+    graphs.added_sym_edge = torch.cat([graphs.added_sym_edge, torch.tensor([10 ** 6])])
+    assert int(shard_scene_graphs(graphs, 0, 2).added_sym_edge.max()) < graphs.edge_index.size(1)
 
 
 def _worker(rank, world, port, num_graphs, ret):

@@ -35,7 +35,8 @@ def _worker(rank, world, port, ret):
         g = torch.Generator().manual_seed(5)
         graphs = SceneGraphBatch(x=torch.randint(2, 400, (batch.numel(), 12), generator=g), edge_index=ei,
                                  edge_attr=torch.randint(2, 400, (ei.size(1), 1), generator=g), batch=batch,
-                                 added_sym_edge=torch.zeros(0, dtype=torch.long), num_graphs=b).to(device=dev)
+                                 added_sym_edge=torch.randint(0, ei.size(1) // 3, (2 * b,), generator=g),
+                                 num_graphs=b).to(device=dev)
         questions = torch.randint(4, 500, (7, b), generator=g).to(dev)
         with torch.no_grad():
             gathered = distributed_answer_logits(model, questions, graphs)

@@ -308,6 +308,33 @@ def test_host_runner_redoes_out_of_range_batch_with_full_range_projection():
     assert torch.isfinite(got).all() and (got - want).abs().max() <= 1e-5 * max(scale, 1.0)
 
 
+def test_host_runner_graph_replays_survive_a_full_range_rerun():
+    """With CUDA-graph capture (the default) the slots' graphs hold raw pointers into the fp16 weight pack; the
+    full-range rerun of one overflowed batch must not free or overwrite it: batches submitted afterwards still
+    match the oracle."""
+    from graphvqa_b200.host_api import GatSeqHostRunner
+    cfg = dict(in_channels=64, out_channels=64, edge_attr_dim=64, ins_dim=32, num_ins=2, gat_heads=4)
+    o, e = _pair(cfg, seed=71)
+    ei, batch = random_graphs(6, 4, 12, 2.0, seed=9)
+    good = [list(_inputs(ei, batch, 6, 64, 64, 32, 2, seed=80 + i)) for i in range(6)]
+    bad = list(_inputs(ei, batch, 6, 64, 64, 32, 2, seed=99))
+    bad[0][1, 3] = 8.0e4
+    with torch.no_grad():
+        want_good = [o(*a) for a in good]
+        want_bad = o(*bad)
+    runner = GatSeqHostRunner(e, DEV, depth=2, use_cuda_graph=True)
+    pin = lambda a: [t.pin_memory() for t in a]
+    for i in range(4):                                   # warm up: eager, capture, replays on both slots
+        got = runner(*pin(good[i])).clone()
+        assert (got - want_good[i]).abs().max() <= 1e-4
+    assert all(s.graph is not None for s in runner.slots)
+    got = runner(*pin(bad)).clone()                      # overflow -> rerun with the tf32 split
+    assert torch.isfinite(got).all() and (got - want_bad).abs().max() <= 1e-5 * max(float(want_bad.abs().max()), 1.0)
+    for i in range(6):                                   # replays after the rerun read the SAME fp16 pack
+        got = runner(*pin(good[i])).clone()
+        assert (got - want_good[i]).abs().max() <= 1e-4, i
+
+
 @pytest.mark.parametrize("graphs,nodes,edges", [(256, 30, 60), (128, 200, 800)])
 def test_fused_hop_full_size_properties(graphs, nodes, edges):
     """Size-independent properties of the fused hop at the full BASELINE sizes (cfg2; cfg4 per GPU), straight
