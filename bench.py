@@ -33,6 +33,11 @@ NCU_TRAFFIC_SOURCE = "profiles/r01/hop_final_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
 UNIT = "questions/s"
+# the ONE workload string both arms print (config.workload); implementation details go into other config keys
+WORKLOAD = ("cfg2: 256 synthetic GQA-shape scene graphs per GPU (30 nodes/60 edges), F=512, D=512, 4 heads, "
+            "5-hop GAT-skip (gat_seq.forward)")
+DTYPE = "f32 (projection on tcgen05 with 3xf16-split operands, fp32 accumulate; everything else fp32)"
+SG_VOCAB = 2577          # rebuilt GQA scene-graph vocabulary
 
 
 def hop_bytes(n, e, h, c):
@@ -139,30 +144,243 @@ def cpu_baseline(cfg, steps, warmup, sample_graphs=None):
                 times.append(dt)
     mean = sum(times) / len(times)
     return dict(value=sub["graphs"] / mean, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample="%d graphs of %s per step (full 5-hop gat_seq, fp32, torch %d threads), mean of %d steps"
-                       % (sub["graphs"], cfg["name"], torch.get_num_threads(), len(times)),
+                sample="%d graphs of %s per step (full 5-hop gat_seq, fp32, torch %d threads), mean of %d steps "
+                       "after %d warm-up" % (sub["graphs"], cfg["name"], torch.get_num_threads(), len(times), warmup),
                 ms_per_step=mean * 1e3)
 
 
+def make_token_inputs(cfg, seed, sym_per_graph=4):
+    """The same synthetic batch at the reference's own boundary: token ids instead of pre-encoded features
+    (x [N,12], edge_attr [E,1] token ids, un-offset added_sym_edge) + what the text side hands over."""
+    from graphvqa_b200.graph_batch import synthetic_topology
+    ei, batch, max_nodes = synthetic_topology(cfg["graphs"], cfg["nodes"], cfg["edges"], seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    n, e, b = batch.numel(), ei.size(1), cfg["graphs"]
+    x = torch.randint(4, SG_VOCAB, (n, 12), generator=g)
+    x[torch.rand(n, 12, generator=g) < 0.6] = 1
+    x[:, 0] = torch.randint(4, SG_VOCAB, (n,), generator=g)
+    ea = torch.randint(4, SG_VOCAB, (e, 1), generator=g)
+    sym = torch.randint(0, cfg["edges"], (b * sym_per_graph,), generator=g)          # graph-local, un-offset
+    ins = torch.randn(cfg["hops"], b, cfg["ins"], generator=g)
+    q0 = torch.randn(b, cfg["ins"], generator=g)
+    return dict(x=x, edge_index=ei, edge_attr=ea, added_sym_edge=sym, batch=batch, instr_vectors=ins, q0=q0,
+                max_nodes=max_nodes, max_edges=synthetic_topology.last_max_edges)
+
+
+def per_graph_tensors(tok, cfg):
+    """Split a token batch back into the per-graph tuples a dataset's __getitem__ yields (input of the collator)."""
+    n_, e_, b = cfg["nodes"], cfg["edges"], cfg["graphs"]
+    k = tok["added_sym_edge"].numel() // b
+    return [(tok["x"][i * n_:(i + 1) * n_], tok["edge_index"][:, i * e_:(i + 1) * e_] - i * n_,
+             tok["edge_attr"][i * e_:(i + 1) * e_], tok["added_sym_edge"][i * k:(i + 1) * k]) for i in range(b)]
+
+
+def cpu_graph_side(cfg, steps, warmup):
+    """The reference's graph side at its own boundary (scene-graph encoder -> gat_seq -> pooling -> logit_fc,
+    pipeline_model_gat.py:751, 791-816), restated in oracle/, timed on the host cores."""
+    import types
+    from oracle import graphvqa_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = orc.GraphSide(SG_VOCAB, sg_emb_dim=cfg["feat"], question_hidden_dim=cfg["ins"]).eval()
+    randomise_bn(model.gat_seq, 7)
+    tok = make_token_inputs(cfg, seed=1234)
+    g = types.SimpleNamespace(**{k: tok[k] for k in ("x", "edge_index", "edge_attr", "added_sym_edge", "batch")})
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model(g, tok["instr_vectors"], tok["q0"])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return dict(value=cfg["graphs"] / mean, unit=UNIT, ms_per_step=mean * 1e3, steps=len(times),
+                what="token ids -> scene-graph encoder -> 5-hop gat_seq -> attention pooling -> logit_fc (oracle "
+                     "GraphSide, F=%d), %d graphs per step" % (cfg["feat"], cfg["graphs"]))
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port: the reference's own modules need
+    torch_geometric / torch_scatter, which cannot be installed here) on all host cores.  Honours --steps / --warmup
+    as given; under torchrun rank 0 alone runs it, on the WHOLE job's graphs (weak scaling: 256 per GPU)."""
     if rank != 0:
         return
-    cfg = CFG2
-    steps = max(1, min(args.steps, 5))
-    base = cpu_baseline(cfg, steps=steps, warmup=min(args.warmup, 1))
+    cfg = dict(CFG2)
+    cfg["graphs"] = CFG2["graphs"] * max(1, args.gpus)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base = cpu_baseline(cfg, steps=steps, warmup=warmup)
+    side = cpu_graph_side(CFG2, steps=2, warmup=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_step"],
+        "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 256 synthetic GQA-shape scene graphs (30 nodes/60 edges), F=512, D=512, "
-                               "4 heads, 5-hop GAT-skip (gat_seq.forward)", "impl_note":
+        "config": {"workload": WORKLOAD, "graphs_per_step": cfg["graphs"], "impl_note":
                    "CPU restatement of the reference's PyG dataflow (oracle/graphvqa_oracle.py); the reference's "
                    "own modules need torch_geometric/torch_scatter which are not installable here"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # the engine arm's e2e crosses the boundary the reference's loop has (token ids in, answer logits out) and so
+        # also runs the scene-graph encoder, the pooling and logit_fc; the same work on the host cores, for a
+        # like-for-like e2e comparison (this line's value / e2e time gat_seq.forward only, i.e. LESS work)
+        "graph_side": side,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _bracketed(fn, flush, reps=24):
+    """Median CUDA-event bracket of one launch behind a CLEAN L2 flush (a 256 MB buffer is read, not written) with
+    the stream kept busy, like profiles/microbench/kernel_roofline.py; includes the ~2.7 us an event pair reads."""
+    ts = []
+    for _ in range(reps):
+        flush.sum(); torch.cuda._sleep(150000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts = sorted(ts[4:])
+    return ts[len(ts) // 2]
+
+
+def variant_rooflines(dev, peak, variant):
+    """The other HBM-bound kernels of SURVEY.md section 8 at their BASELINE shapes (cfg3 GINE, cfg5 LCGN per GPU,
+    graph LayerNorm, GCN) and the fused hop at the reference width F=300 and at cfg4 per GPU, measured in this
+    process: algorithmic bytes / bracketed duration."""
+    from graphvqa_b200 import _cabi
+    from graphvqa_b200.graph_batch import GraphCSR, synthetic_topology
+    from graphvqa_b200.my_graph_layernorm import LayerNorm
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+    g = torch.Generator().manual_seed(0)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=g).to(dev)
+
+    def graphs(b, n_, e_):
+        ei, batch, mx = synthetic_topology(b, n_, e_, seed=1234)
+        csr = GraphCSR.build(ei.to(dev), batch.to(dev), b, max_nodes_per_graph=mx,
+                             max_in_edges_per_graph=synthetic_topology.last_max_edges)
+        return ei.size(1), batch.numel(), batch.to(dev), csr
+    out = {}
+
+    def add(name, kernel, us, nbytes, shape):
+        gbs = nbytes / us / 1e3
+        out[name] = {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                     "avg_launch_us": us, "algorithmic_bytes_per_launch": nbytes, "method": "event_bracket, clean L2 flush",
+                     "shape": shape}
+
+    def hop(name, b, n_, e_, f, h=4):
+        e, n, _, csr = graphs(b, n_, e_)
+        x_l, a_edge, hprev, o = rnd(n, h * f + 16), rnd(e, 32), rnd(n, f), torch.empty(n, f, device=dev)
+        gb, ag, bias, sc, sh = rnd(b, f), rnd(b, h), rnd(f), rnd(f), rnd(f)
+        si = sf = None
+        if variant in (_cabi.VARIANT_AUTO, _cabi.VARIANT_SLAB):      # per-batch slabs of the one-round-trip prologue
+            si, sf = _cabi.build_hop_slabs(csr.as_dict(), a_edge, ag.view(1, b, h), 1, h, n)
+            sf = sf[0]
+        us = _bracketed(lambda: _cabi.gat_hop(x_l, x_l[:, h * f:h * f + 2 * h], a_edge, csr.as_dict(), h, f, o, lde=32,
+                                              graph_bias=gb, a_graph=ag, h_prev=hprev, bias=bias, ep_scale=sc, ep_shift=sh,
+                                              epilogue=_cabi.EPI_AFFINE_RELU, variant=variant, slab_idx=si, slab_f=sf,
+                                              **csr.hints()), flush)
+        add(name, "gvqa_gat_hop_f32", us, hop_bytes(n, e, h, f), "B=%d, %d nodes/%d edges, F=%d, H=%d" % (b, n_, e_, f, h))
+    hop("gat_hop_f300", 256, 30, 60, 300)
+    hop("gat_hop_cfg4_per_gpu", 128, 200, 800, 512)
+    e, n, batch, csr = graphs(256, 30, 60)
+    ln, x = LayerNorm(512).to(dev).eval(), rnd(n, 512)
+    with torch.no_grad():
+        add("graph_layernorm_cfg2", "gvqa_graph_layernorm_f32", _bracketed(lambda: ln(x, batch, num_graphs=256, csr=csr), flush),
+            8 * n * 512 + 4 * n, "N=%d, F=512" % n)
+    h_, ea, ins, z = rnd(n, 512), rnd(e, 512), rnd(256, 512), torch.empty(n, 1024, device=dev)
+    add("gine_cfg3", "gvqa_gine_aggregate_f32", _bracketed(lambda: _cabi.gine_aggregate(h_, ea, ins, csr.as_dict(), 0.0, out=z), flush),
+        4 * (n * 512 + e * 512 + 256 * 512 + n * 1024) + 4 * (n + 1 + e), "cfg3: B=256, 30/60, F=512, D=512")
+    xw, gt, bias, oc = rnd(n, 512), rnd(256, 512), rnd(512), torch.empty(n, 512, device=dev)
+    dinv = _cabi.gcn_degree(csr.as_dict(), n, dev)
+    add("gcn_cfg2", "gvqa_gcn_aggregate_f32", _bracketed(lambda: _cabi.gcn_aggregate(xw, gt, dinv, bias, csr.as_dict(), out=oc), flush),
+        4 * (2 * n * 512 + e) + 4 * (n + 1 + e), "B=256, 30/60, C=512")
+    e5, n5, _, csr5 = graphs(128, 30, 60)
+    proj, pc, cc, b5, o5 = rnd(n5, 1536), rnd(128, 512), rnd(128, 512), rnd(512), torch.empty(n5, 512, device=dev)
+    add("lcgn_cfg5_per_gpu", "gvqa_lcgn_hop_f32",
+        _bracketed(lambda: _cabi.lcgn_hop(proj[:, :512], proj[:, 512:1024], proj[:, 1024:], pc, cc, b5, csr5.as_dict(), 0.2, out=o5), flush),
+        4 * (4 * n5 * 512 + 2 * 128 * 512) + 4 * (n5 + 1 + e5), "cfg5 per GPU: B=128, 30/60, C=512")
+    return out
+
+
+def collate_throughput(cfg, reps=10):
+    """Loader side: per-graph tensors -> int32 wire batch with the destination-CSR built on
+    the host, one core."""
+    from graphvqa_b200.collate import WireCollator
+    tok = make_token_inputs(cfg, seed=99)
+    graphs = [tuple(t.to(torch.int32) for t in g) for g in per_graph_tensors(tok, cfg)]
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        c = WireCollator(depth=2)
+        for _ in range(2):
+            c(graphs)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            w = c(graphs)
+        dt = (time.perf_counter() - t0) / reps
+    finally:
+        torch.set_num_threads(threads)
+    return {"graphs_per_s_per_core": cfg["graphs"] / dt, "ms_per_batch": dt * 1e3, "batch_graphs": cfg["graphs"],
+            "what": "collate.WireCollator: concatenation + int32 narrowing + gvqa_build_csr_host into a pinned arena "
+                    "(per-graph tensors in, as a dataset __getitem__ yields them)",
+            "wire_bytes": sum(t.numel() * t.element_size() for t in (w.x, w.edge_index, w.edge_attr, w.edge_sign))
+            + sum(t.numel() * t.element_size() for t in w.csr_host.values())}
+
+
+def cfg4_sharded(args, dev, rank, world, steps):
+    """BASELINE cfg4 on `world` GPUs: B=1024 graphs x 200 nodes / 800 edges, F=512, sharded by contiguous graph
+    range (dist.shard_scene_graphs), per rank scene-graph encoder -> 5-hop gat_seq -> pooling -> logit_fc, then ONE
+    all_gather_into_tensor of the [B/G, 1842] logits -- inside the timed region.  Rank 0 afterwards runs the whole
+    batch alone: shard_parity_max_abs = max |gathered - single-GPU| (the sharded == single-GPU invariant)."""
+    import torch.distributed as dist
+    from graphvqa_b200 import dist as gdist
+    from graphvqa_b200.graph_batch import SceneGraphBatch
+    from graphvqa_b200.pipeline_model_gat import PipelineModel, VocabSpec
+    cfg = dict(name="cfg4", graphs=1024, nodes=200, edges=800, feat=512, ins=512, heads=4, hops=5)
+    b = cfg["graphs"]
+    tok = make_token_inputs(cfg, seed=4321)                       # the same batch on every rank (same seed)
+    full = SceneGraphBatch(x=tok["x"], edge_index=tok["edge_index"], edge_attr=tok["edge_attr"], batch=tok["batch"],
+                           added_sym_edge=tok["added_sym_edge"], num_graphs=b, max_nodes_per_graph=tok["max_nodes"],
+                           max_in_edges_per_graph=tok["max_edges"])
+    torch.manual_seed(0)
+    model = PipelineModel(VocabSpec(text_vocab_size=64, sg_vocab_size=SG_VOCAB), sg_emb_dim=cfg["feat"]).eval()
+    randomise_bn(model.gat_seq, 7)
+    model = model.to(dev)
+    model.gat_seq.kernel_variant = args.variant
+    model.strict_range = False
+    lo, hi = gdist.graph_range(b, rank, world)
+    shard = gdist.shard_scene_graphs(full, rank, world, num_graphs=b).to(device=dev)
+    ins = tok["instr_vectors"][:, lo:hi].contiguous().to(dev)
+    q_enc = tok["q0"][lo:hi].contiguous().to(dev).unsqueeze(0)
+
+    def step():
+        local = model.graph_side(shard, ins, q_enc, hi - lo)
+        return gdist.all_gather_logits(local, b)
+    with torch.no_grad():
+        for _ in range(3):
+            gathered = step()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            gathered = step()
+        e1.record(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t) / steps
+        model.gat_seq.check_overflow()
+        parity = None
+        if rank == 0:
+            single = model.graph_side(full.to(device=dev), tok["instr_vectors"].to(dev), tok["q0"].to(dev).unsqueeze(0), b)
+            parity = float((gathered - single).abs().max())
+        dist.barrier()
+    return {"workload": "cfg4: 1024 synthetic scene graphs (200 nodes/800 edges), F=512, sharded over %d GPUs by "
+                        "contiguous graph range; token ids -> scene-graph encoder -> 5-hop gat_seq -> attention pooling "
+                        "-> logit_fc per rank" % world,
+            "value": b / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "graphs_per_gpu": hi - lo,
+            "collective": "all_gather_into_tensor[B/G=%d,1842] fp32 (NCCL), inside the timed region" % (hi - lo),
+            "added_sym_edge_entries": int(tok["added_sym_edge"].numel()),
+            "shard_parity_max_abs": parity, "shard_parity_bar": 2e-5, "launch": "eager (no CUDA graph)"}
 
 
 def run_engine(args, rank, local_rank, world):
@@ -327,31 +545,77 @@ def run_engine(args, rank, local_rank, world):
             except Exception:                              # external events unsupported: keep the other two views
                 model.hop_events = None
 
-        # ---------------- end to end: pinned host buffers -> H2D -> hot path -> D2H --------------
+        # ---------------- end to end (1): the operator boundary, pre-encoded fp32 features over PCIe ---------
         # through the public host-buffer API (graphvqa_b200.host_api.GatSeqHostRunner): copies of
         # neighbouring batches overlap the kernels of the current one (3 streams, 3 device slots).
-        from graphvqa_b200.host_api import GatSeqHostRunner
+        from graphvqa_b200.host_api import GatSeqHostRunner, GraphSideHostRunner
+
+        def pipelined(runner, submit_args, steps, read):
+            for i in range(6):
+                runner.submit(*submit_args(i))
+            runner.drain()
+            torch.cuda.synchronize(); barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(runner.s_h2d)
+            checksum = 0.0
+            for i in range(steps):
+                t_id = runner.submit(*submit_args(i))
+                if i >= 2:
+                    checksum += read(runner.result(t_id - 2))   # consume results as they arrive (slot i-2 is reused
+                                                                # by batch i+1, so it is read before then)
+            runner.drain()
+            e1.record(runner.s_d2h)
+            torch.cuda.synchronize()
+            t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            return b * world / (float(t2) / steps / 1e3)
+
         runner = GatSeqHostRunner(model, dev, depth=3, use_cuda_graph=not args.no_graph,
                                   max_nodes_per_graph=max_nodes, max_in_edges_per_graph=max_edges)
-        for i in range(6):
-            runner.submit(pinned[i % R])
-        runner.drain()
-        torch.cuda.synchronize(); barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(runner.s_h2d)
-        checksum = 0.0
-        for i in range(args.steps):
-            t_id = runner.submit(pinned[i % R])
-            if i >= 2:
-                checksum += float(runner.result(t_id - 2)[0, 0])    # consume results as they arrive (slot i-2 is
-                                                                    # reused by batch i+1, so it is read before then)
-        runner.drain()
-        e1.record(runner.s_d2h)
-        torch.cuda.synchronize()
-        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_value = b * world / (float(t2) / args.steps / 1e3)
+        e2e_operator = pipelined(runner, lambda i: (pinned[i % R],), args.steps, lambda t: float(t[0, 0]))
+        del runner
+
+        # ---------------- end to end (2, the headline): the reference's own boundary -----------------------
+        # token ids in, answer logits out (mainExplain_gat.py:710-714, 758-765): a wire-format batch from the
+        # loader-side collator (int32 tokens + host-built destination-CSR) plus the text side's instruction vectors
+        # and question summary go up; scene-graph encoder -> 5-hop gat_seq -> attention pooling -> logit_fc run as
+        # ONE CUDA graph per slot; short_answer_logits [B,1842] come back.
+        from graphvqa_b200.collate import WireCollator
+        from graphvqa_b200.pipeline_model_gat import PipelineModel, VocabSpec
+        torch.manual_seed(0)
+        pm = PipelineModel(VocabSpec(text_vocab_size=64, sg_vocab_size=SG_VOCAB), sg_emb_dim=cfg["feat"]).eval()
+        pm.gat_seq.load_state_dict(model.state_dict())           # the SAME hop stack as the resident measurement
+        pm = pm.to(dev)
+        pm.gat_seq.kernel_variant, pm.gat_seq.projection = args.variant, args.projection
+        collator = WireCollator(depth=R + 1)
+        wires, text = [], []
+        for r in range(R):
+            tok = make_token_inputs(cfg, seed=1234 + 10 * (rank * R + r))
+            wires.append(collator(per_graph_tensors(tok, cfg)))
+            text.append((tok["instr_vectors"].pin_memory(), tok["q0"].pin_memory()))
+        gs_runner = GraphSideHostRunner(pm, dev, depth=3, use_cuda_graph=not args.no_graph)
+        gs_bytes = GraphSideHostRunner.bytes_per_batch(wires[0], *text[0])
+        e2e_value = pipelined(gs_runner, lambda i: (wires[i % R], text[i % R][0], text[i % R][1]), args.steps,
+                              lambda t: float(t[0, 0]))
+        # the same graph side with everything resident (CUDA-graph replay of slot 0), for the compute share of e2e
+        gph0 = gs_runner.slots[0].graph
+        graph_side_ms = None
+        if gph0 is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(args.steps):
+                gph0.replay()
+            ev1.record(); torch.cuda.synchronize()
+            graph_side_ms = ev0.elapsed_time(ev1) / args.steps
+        pm.gat_seq.check_overflow()
+        del gs_runner
+
+        # ---------------- the other kernels of the path, the loader side, the sharded large-graph config --------
+        variants = variant_rooflines(dev, peak, args.variant) if (rank == 0 and not args.skip_variants) else None
+        sharded = cfg4_sharded(args, dev, rank, world, steps=max(3, min(args.steps, 10))) if (world > 1 and not args.skip_cfg4) else None
+        collate = collate_throughput(cfg) if rank == 0 else None
 
     model.check_overflow()      # the fp16-split projection's range flag: the timed path computed valid results
     if rank != 0:
@@ -365,19 +629,30 @@ def run_engine(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: %d synthetic GQA-shape scene graphs per GPU (30 nodes/60 edges), F=512, "
-                               "D=512, 4 heads, 5-hop GAT-skip (gat_seq.forward: CSR build + edge-logit pre-pass + "
-                               "5 x (fp32-accurate tcgen05 projection + fused hop))" % b,
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "step": "gat_seq.forward = CSR build + edge-logit pre-pass + 5 x (fp32-accurate tcgen05 projection + "
+                           "fused hop)",
+                   "hop_kernel_variant": args.variant,
                    "graphs_per_gpu": b, "parallelism": "graph-sharded x%d, no data-path collective" % world,
                    "l2_hygiene": "4 distinct input sets (~200 MB > 126 MB L2) rotated step to step",
                    "cuda_graph": graphs is not None},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": n * c * 4},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": gs_bytes, "d2h_bytes_per_step": b * 1842 * 4,
+                "boundary": "graphvqa_b200.host_api.GraphSideHostRunner: int32 token ids + host-built CSR + the text "
+                            "side's instr_vectors / question summary in pinned host memory -> scene-graph encoder -> "
+                            "5-hop gat_seq -> attention pooling -> logit_fc -> short_answer_logits[B,1842] in pinned "
+                            "host memory; one CUDA graph per slot, 3 slots, 3 streams",
+                "graph_side_resident_ms": graph_side_ms,
+                "note": "does MORE work per question than `value` (encoder, pooling and answer head on top of the hop "
+                        "stack); the reference arm's `graph_side` object times the same work on the host cores"},
+        "e2e_operator": {"value": e2e_operator, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": n * c * 4,
+                         "boundary": "graphvqa_b200.host_api.GatSeqHostRunner: the five gat_seq.forward tensors "
+                                     "(pre-encoded fp32 features) up, node states down; PCIe-bound"},
         # per step: 5 CSR kernels + hops x (projection GEMM + fused hop); the edge-logit and instruction pre-pass
         # products ride in hop 0's projection launch (grouped) or cost two launches of their own
-        "gpu_launches": args.steps * (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops),
+        "gpu_launches": args.steps * (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
+                                      + (1 if model.use_slabs and args.variant in (0, 5) else 0)),
         "roofline": {"bound": "hbm", "kernel": "gat_hop_block_kernel (gvqa_gat_hop_f32)",
                      "achieved": primary_achieved, "peak": peak, "unit": "GB/s", "frac": primary_achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
@@ -410,6 +685,12 @@ def run_engine(args, rank, local_rank, world):
             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "nominal"}
     if base is not None:
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if variants is not None:
+        line["roofline_variants"] = variants
+    if collate is not None:
+        line["collate"] = collate
+    if sharded is not None:
+        line["extra"] = {"cfg4_sharded": sharded}
     print(json.dumps(line), flush=True)
 
 
@@ -421,7 +702,11 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", type=int, default=0, help="fused-hop kernel: 0 auto, 1 gather, 2 staged, 3 block")
+    ap.add_argument("--skip-variants", action="store_true", help="skip the roofline_variants object")
+    ap.add_argument("--skip-cfg4", action="store_true", help="N > 1: skip the sharded cfg4 run with the logits all-gather")
+    ap.add_argument("--variant", type=int, default=0,
+                    help="fused-hop kernel: 0 auto (slab), 1 gather, 2 staged, 3 block, 4 persistent warp-specialised, "
+                         "5 block with the one-round-trip slab prologue")
     ap.add_argument("--projection", default="3xf16", choices=["3xf16", "3xtf32", "cublas"])
     ap.add_argument("--gemm-flags", type=int, default=0, help="debug flags of the projection GEMM (experiments)")
     ap.add_argument("--l2-persist", type=int, default=0, help="MiB of L2 set aside to keep x_l resident (0 = off)")

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
 ABI_VERSION = 4
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU, EPI_GRAPH_LN = 0, 1, 2, 3
-VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK, VARIANT_WS = 0, 1, 2, 3, 4
+VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK, VARIANT_WS, VARIANT_SLAB = 0, 1, 2, 3, 4, 5
 HOP_INPUTS_OLDER_THAN_PREDECESSOR = 1
 
 _c_i32, _c_i64, _c_f32, _c_vp, _c_sz = (ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
@@ -34,8 +34,14 @@ class GatHopArgs(ctypes.Structure):
         ("heads", _c_i32), ("channels", _c_i32), ("negative_slope", _c_f32), ("epilogue", _c_i32),
         ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
         ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64), ("flags", _c_i32), ("ln_eps", _c_f32),
-        ("ln_weight", _c_vp), ("ln_bias", _c_vp), ("sched", _c_vp),
+        ("ln_weight", _c_vp), ("ln_bias", _c_vp), ("slab_idx", _c_vp), ("slab_f", _c_vp), ("sched", _c_vp),
     ]
+
+
+class GatSlabPlan(ctypes.Structure):
+    """Mirror of ``struct gvqa_gat_slab_plan``."""
+    _fields_ = [("nodes_per_cta", _c_i32), ("edge_capacity", _c_i32), ("num_ctas", _c_i32), ("idx_words", _c_i64),
+                ("f_words_per_hop", _c_i64)]
 
 
 class GemmProblem(ctypes.Structure):
@@ -61,6 +67,9 @@ SIGNATURES = {
     "gvqa_skinny_matmul_f32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, ctypes.c_int,
                                               ctypes.c_int, _c_vp]),
     "gvqa_gat_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatHopArgs), _c_vp]),
+    "gvqa_gat_hop_slab_plan": (ctypes.c_int, [_c_i64, _c_i64, _c_i32, ctypes.POINTER(GatSlabPlan)]),
+    "gvqa_gat_hop_build_slabs_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
+                                                    _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
     "gvqa_debug_set_gemm_trace": (None, [_c_vp]),
@@ -197,7 +206,7 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
             a_graph=None, h_prev=None, bias=None, ep_scale=None, ep_shift=None, alpha_out=None,
             negative_slope=0.2, epilogue=EPI_NONE, num_graphs=None, max_nodes_per_graph=0,
             max_in_edges_per_graph=0, variant=VARIANT_AUTO, inputs_older_than_predecessor=False,
-            ln_weight=None, ln_bias=None, ln_eps=1e-5, sched=None):
+            ln_weight=None, ln_bias=None, ln_eps=1e-5, sched=None, slab_idx=None, slab_f=None):
     require_cuda(x_l, a_node, a_edge, h_out, graph_bias, a_graph, h_prev, bias, ep_scale, ep_shift, alpha_out,
                  ln_weight, ln_bias, sched)
     if variant == VARIANT_WS and sched is None:
@@ -226,9 +235,32 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.ld_a_graph = a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else 0
     a.flags = HOP_INPUTS_OLDER_THAN_PREDECESSOR if inputs_older_than_predecessor else 0
     a.ln_eps, a.ln_weight, a.ln_bias, a.sched = ln_eps, ptr(ln_weight), ptr(ln_bias), ptr(sched)
+    a.slab_idx, a.slab_f = ptr(slab_idx), ptr(slab_f)
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
     return h_out
+
+
+def build_hop_slabs(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
+    """Per-batch slabs of the one-round-trip hop prologue (hop variant 5).  ``a_edge_all`` [E, >= hops*H] (hop j at
+    columns j*H..), ``a_graph_all`` None or a [hops, B, H] view with unit column stride (row / hop strides free).
+    Returns (slab_idx int32, slab_f float32 [hops, f_words_per_hop])."""
+    require_cuda(a_edge_all, a_graph_all)
+    e = csr["num_edges"]
+    plan = GatSlabPlan()
+    check(lib().gvqa_gat_hop_slab_plan(num_nodes, e, heads, ctypes.byref(plan)), "gvqa_gat_hop_slab_plan")
+    dev = a_edge_all.device
+    slab_idx = torch.empty(plan.idx_words, dtype=torch.int32, device=dev)
+    slab_f = torch.empty(hops, plan.f_words_per_hop, dtype=torch.float32, device=dev)
+    if a_graph_all is not None and (a_graph_all.dim() != 3 or a_graph_all.stride(2) != 1 or a_graph_all.dtype != torch.float32):
+        raise ValueError("build_hop_slabs: a_graph_all must be a float32 [hops, B, H] view with unit column stride")
+    with torch.cuda.device(dev):
+        check(lib().gvqa_gat_hop_build_slabs_f32(
+            ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"]), ptr(csr["node_graph"]), ptr(a_edge_all),
+            a_edge_all.stride(0), ptr(a_graph_all), 0 if a_graph_all is None else a_graph_all.stride(1),
+            0 if a_graph_all is None else a_graph_all.stride(0), hops, num_nodes, e, heads, ptr(slab_idx), ptr(slab_f),
+            stream_handle(dev)), "gvqa_gat_hop_build_slabs_f32")
+    return slab_idx, slab_f
 
 
 _hop_sched = {}

@@ -139,3 +139,88 @@ def collate_scene_graphs(scene_graphs, vocab, pin_memory=True):
             if t is not None:
                 setattr(out, name, t.pin_memory())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Wire format: what a loader worker hands to the GPU process.
+# ------------------------------------------------------------------------------------------------------------
+class _PinnedArena:
+    """Reusable pinned host buffers, one per field, grown geometrically (cudaHostAlloc costs ~100 us per call)."""
+
+    def __init__(self, pin):
+        self.pin, self.bufs = pin, {}
+
+    def get(self, name, count, dtype):
+        t = self.bufs.get(name)
+        if t is None or t.numel() < count or t.dtype != dtype:
+            t = torch.empty(max(int(count * 1.25), 16), dtype=dtype)
+            if self.pin:
+                t = t.pin_memory()
+            self.bufs[name] = t
+        return t[:count]
+
+
+class WireCollator:
+    """Batches per-graph tensors into the engine's wire format: int32 everywhere, ONE pinned arena per in-flight
+    batch, the destination-CSR built on the host (``gvqa_build_csr_host``) -- the GPU then runs no CSR kernel and
+    receives ~1/3 of the bytes of the reference's int64 COO (torch_geometric ``Batch.from_data_list``,
+    gqa_dataset_entry.py:631-675).  Vectorised: concatenations and two ``repeat_interleave`` calls, no per-edge
+    Python.  ``depth`` arenas are used round-robin (a batch stays valid until ``depth`` more have been collated).
+
+    ``graphs``: list of ``(x [n,12], edge_index [2,e], edge_attr [e,1], added_sym_edge [k])`` integer tensors, i.e.
+    what ``convert_scene_graph`` (or the reference's ``convert_one_gqa_scene_graph``) yields per sample."""
+
+    def __init__(self, depth=4, pin_memory=True):
+        pin = bool(pin_memory) and torch.cuda.is_available()
+        self.arenas = [_PinnedArena(pin) for _ in range(depth)]
+        self.count = 0
+
+    def __call__(self, graphs):
+        from . import _cabi
+        if not graphs:
+            raise ValueError("WireCollator: empty list")
+        arena = self.arenas[self.count % len(self.arenas)]
+        self.count += 1
+        b = len(graphs)
+        n_per = torch.tensor([g[0].size(0) for g in graphs], dtype=torch.int64)
+        e_per = torch.tensor([g[1].size(1) for g in graphs], dtype=torch.int64)
+        n, e = int(n_per.sum()), int(e_per.sum())
+        i32 = torch.int32
+        def cat_into(name, tensors, shape, dim=0):
+            """concatenate (one call) and narrow to int32 (one pass) into the arena"""
+            dst = arena.get(name, n * MAX_OBJ_TOKEN_LEN if name == "x" else (2 * e if name == "edge_index" else e), i32)
+            dst = dst.view(shape)
+            if tensors[0].dtype == i32:
+                torch.cat(tensors, dim=dim, out=dst)
+            else:
+                dst.copy_(torch.cat(tensors, dim=dim))
+            return dst
+        x = cat_into("x", [g[0] for g in graphs], (n, MAX_OBJ_TOKEN_LEN))
+        ei = cat_into("edge_index", [g[1] for g in graphs], (2, e), dim=1)
+        node_off = (n_per.cumsum(0) - n_per).to(i32)
+        ei += torch.repeat_interleave(node_off, e_per, output_size=e)     # node offsets on edge_index only
+        ea = cat_into("edge_attr", [g[2].view(-1) for g in graphs], (e,)).view(e, 1)
+        batch = arena.get("batch", n, i32)
+        batch.copy_(torch.repeat_interleave(torch.arange(b, dtype=i32), n_per, output_size=n))
+        # the reference applies the graph-local, un-offset added_sym_edge indices to the BATCHED edge rows
+        sym = torch.cat([g[3].reshape(-1) for g in graphs]).to(torch.int64)
+        sign = arena.get("edge_sign", e, torch.float32)
+        sign.fill_(1.0)
+        if sym.numel():
+            sign[sym[(sym >= 0) & (sym < e)]] = -1.0
+        parts = dict(rowptr=arena.get("rowptr", n + 1, i32), col_src=arena.get("col_src", max(e, 1), i32),
+                     perm=arena.get("perm", max(e, 1), i32), graph_ptr=arena.get("graph_ptr", b + 1, i32),
+                     node_graph=arena.get("node_graph", max(n, 1), i32), stats=arena.get("stats", 8, i32))
+        _cabi.check(_cabi.lib().gvqa_build_csr_host(
+            ei.data_ptr(), 4, e, batch.data_ptr(), 4, n, b, parts["rowptr"].data_ptr(), parts["col_src"].data_ptr(),
+            parts["perm"].data_ptr(), parts["graph_ptr"].data_ptr(), parts["node_graph"].data_ptr(),
+            parts["stats"].data_ptr()), "gvqa_build_csr_host")
+        return SceneGraphBatch(x=x, edge_index=ei, edge_attr=ea, batch=batch, added_sym_edge=sym.to(i32), edge_sign=sign,
+                               num_graphs=b, max_nodes_per_graph=int(parts["stats"][0]),
+                               max_in_edges_per_graph=int(parts["stats"][1]), csr_host=parts)
+
+
+def collate_wire(scene_graphs, vocab, collator=None):
+    """Raw GQA scene graphs -> wire-format ``SceneGraphBatch`` (conversion per graph + ``WireCollator``)."""
+    collator = collator or WireCollator(depth=1)
+    return collator([convert_scene_graph(sg, vocab) for sg in scene_graphs])

@@ -63,6 +63,9 @@ struct HopParams {
   int32_t epilogue;
   int32_t early;   // GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR: topology / a_edge / a_graph may be read before pdl_wait()
   int32_t prefetch;   // GVQA_HOP_PREFETCH (experiments): 1 = the CTA's h_prev rows are pulled into L2 during the index prologue
+  const int32_t* slab_idx;   // variant 5 (slab kernel): per-CTA index slabs / this hop's logit-term slabs
+  const float* slab_f;
+  int32_t win;               // rows of a_node staged either side of the CTA's node range (max nodes per graph)
   int32_t* sched;     // variant 4: {next chunk, finished CTAs}, zero before the first launch, self-resetting
   const float* ln_weight;   // GVQA_EPI_GRAPH_LN: one float each (or NULL), my_graph_layernorm.py:40-41
   const float* ln_bias;
@@ -437,6 +440,69 @@ __device__ __forceinline__ void stream_node(const HopParams& p, int i, int lane,
   }
 }
 
+// 128-bit read-only load (L1-allocating like __ldg) that the compiler must issue where it stands: used to start the
+// first node's row traffic BEFORE the softmax phase, so that the phase hides behind the memory latency.
+__device__ __forceinline__ float4 ldg_issue_now(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// stream_node for a node whose skip row, graph term and FIRST in-edge's source rows were requested earlier
+// (`pre[h][j]`): same accumulation order as stream_node (edge r0 first, heads in order), so the results are identical.
+template <int J, int H, int HP, typename Sink>
+__device__ __forceinline__ void stream_node_pre(const HopParams& p, int i, int lane, int C4, const int32_t* src_s,
+                                                const float* alpha_s, int r0, int r1, int gid, const float4 (&pre)[HP][J],
+                                                int epilogue, Sink&& sink) {
+  float4 acc[J], skip[J], gb[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    skip[j] = acc[j];
+    gb[j] = acc[j];
+    const int c4 = lane + 32 * j;
+    if (c4 < C4) {
+      if (p.h_prev) skip[j] = ldg_stream(p.h_prev + (int64_t)i * p.C + 4 * c4);
+      if (p.graph_bias && r1 > r0) gb[j] = ldg_cached(p.graph_bias + (int64_t)gid * p.ldgb + 4 * c4);
+    }
+  }
+  if (r1 > r0) {
+    const float* row = p.x_l + (int64_t)src_s[r0] * p.ldx;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float a = alpha_s[r0 * H + h];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < C4) {
+          if (h < HP) fma4(acc[j], a, pre[h < HP ? h : 0][j]);
+          else fma4(acc[j], a, ldg_cached(row + h * p.C + 4 * c4));
+        }
+      }
+    }
+  }
+#pragma unroll 2
+  for (int k = r0 + 1; k < r1; ++k) {
+    const float* row = p.x_l + (int64_t)src_s[k] * p.ldx;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float a = alpha_s[k * H + h];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < C4) fma4(acc[j], a, ldg_cached(row + h * p.C + 4 * c4));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < C4)
+      sink(c4, epilogue_value4(p, c4, acc[j], 1.0f / H, p.graph_bias != nullptr && r1 > r0, gb[j], p.h_prev != nullptr,
+                               skip[j], epilogue));
+  }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -445,14 +511,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Kernel 4: persistent warp-specialised hop.  Warp 0 = producer (claims chunks, index round trips,
 // softmax into a ring slot), warps 1..4 = consumers (weighted gather + epilogue).
 // ------------------------------------------------------------------------------------------
-constexpr int kWsConsumers = 4;
-constexpr int kWsThreads = 32 * (kWsConsumers + 1);
 constexpr int kWsSlots = 3;
 constexpr int kWsEdgeCap = 128;   // in-edges of one chunk staged in a slot; larger chunks take the per-warp path
 
 template <int H>
 struct WsGeom {
-  static constexpr int kChunk = H >= 8 ? 4 : 8;   // kChunk * H <= 32: one producer lane per (node, head)
+  // kChunk * H <= 32 (one producer lane per (node, head)); one consumer warp per node of a chunk, so a chunk is ONE
+  // round of the consumers; 7 + 1 warps = 256 threads leave 128 registers per thread at two CTAs per SM
+  static constexpr int kChunk = H >= 8 ? 3 : 7;
+  static constexpr int kConsumers = kChunk;
+  static constexpr int kThreads = 32 * (kConsumers + 1);
 };
 
 template <int H>
@@ -465,8 +533,9 @@ struct __align__(16) WsSlot {
 };
 
 template <int J, int H>
-__global__ void __launch_bounds__(kWsThreads, 3) gat_hop_ws_kernel(const HopParams p, const int nchunks) {
+__global__ void __launch_bounds__(WsGeom<H>::kThreads, H >= 8 ? 4 : 2) gat_hop_ws_kernel(const HopParams p, const int nchunks) {
   constexpr int kChunk = WsGeom<H>::kChunk;
+  constexpr int kWsConsumers = WsGeom<H>::kConsumers;
   __shared__ WsSlot<H> slots[kWsSlots];
   __shared__ __align__(8) uint64_t full_bar[kWsSlots], empty_bar[kWsSlots];
   __shared__ float gather_alpha[kWsConsumers][kEdgeChunk * H];   // scratch of the oversize-chunk path
@@ -493,12 +562,14 @@ __global__ void __launch_bounds__(kWsThreads, 3) gat_hop_ws_kernel(const HopPara
   if (wid == 0) {
     // ---------------- producer ----------------
     const int node = lane / H, head = lane - node * H;
+    // chunk claims: the first is static (blockIdx.x: no round trip before the first index load), every later one is
+    // requested one iteration ahead, so the atomic's latency hides behind the preparation of the current chunk
+    int c = blockIdx.x, c_next = 0;
 #pragma unroll 1
     for (int it = 0;; ++it) {
       const int s = it % kWsSlots;
-      int c = 0;
-      if (lane == 0) c = atomicAdd(p.sched, 1);
-      c = __shfl_sync(kFull, c, 0);
+      if (it > 0) c = __shfl_sync(kFull, c_next, 0);
+      if (lane == 0 && c < nchunks) c_next = (int)gridDim.x + atomicAdd(p.sched, 1);
       mbar_wait(&empty_bar[s], (uint32_t)(((it / kWsSlots) & 1) ^ 1));     // consumers have left the slot
       WsSlot<H>& sl = slots[s];
       if (c >= nchunks) {
@@ -718,6 +789,197 @@ __global__ void __launch_bounds__(kLnHopThreads) gat_hop_graphln_kernel(const Ho
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Kernel 6: block-phase gather with a ONE-round-trip prologue ("slab" kernel).
+//
+// The block kernel's prologue is three dependent trips (row pointers -> sources / edge ids -> logit terms) during
+// which no bulk traffic flows (3.6 us of a ~20 us kernel at cfg2, profiles/r01/hop_timeline_block_kernel.txt).
+// Everything in it except a_node is hop-invariant per batch, and the CTA partition depends on N only.  So a
+// per-batch pass (gat_slab_build_kernel, beside the CSR build) writes, per hop CTA, a fixed-stride slab
+//     idx  : { eC | -1, eA, rp_rel[npc+1], gid[npc], src[cap], local target[cap] }       (int32, once per batch)
+//     f[j] : { a_graph[g(i), h] per node, a_edge_j[perm[k], h] per staged in-edge }       (fp32, per hop j)
+// whose address depends on blockIdx only: the hop CTA pulls both with two TMA bulk copies (cp.async.bulk +
+// mbarrier) while its threads load the a_node rows of a WINDOW of nodes around its own range (sources live in the
+// same graph, i.e. within max_nodes_per_graph rows) -- one trip.  Sources outside the window and CTAs whose in-edges
+// exceed the slab capacity fall back to global loads / the block kernel's path, so the hints stay hints.
+// ------------------------------------------------------------------------------------------
+struct SlabGeom {
+  int32_t npc, cap, grid, idx_stride, f_stride;    // strides in 4-byte words (multiples of 4 -> 16-byte aligned)
+};
+
+__host__ __device__ inline SlabGeom slab_geom(int64_t N, int64_t E, int H) {
+  SlabGeom g;
+  int npc = (int)((N + kNumSMs * 4 - 1) / (kNumSMs * 4));
+  g.npc = npc < 4 ? 4 : (npc > kBlkNodes ? kBlkNodes : npc);
+  const int64_t avg2 = N > 0 ? (2 * E * g.npc + N - 1) / N : 0;     // twice the mean in-edges of a CTA
+  int cap = (int)((avg2 + 31) / 32 * 32);
+  g.cap = cap < 32 ? 32 : (cap > kBlkEdgeCap ? kBlkEdgeCap : cap);
+  g.grid = (int)((N + g.npc - 1) / g.npc);
+  g.idx_stride = (2 + (g.npc + 1) + g.npc + 3) / 4 * 4 + 2 * g.cap;      // header | src[cap] | local target[cap]
+  g.f_stride = ((g.npc + g.cap) * H + 3) / 4 * 4;
+  return g;
+}
+
+template <int H>
+__global__ void __launch_bounds__(128) gat_slab_build_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ node_graph, const float* __restrict__ a_edge, int64_t lde,
+    const float* __restrict__ a_graph, int64_t ldag, int64_t hop_stride_ag, int hops, int N, SlabGeom g,
+    int32_t* __restrict__ slab_idx, float* __restrict__ slab_f) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int i0 = b * g.npc, nn = min(g.npc, N - i0);
+  int32_t* idx = slab_idx + (size_t)b * g.idx_stride;
+  const int hdr = g.idx_stride - 2 * g.cap;
+  const int eA = rowptr[i0], eC = rowptr[i0 + nn] - eA;
+  const bool fits = eC <= g.cap;
+  if (tid == 0) { idx[0] = fits ? eC : -1; idx[1] = eA; }
+  for (int t = tid; t <= g.npc; t += 128) idx[2 + t] = t <= nn ? rowptr[i0 + t] - eA : eC;
+  for (int t = tid; t < g.npc; t += 128) idx[2 + g.npc + 1 + t] = t < nn ? node_graph[i0 + t] : 0;
+  if (!fits) return;
+  for (int k = tid; k < g.cap; k += 128) idx[hdr + k] = k < eC ? col_src[eA + k] : 0;
+  for (int node = 0; node < nn; ++node)           // local target node of every staged in-edge
+    for (int k = rowptr[i0 + node] - eA + tid; k < rowptr[i0 + node + 1] - eA; k += 128) idx[hdr + g.cap + k] = node;
+  for (int j = 0; j < hops; ++j) {
+    float* f = slab_f + ((size_t)j * g.grid + b) * g.f_stride;
+    for (int t = tid; t < g.npc * H; t += 128) {
+      const int node = t / H, h = t - node * H;
+      f[t] = (a_graph != nullptr && node < nn) ? a_graph[(size_t)j * hop_stride_ag + (size_t)node_graph[i0 + node] * ldag + h] : 0.f;
+    }
+    for (int t = tid; t < g.cap * H; t += 128) {
+      const int k = t / H, h = t - k * H;
+      float v = 0.f;
+      if (k < eC) {
+        const int64_t e = perm ? perm[eA + k] : (eA + k);
+        v = a_edge[e * lde + (size_t)j * H + h];
+      }
+      f[g.npc * H + t] = v;
+    }
+  }
+}
+
+constexpr int kSlabWinRows = 512;      // a_node rows staged around the CTA's node range (2H floats each)
+
+template <int J, int H, int HP>
+__global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_slab_kernel(
+    const HopParams p, const SlabGeom g, const int32_t* __restrict__ slab_idx, const float* __restrict__ slab_f,
+    const int win) {
+  extern __shared__ __align__(128) unsigned char slab_smem[];
+  // layout: [idx: idx_stride ints][f: f_stride floats][a_node window: win_rows * 2H floats][mbarrier]
+  int32_t* idx_s = reinterpret_cast<int32_t*>(slab_smem);
+  float* f_s = reinterpret_cast<float*>(idx_s + g.idx_stride);
+  const int win_rows = g.npc + 2 * win;
+  float* an_s = f_s + g.f_stride;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(an_s + (size_t)win_rows * 2 * H);
+  __shared__ float gscratch[4][kEdgeChunk * H];     // per-warp scratch of the oversize path
+  __shared__ int32_t gsrc[4][kEdgeChunk];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int i0 = blockIdx.x * g.npc;
+  const int nn = min(g.npc, p.N - i0);
+  const int C4 = p.C >> 2;
+  GVQA_HOP_TRACE(0);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (tid == 0) {
+    const uint32_t bytes_i = (uint32_t)g.idx_stride * 4u, bytes_f = (uint32_t)g.f_stride * 4u;
+    mbar_expect_tx(bar, bytes_i + bytes_f);
+    bulk_g2s(idx_s, slab_idx + (size_t)blockIdx.x * g.idx_stride, bytes_i, bar);
+    bulk_g2s(f_s, slab_f + (size_t)blockIdx.x * g.f_stride, bytes_f, bar);
+  }
+  // the same trip: a_node rows of the window [w0, w1) (source logit terms a_l of every node a source can be, and the
+  // target terms a_r of the CTA's own nodes)
+  const int w0 = max(0, i0 - win), w1 = min(p.N, i0 + g.npc + win);
+  for (int t = tid; t < (w1 - w0) * H; t += kBlkThreads) {        // 2H floats per row = H float2 (8-byte aligned rows)
+    const int r = t / H, q = t - r * H;
+    reinterpret_cast<float2*>(an_s)[t] = __ldg(reinterpret_cast<const float2*>(p.a_node + (int64_t)(w0 + r) * p.lda) + q);
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+  GVQA_HOP_TRACE(1);
+  const int eC = idx_s[0];
+  if (eC < 0) {
+    // more in-edges than the slab holds: per-warp chunked path from global memory
+    for (int node = wid; node < nn; node += kBlkThreads / 32)
+      gather_node<J, H>(p, i0 + node, lane, 0, C4, gscratch[wid], gsrc[wid], true);
+    return;
+  }
+  const int32_t* rp_s = idx_s + 2;
+  const int32_t* gid_s = idx_s + 2 + g.npc + 1;
+  const int32_t* src_s = idx_s + (g.idx_stride - 2 * g.cap);
+  const int32_t* dst_s = src_s + g.cap;
+  float* alpha_s = f_s + g.npc * H;
+  // ---- the sources are known: request this warp's first node now (skip row, graph term, the source rows of its
+  // first in-edge); the logit / softmax phase below then runs under that memory latency instead of before it ----
+  // HP = heads of the first in-edge requested early (template parameter, chosen by launch_slab): limited by the
+  // 128-register budget -- a spill store of such a register would wait for its load right there and serialise the
+  // phase it is meant to hide
+  constexpr bool kPre = HP > 0;
+  float4 pre[kPre ? HP : 1][kPre ? J : 1];
+  const int node0 = wid;
+  const int r0_0 = node0 < nn ? rp_s[node0] : 0, r1_0 = node0 < nn ? rp_s[node0 + 1] : 0;
+  if constexpr (kPre) {
+    // unconditional loads from always-valid addresses (a node without in-edges or a lane beyond the row reads a
+    // row / column it ignores later): no zero-initialisation, so nothing has to wait for the data before its use
+    const int src0 = (node0 < nn && r1_0 > r0_0) ? src_s[r0_0] : i0;
+    const float* row = p.x_l + (int64_t)src0 * p.ldx;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c4 = min(lane + 32 * j, C4 - 1);
+#pragma unroll
+      for (int h = 0; h < HP; ++h) pre[h][j] = ldg_issue_now(row + h * p.C + 4 * c4);
+    }
+  }
+  // ---- logits: one thread per (in-edge, head), assembled from shared memory only ----
+  for (int t = tid; t < eC * H; t += kBlkThreads) {
+    const int k = t / H, h = t - k * H;
+    const int src = src_s[k], node = dst_s[k];
+    const float al = (src >= w0 && src < w1) ? an_s[(size_t)(src - w0) * 2 * H + h] : p.a_node[(int64_t)src * p.lda + h];
+    const float tg = f_s[node * H + h] + an_s[(size_t)(i0 + node - w0) * 2 * H + H + h];
+    alpha_s[t] = leaky_relu((alpha_s[t] + al) + tg, p.slope);
+  }
+  __syncthreads();
+  // ---- softmax: one thread per (node, head) over its few logits (PyG: exp(l - max) / (sum + 1e-16)) ----
+  if (tid < nn * H) {
+    const int node = tid / H, h = tid - node * H;
+    const int r0 = rp_s[node], r1 = rp_s[node + 1];
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int k = r0; k < r1; ++k) mx = fmaxf(mx, alpha_s[k * H + h]);
+    float sum = 0.f;
+#pragma unroll 4
+    for (int k = r0; k < r1; ++k) {
+      const float ex = expf(alpha_s[k * H + h] - mx);
+      alpha_s[k * H + h] = ex;
+      sum += ex;
+    }
+    const float inv = 1.0f / (sum + 1e-16f);
+#pragma unroll 4
+    for (int k = r0; k < r1; ++k) alpha_s[k * H + h] *= inv;      // column h of these rows is this thread's alone
+  }
+  __syncthreads();
+  GVQA_HOP_TRACE(3);
+  if constexpr (kPre) {
+    if (node0 < nn) {
+      const int i = i0 + node0;
+      stream_node_pre<J, H, kPre ? HP : 1>(p, i, lane, C4, src_s, alpha_s, r0_0, r1_0, gid_s[node0], pre, p.epilogue,
+                            [&](int c4, const float4& v) { stg_stream(p.h_out + (int64_t)i * p.C + 4 * c4, v); });
+    }
+  }
+#pragma unroll 1
+  for (int node = wid + (kPre ? kBlkThreads / 32 : 0); node < nn; node += kBlkThreads / 32) {
+    const int i = i0 + node;
+    stream_node<J, H>(p, i, lane, C4, src_s, alpha_s, rp_s[node], rp_s[node + 1], gid_s[node], p.epilogue,
+                      [&](int c4, const float4& v) { stg_stream(p.h_out + (int64_t)i * p.C + 4 * c4, v); });
+  }
+  if (p.trace && lane == 0 && wid < 4) p.trace[(size_t)blockIdx.x * 8 + 4 + wid] = gtime_ns();
+}
+
 template <int J, int H>
 static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
   if (variant == 1) {
@@ -738,6 +1000,7 @@ static int launch_flat(const HopParams& p, int variant, cudaStream_t stream) {
 
 template <int J, int H>
 static int launch_ws(const HopParams& p, cudaStream_t stream) {
+  constexpr int kWsThreads = WsGeom<H>::kThreads;
   static const int per_sm = [] {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gat_hop_ws_kernel<J, H>, kWsThreads, 0) != cudaSuccess || nb < 1) {
@@ -780,6 +1043,38 @@ static int launch_graphln(const HopParams& p, int max_nodes_hint, cudaStream_t s
   return GVQA_OK;
 }
 
+template <int J, int H>
+static int launch_slab(const HopParams& p, cudaStream_t stream) {
+  const SlabGeom g = slab_geom(p.N, p.E, H);
+  int win = p.win;
+  if (g.npc + 2 * win > kSlabWinRows) win = (kSlabWinRows - g.npc) / 2;   // farther sources: global loads
+  const size_t smem = (size_t)g.idx_stride * 4 + (size_t)g.f_stride * 4 + (size_t)(g.npc + 2 * win) * 2 * H * 4 + 16;
+  if (smem > 48 * 1024) return GVQA_ERR_UNSUPPORTED;
+  // early-issued heads: default = what fits the register budget without spills (measured, profiles/r02/); the
+  // GVQA_HOP_PRE environment variable overrides it for experiments (0, 1, 2 or H)
+  static const int env_pre = [] {
+    const char* e = getenv("GVQA_HOP_PRE");
+    return e ? atoi(e) : -1;
+  }();
+  constexpr int kDefault = (J * H <= 12) ? H : 0;
+  const int hp = env_pre < 0 ? kDefault : env_pre;
+  cudaError_t err;
+#define GVQA_SLAB_LAUNCH(HPV)                                                                                       \
+  err = launch_pdl(2, gat_hop_slab_kernel<J, H, HPV>, dim3((unsigned)g.grid), dim3(kBlkThreads), smem, stream, p, g, \
+                   p.slab_idx, p.slab_f, win)
+  if (hp >= H && J * H <= 16) GVQA_SLAB_LAUNCH(H);
+  else if (hp >= 2 && H >= 2 && J * 2 <= 16) GVQA_SLAB_LAUNCH((H >= 2 ? 2 : 1));
+  else if (hp >= 1 && J <= 8) GVQA_SLAB_LAUNCH(1);
+  else GVQA_SLAB_LAUNCH(0);
+#undef GVQA_SLAB_LAUNCH
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    return GVQA_ERR_CUDA;
+  }
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
 template <int H>
 static int dispatch_flat(const HopParams& p, int variant, cudaStream_t stream, int max_nodes_hint = 0) {
   const int jj = (p.C / 4 + 31) / 32;
@@ -791,6 +1086,17 @@ static int dispatch_flat(const HopParams& p, int variant, cudaStream_t stream, i
       case 4: return launch_graphln<4, H>(p, max_nodes_hint, stream);
       case 5: case 6: return launch_graphln<6, H>(p, max_nodes_hint, stream);
       case 7: case 8: return launch_graphln<8, H>(p, max_nodes_hint, stream);
+      default: return GVQA_ERR_UNSUPPORTED;
+    }
+  }
+  if (variant == 5) {
+    switch (jj) {
+      case 1: return launch_slab<1, H>(p, stream);
+      case 2: return launch_slab<2, H>(p, stream);
+      case 3: return launch_slab<3, H>(p, stream);
+      case 4: return launch_slab<4, H>(p, stream);
+      case 5: case 6: return launch_slab<6, H>(p, stream);
+      case 7: case 8: return launch_slab<8, H>(p, stream);
       default: return GVQA_ERR_UNSUPPORTED;
     }
   }
@@ -1092,7 +1398,9 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   if (a->epilogue == GVQA_EPI_GRAPH_LN && (!a->graph_ptr || a->num_graphs <= 0)) return GVQA_ERR_NULL_POINTER;
   if (a->variant == 4 && !a->sched) return GVQA_ERR_NULL_POINTER;
   if ((C & 3) || C > 1024 || !(H == 1 || H == 2 || H == 4 || H == 8)) return GVQA_ERR_UNSUPPORTED;
-  if (a->variant < 0 || a->variant > 4) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant < 0 || a->variant > 5) return GVQA_ERR_UNSUPPORTED;
+  if (a->variant == 5 && (!a->slab_idx || !a->slab_f)) return GVQA_ERR_NULL_POINTER;
+  if ((a->slab_idx && (reinterpret_cast<uintptr_t>(a->slab_idx) & 15)) || (a->slab_f && !aligned16(a->slab_f))) return GVQA_ERR_MISALIGNED;
   if ((a->ldx & 3) || (a->ld_graph_bias & 3) || !aligned16(a->x_l) || !aligned16(a->h_out) || (a->h_prev && !aligned16(a->h_prev)) ||
       (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
@@ -1116,6 +1424,7 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
   }();
   p.prefetch = env_prefetch;
   p.sched = a->sched; p.ln_weight = a->ln_weight; p.ln_bias = a->ln_bias; p.ln_eps = a->ln_eps;
+  p.slab_idx = a->slab_idx; p.slab_f = a->slab_f; p.win = a->max_nodes_per_graph > 0 ? a->max_nodes_per_graph : 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   if (a->variant == 2 && a->epilogue != GVQA_EPI_GRAPH_LN) {
@@ -1130,7 +1439,13 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
       case 8: return launch_staged<8>(p, plan, stream);
     }
   }
-  const int variant = a->variant == 1 ? 1 : (a->variant == 4 ? 4 : 3);
+  // auto: the slab kernel when the caller prepared slabs and does not ask for the attention weights (the slabs
+  // carry no edge ids), else the block kernel
+  int variant = a->variant == 1 ? 1 : (a->variant == 4 ? 4 : 3);
+  if ((a->variant == 0 || a->variant == 5) && a->slab_idx && a->slab_f && !a->alpha_out && (a->ld_a_node == 0 || (a->ld_a_node & 1) == 0))
+    variant = 5;
+  else if (a->variant == 5)
+    return GVQA_ERR_UNSUPPORTED;
   switch (H) {
     case 1: return dispatch_flat<1>(p, variant, stream, a->max_nodes_per_graph);
     case 2: return dispatch_flat<2>(p, variant, stream, a->max_nodes_per_graph);
@@ -1138,4 +1453,47 @@ extern "C" GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* a, void* strea
     case 8: return dispatch_flat<8>(p, variant, stream, a->max_nodes_per_graph);
   }
   return GVQA_ERR_UNSUPPORTED;
+}
+
+
+extern "C" GVQA_API int gvqa_gat_hop_slab_plan(int64_t num_nodes, int64_t num_edges, int32_t heads, gvqa_gat_slab_plan* plan) {
+  if (!plan) return GVQA_ERR_NULL_POINTER;
+  if (num_nodes <= 0 || num_edges < 0 || num_nodes >= (1ll << 31) || num_edges >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (!(heads == 1 || heads == 2 || heads == 4 || heads == 8)) return GVQA_ERR_UNSUPPORTED;
+  const gvqa::SlabGeom g = gvqa::slab_geom(num_nodes, num_edges, heads);
+  plan->nodes_per_cta = g.npc;
+  plan->edge_capacity = g.cap;
+  plan->num_ctas = g.grid;
+  plan->idx_words = (int64_t)g.grid * g.idx_stride;
+  plan->f_words_per_hop = (int64_t)g.grid * g.f_stride;
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_gat_hop_build_slabs_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
+                                                     const int32_t* node_graph, const float* a_edge, int64_t lde,
+                                                     const float* a_graph, int64_t ld_a_graph, int64_t hop_stride_a_graph,
+                                                     int32_t hops, int64_t num_nodes, int64_t num_edges, int32_t heads,
+                                                     int32_t* slab_idx, float* slab_f, void* stream_) {
+  using namespace gvqa;
+  if (num_nodes < 0 || num_edges < 0 || hops <= 0 || num_nodes >= (1ll << 31) || num_edges >= (1ll << 31)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0) return GVQA_OK;
+  if (!rowptr || !node_graph || !slab_idx || !slab_f || (num_edges > 0 && (!col_src || !a_edge))) return GVQA_ERR_NULL_POINTER;
+  if (lde < (int64_t)hops * heads || (a_graph && ld_a_graph < heads)) return GVQA_ERR_BAD_SHAPE;
+  if (!(heads == 1 || heads == 2 || heads == 4 || heads == 8)) return GVQA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(slab_idx) & 15) || !aligned16(slab_f)) return GVQA_ERR_MISALIGNED;
+  const SlabGeom g = slab_geom(num_nodes, num_edges, heads);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+#define GVQA_SLAB(HH)                                                                                                \
+  gat_slab_build_kernel<HH><<<(unsigned)g.grid, 128, 0, stream>>>(rowptr, col_src, perm, node_graph, a_edge, lde, a_graph, \
+                                                                  ld_a_graph, hop_stride_a_graph, hops, (int)num_nodes, g, \
+                                                                  slab_idx, slab_f)
+  switch (heads) {
+    case 1: GVQA_SLAB(1); break;
+    case 2: GVQA_SLAB(2); break;
+    case 4: GVQA_SLAB(4); break;
+    default: GVQA_SLAB(8); break;
+  }
+#undef GVQA_SLAB
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
 }

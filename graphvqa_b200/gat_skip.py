@@ -167,6 +167,9 @@ class gat_seq(nn.Module):
         self.dropout = dropout
         self.in_channels, self.edge_attr_dim, self.ins_dim = in_channels, edge_attr_dim, ins_dim
         self.kernel_variant = _cabi.VARIANT_AUTO
+        # per-batch slabs for the hop kernel's one-round-trip prologue (hop variant 5): built once per forward beside
+        # the pre-pass (one small launch), consumed by all hops when kernel_variant is AUTO or SLAB
+        self.use_slabs = os.environ.get("GVQA_HOP_SLABS", "1") != "0"
         # node projection h @ W_h^T, all with fp32-level accuracy:
         #   "3xf16"  hand-written tcgen05 GEMM on fp16-split operands (default; inputs must fit fp16's range,
         #            guarded by a device flag, see check_overflow)
@@ -271,6 +274,8 @@ class gat_seq(nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 csr = GraphCSR.build(edge_index, batch, b, **(csr_hints or {}))
+                csr_ready = torch.cuda.Event()
+                csr_ready.record(side)
             for t in (csr.rowptr, csr.col_src, csr.perm, csr.graph_ptr, csr.node_graph, csr.stats):
                 t.record_stream(cur)
         csr_d = csr.as_dict()
@@ -337,6 +342,28 @@ class gat_seq(nn.Module):
                 graph_bias_all = torch.bmm(ins, pk["w_ins"])                    # [hops, B, C]
                 a_graph_all = torch.bmm(ins, pk["v_graph"])                     # [hops, B, H]
 
+        # per-batch slabs of the one-round-trip hop prologue: built on the side stream, concurrently with hop 0 (which
+        # therefore still runs the block kernel) and the next projection; hops >= 1 consume them
+        slab_idx = slab_f = slab_ready = None
+        if self.use_slabs and n > 0 and num_hops > 1 and self.kernel_variant in (_cabi.VARIANT_AUTO, _cabi.VARIANT_SLAB) \
+                and not self.skip_hop_launch:
+            if torch.is_tensor(a_graph_all):                    # [hops, B, H] from the bmm
+                ag3 = a_graph_all
+            elif g_all.dim() == 3:                              # [hops, B, ld]: columns [c, c+H)
+                ag3 = g_all[:, :, c:c + heads]
+            else:                                               # [hops, B, hops, ld]: the (i, :, i, c:c+H) blocks
+                ld4 = g_all.size(3)
+                ag3 = torch.as_strided(g_all, (num_hops, b, heads), (b * num_hops * ld4 + ld4, num_hops * ld4, 1),
+                                       g_all.storage_offset() + c)
+            cur = torch.cuda.current_stream(x.device)
+            sstream = self._side_stream(x.device)
+            sstream.wait_stream(cur)            # the pre-pass products (and, without a side CSR build, the topology)
+            with torch.cuda.stream(sstream):
+                slab_idx, slab_f = _cabi.build_hop_slabs(csr_d, a_edge_all, ag3, num_hops, heads, n)
+                slab_ready = torch.cuda.Event()
+                slab_ready.record(sstream)
+            for t in (slab_idx, slab_f):
+                t.record_stream(cur)
         h = x
         hops = []
         a_node = x_l[:, hc:hc + 2 * heads] if fused_logits else \
@@ -358,9 +385,12 @@ class gat_seq(nn.Module):
                 with _strict_fp32_matmul():
                     torch.mm(h, pk["w_h"][i].t(), out=x_l)
                 _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
-            if side is not None:                # the hop is the first consumer of the topology
-                torch.cuda.current_stream(x.device).wait_stream(side)
-                side = None
+            if side is not None:                # the hop is the first consumer of the topology (the event, not the
+                torch.cuda.current_stream(x.device).wait_event(csr_ready)   # stream: the slab build queued behind
+                side = None                                                 # the CSR build must not hold hop 0 up)
+            if i == 1 and slab_ready is not None:
+                torch.cuda.current_stream(x.device).wait_event(slab_ready)
+            use_slab = slab_idx is not None and i >= 1
             last = i == num_hops - 1
             ln = None if last else self._interleaved_ln
             if last:
@@ -380,7 +410,9 @@ class gat_seq(nn.Module):
                 _cabi.gat_hop(x_l, a_node, a_edge_all[:, i * heads:], csr_d, heads, c, h_out,
                               lde=a_edge_all.stride(0), graph_bias=graph_bias_all[i], a_graph=a_graph_all[i],
                               h_prev=h, bias=self.convs[i].bias, negative_slope=self.convs[i].negative_slope,
-                              variant=self.kernel_variant, **epi,
+                              variant=(self.kernel_variant if use_slab or self.kernel_variant != _cabi.VARIANT_SLAB
+                                       else _cabi.VARIANT_BLOCK),
+                              slab_idx=slab_idx if use_slab else None, slab_f=slab_f[i] if use_slab else None, **epi,
                               # topology and pre-pass outputs are older than the projection launched just above
                               # (except hop 0 of a grouped launch, whose predecessor also wrote the pre-pass outputs)
                               inputs_older_than_predecessor=fused_logits and not (grouped and i == 0), **csr.hints())

@@ -78,12 +78,16 @@ class SceneGraphBatch:
     """Attribute bag with the reference Batch surface.  Extra: ``max_nodes_per_graph`` hint and a
     lazily built, cached ``csr`` (dropped by ``.to`` to another device)."""
 
-    _TENSOR_FIELDS = ("x", "edge_index", "edge_attr", "added_sym_edge", "batch", "y")
+    _TENSOR_FIELDS = ("x", "edge_index", "edge_attr", "added_sym_edge", "batch", "y", "edge_sign")
 
     def __init__(self, x=None, edge_index=None, edge_attr=None, batch=None, added_sym_edge=None, y=None,
-                 num_graphs=None, max_nodes_per_graph=0, max_in_edges_per_graph=0):
+                 num_graphs=None, max_nodes_per_graph=0, max_in_edges_per_graph=0, edge_sign=None, csr_host=None):
         self.x, self.edge_index, self.edge_attr, self.batch = x, edge_index, edge_attr, batch
         self.added_sym_edge, self.y = added_sym_edge, y
+        # wire format (collate.WireCollator): `edge_sign` [E] float32 = -1 on the rows the reference negates through
+        # `added_sym_edge` (pipeline_model_gat.py:590), +1 elsewhere -- a fixed-shape stand-in for the ragged index
+        # list; `csr_host` = the loader-built int32 destination-CSR (dict of host tensors), shipped by .to()
+        self.edge_sign, self.csr_host = edge_sign, csr_host
         self.num_graphs = num_graphs
         self.max_nodes_per_graph = max_nodes_per_graph
         self.max_in_edges_per_graph = max_in_edges_per_graph
@@ -99,15 +103,17 @@ class SceneGraphBatch:
 
     def to(self, device=None, non_blocking=False):
         out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph,
-                              max_in_edges_per_graph=self.max_in_edges_per_graph)
+                              max_in_edges_per_graph=self.max_in_edges_per_graph, csr_host=self.csr_host)
         for name in self._TENSOR_FIELDS:
             t = getattr(self, name)
             setattr(out, name, None if t is None else t.to(device=device, non_blocking=non_blocking))
+        if self.csr_host is not None and device is not None and torch.device(device).type == "cuda":
+            out._csr = GraphCSR.from_host(self.csr_host, device, non_blocking=non_blocking)   # no CSR kernel on the GPU
         return out
 
     def pin_memory(self):
         out = SceneGraphBatch(num_graphs=self.num_graphs, max_nodes_per_graph=self.max_nodes_per_graph,
-                              max_in_edges_per_graph=self.max_in_edges_per_graph)
+                              max_in_edges_per_graph=self.max_in_edges_per_graph, csr_host=self.csr_host)
         for name in self._TENSOR_FIELDS:
             t = getattr(self, name)
             setattr(out, name, None if t is None else t.pin_memory())

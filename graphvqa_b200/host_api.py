@@ -1,20 +1,27 @@
-"""Host-buffer entry point of the hot path: ``gat_seq`` fed from (pinned) host memory.
+"""Host-buffer entry points of the hot path.
 
-``GatSeqHostRunner`` is the call a data-loader-side user makes: it takes the five host tensors of one
-batch (``x, edge_index, edge_attr, instr_vectors, batch`` -- the arguments of the reference's
-``gat_seq.forward``, gat_skip.py:249), moves them to the GPU, builds the CSR, runs the hop stack and
-returns the node states in pinned host memory.  Consecutive batches are software-pipelined over three
-CUDA streams and ``depth`` device slots: the H2D copy of batch i+1 and the D2H copy of batch i-1
-overlap the kernels of batch i (PCIe is full duplex).  ``depth`` = 3 keeps the H2D engine saturated: with 2
-slots the host has to wait for batch i-2's result before it may enqueue batch i's copy, which left the link
-idle ~45 % of the time (profiles/microbench/e2e_probe.py: 1.75 ms -> 0.98 ms per cfg2 batch, the PCIe bound).  With ``use_cuda_graph`` the per-slot compute
-(CSR build + pre-pass + hops) is captured once per input shape and replayed.
+``GatSeqHostRunner``   the operator boundary: the five host tensors of one ``gat_seq.forward`` call
+                       (``x, edge_index, edge_attr, instr_vectors, batch`` -- gat_skip.py:249 of the reference) in,
+                       node states out.  Ships pre-encoded fp32 features: ~50 MB per 256-graph batch, PCIe-bound.
+``GraphSideHostRunner`` the boundary the reference's own loop has (mainExplain_gat.py:710-714, 758-765): TOKEN IDS in,
+                       answer logits out.  One wire-format batch (``collate.WireCollator``: int32 tokens + the
+                       loader-built destination-CSR) plus the text side's ``instr_vectors`` / question summary go up
+                       (~4 MB per 256-graph batch), ``short_answer_logits`` [B, 1842] come back (1.9 MB); scene-graph
+                       encoder -> hop stack -> conditional attention pooling -> logit_fc run as ONE CUDA graph.
+
+Both software-pipeline consecutive batches over three CUDA streams and ``depth`` device slots: the H2D copy of batch
+i+1 and the D2H copy of batch i-1 overlap the kernels of batch i (PCIe is full duplex).  ``depth`` = 3 keeps the H2D
+engine saturated: with 2 slots the host has to wait for batch i-2's result before it may enqueue batch i's copy, which
+left the link idle ~45 % of the time (profiles/microbench/e2e_probe.py).  With ``use_cuda_graph`` the per-slot compute
+is captured once per input shape and replayed.
+
+The default fp16-split projection flags inputs outside fp16's range on the device; the flag travels with every
+result and ``result()`` redoes such a batch with the tf32 split (full fp32 range), so the caller always receives
+valid numbers.
 """
 import torch
 
-from .graph_batch import GraphCSR
-
-_KEYS = ("x", "edge_index", "edge_attr", "instr_vectors", "batch")
+from .graph_batch import GraphCSR, SceneGraphBatch
 
 
 class _Slot:
@@ -33,36 +40,46 @@ class _Slot:
         self.busy = False
 
 
-class GatSeqHostRunner:
-    def __init__(self, model, device, depth=3, use_cuda_graph=True, max_nodes_per_graph=0,
-                 max_in_edges_per_graph=0):
-        self.model, self.device, self.depth = model, torch.device(device), depth
+class _PipelinedRunner:
+    """Slot / stream machinery shared by the two runners.  Subclasses define ``_keys`` (names of the host tensors of
+    one batch), ``_forward(dev_dict) -> device tensor`` and ``_range_seq()`` (the gat_seq whose fp16 flag guards the
+    batch, or None)."""
+
+    _keys = ()
+
+    def __init__(self, device, depth=3, use_cuda_graph=True):
+        self.device, self.depth = torch.device(device), depth
         self.use_cuda_graph = use_cuda_graph
-        self.hints = dict(max_nodes_per_graph=max_nodes_per_graph, max_in_edges_per_graph=max_in_edges_per_graph)
         self.s_h2d, self.s_compute, self.s_d2h = (torch.cuda.Stream(self.device) for _ in range(3))
         self.slots = [_Slot() for _ in range(depth)]
-        if hasattr(model, "overflow_external"):
-            model.overflow_external = True     # the fp16 range flag travels with each result (see result())
         self.count = 0
+        seq = self._range_seq()
+        if seq is not None:
+            seq.overflow_external = True     # the fp16 range flag travels with each result (see result())
 
-    def _forward(self, d):
-        return self.model(d["x"], d["edge_index"], d["edge_attr"], d["instr_vectors"], d["batch"], csr_hints=self.hints)
+    def _range_seq(self):
+        return None
+
+    def _forward(self, dev):
+        raise NotImplementedError
+
+    def _flag(self):
+        seq = self._range_seq()
+        return None if seq is None else getattr(seq, "_overflow", None)
 
     @torch.no_grad()
     def submit(self, host):
-        """Enqueue one batch (dict or 5-tuple of CPU tensors, ideally pinned).  Returns a ticket."""
-        if not isinstance(host, dict):
-            host = dict(zip(_KEYS, host))
+        """Enqueue one batch (dict of CPU tensors, ideally pinned).  Returns a ticket."""
         slot = self.slots[self.count % self.depth]
         if slot.busy:
             slot.d2h_done.synchronize()     # the slot's previous result must have left the device
-        shapes = tuple((tuple(host[k].shape), host[k].dtype) for k in _KEYS)
+        shapes = tuple((tuple(host[k].shape), host[k].dtype) for k in self._keys)
         if slot.shapes != shapes:
-            slot.dev = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in _KEYS}
+            slot.dev = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in self._keys}
             slot.shapes, slot.graph, slot.out_dev, slot.out_host = shapes, None, None, None
         with torch.cuda.stream(self.s_h2d):
             self.s_h2d.wait_event(slot.compute_done)          # previous compute on this slot has read its inputs
-            for k in _KEYS:
+            for k in self._keys:
                 slot.dev[k].copy_(host[k], non_blocking=True)
             slot.h2d_done.record(self.s_h2d)
         with torch.cuda.stream(self.s_compute):
@@ -75,14 +92,14 @@ class GatSeqHostRunner:
                 with torch.cuda.graph(g, stream=self.s_compute):
                     slot.out_dev = self._forward(slot.dev)
                 slot.graph = g
-            flag = getattr(self.model, "_overflow", None)
+            flag = self._flag()
             if flag is not None:
                 flag.zero_()                                  # this batch's fp16 range flag starts clear ...
             if slot.graph is not None:
                 slot.graph.replay()
             else:
                 slot.out_dev = self._forward(slot.dev)
-            flag = getattr(self.model, "_overflow", None)     # (created by the first forward)
+            flag = self._flag()                               # (created by the first forward)
             if flag is not None:
                 if slot.flag_dev is None:
                     slot.flag_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -104,22 +121,25 @@ class GatSeqHostRunner:
         return self.count - 1
 
     def result(self, ticket):
-        """Pinned host tensor with the node states of batch ``ticket`` (valid until the slot is reused,
-        i.e. until ``depth`` more batches have been submitted)."""
+        """Pinned host tensor with the result of batch ``ticket`` (valid until the slot is reused, i.e. until
+        ``depth`` more batches have been submitted)."""
         slot = self.slots[ticket % self.depth]
         slot.d2h_done.synchronize()
         if int(slot.flag_host) != 0:
-            # an input did not fit fp16: redo this batch with the tf32-split projection (full fp32 range)
+            # an input did not fit fp16: redo this batch with the tf32-split projection (full fp32 range).  The fp16
+            # weight pack stays alive (gat_seq keeps one pack per projection kind), so the slots' captured graphs,
+            # which hold raw pointers into it, remain valid.
             slot.flag_host.zero_()
-            prev = self.model.projection
-            self.model.projection = "3xtf32"
+            seq = self._range_seq()
+            prev = seq.projection
+            seq.projection = "3xtf32"
             try:
                 with torch.no_grad(), torch.cuda.stream(self.s_compute):
-                    dev = {k: slot.host_in[k].to(self.device, non_blocking=True) for k in _KEYS}
+                    dev = {k: slot.host_in[k].to(self.device, non_blocking=True) for k in self._keys}
                     slot.out_host.copy_(self._forward(dev))
                 self.s_compute.synchronize()
             finally:
-                self.model.projection = prev
+                seq.projection = prev
         return slot.out_host
 
     def drain(self):
@@ -127,5 +147,85 @@ class GatSeqHostRunner:
             if s.busy:
                 s.d2h_done.synchronize()
 
+
+_GAT_SEQ_KEYS = ("x", "edge_index", "edge_attr", "instr_vectors", "batch")
+
+
+class GatSeqHostRunner(_PipelinedRunner):
+    _keys = _GAT_SEQ_KEYS
+
+    def __init__(self, model, device, depth=3, use_cuda_graph=True, max_nodes_per_graph=0,
+                 max_in_edges_per_graph=0):
+        self.model = model
+        self.hints = dict(max_nodes_per_graph=max_nodes_per_graph, max_in_edges_per_graph=max_in_edges_per_graph)
+        super().__init__(device, depth, use_cuda_graph)
+
+    def _range_seq(self):
+        return self.model if hasattr(self.model, "overflow_external") else None
+
+    def _forward(self, d):
+        return self.model(d["x"], d["edge_index"], d["edge_attr"], d["instr_vectors"], d["batch"], csr_hints=self.hints)
+
+    def submit(self, host):
+        if not isinstance(host, dict):
+            host = dict(zip(_GAT_SEQ_KEYS, host))
+        return super().submit(host)
+
     def __call__(self, *host):
         return self.result(self.submit(host if len(host) != 1 else host[0]))
+
+
+class GraphSideHostRunner(_PipelinedRunner):
+    """``model``: a ``PipelineModel`` (GAT / GCN / GINE variant).  ``submit(graphs, instr_vectors, q0)`` takes a
+    wire-format ``SceneGraphBatch`` from ``collate.WireCollator`` (host tensors), the instruction vectors [5,B,D] and
+    the question summary ``questions_encoded[0]`` [B,D] (host, ideally pinned); ``result`` returns
+    ``short_answer_logits`` [B,1842] in pinned host memory.  The device never runs a CSR kernel: the topology arrives
+    in its final int32 form."""
+
+    _csr_keys = ("rowptr", "col_src", "perm", "graph_ptr", "node_graph", "stats")
+    _keys = ("x", "edge_index", "edge_attr", "edge_sign") + _csr_keys + ("instr_vectors", "q0")
+
+    def __init__(self, model, device, depth=3, use_cuda_graph=True):
+        self.model = model
+        super().__init__(device, depth, use_cuda_graph)
+
+    def _range_seq(self):
+        return getattr(self.model, "gat_seq", None)
+
+    def _forward(self, d):
+        n, b = d["rowptr"].numel() - 1, d["graph_ptr"].numel() - 1
+        e = d["edge_index"].size(1)
+        hints = self._hints
+        csr = GraphCSR({k: d[k] for k in self._csr_keys}, n, e, b, hints[0], hints[1])
+        g = SceneGraphBatch(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], batch=d["node_graph"],
+                            edge_sign=d["edge_sign"], num_graphs=b, max_nodes_per_graph=hints[0],
+                            max_in_edges_per_graph=hints[1])
+        g._csr = csr
+        model = self.model
+        strict, model.strict_range = model.strict_range, False      # the flag travels with the result instead
+        try:
+            return model.graph_side(g, d["instr_vectors"], d["q0"].unsqueeze(0), b, csr=csr)
+        finally:
+            model.strict_range = strict
+
+    def submit(self, graphs, instr_vectors=None, q0=None):
+        if isinstance(graphs, dict):
+            host = graphs
+        else:
+            if graphs.csr_host is None or graphs.edge_sign is None:
+                raise ValueError("GraphSideHostRunner: pass a wire-format batch (collate.WireCollator)")
+            host = dict(x=graphs.x, edge_index=graphs.edge_index, edge_attr=graphs.edge_attr,
+                        edge_sign=graphs.edge_sign, instr_vectors=instr_vectors, q0=q0, **graphs.csr_host)
+            self._hints = (graphs.max_nodes_per_graph, graphs.max_in_edges_per_graph)
+        return super().submit(host)
+
+    _hints = (0, 0)
+
+    def __call__(self, graphs, instr_vectors, q0):
+        return self.result(self.submit(graphs, instr_vectors, q0))
+
+    @staticmethod
+    def bytes_per_batch(graphs, instr_vectors, q0):
+        host = [graphs.x, graphs.edge_index, graphs.edge_attr, graphs.edge_sign, instr_vectors, q0] + \
+               [graphs.csr_host[k] for k in GraphSideHostRunner._csr_keys]
+        return sum(t.numel() * t.element_size() for t in host)

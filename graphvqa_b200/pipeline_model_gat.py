@@ -261,9 +261,9 @@ class _MetaLayer(nn.Module):
 class GroundTruth_SceneGraph_Encoder(nn.Module):
     """Token-embedding sum -> MetaLayer -> per-graph LayerNorm (pipeline_model_gat.py:553-610)."""
 
-    def __init__(self, sg_vocab_size, sg_pad_idx):
+    def __init__(self, sg_vocab_size, sg_pad_idx, sg_emb_dim=300):
         super().__init__()
-        self.sg_emb_dim = 300
+        self.sg_emb_dim = sg_emb_dim                    # 300 in the reference (:560)
         self.sg_vocab_embedding = nn.Embedding(sg_vocab_size, self.sg_emb_dim, padding_idx=sg_pad_idx)
         self.scene_graph_encoding_layer = _MetaLayer(self.sg_emb_dim, self.sg_emb_dim)
         self.graph_layer_norm = LayerNorm(self.sg_emb_dim)
@@ -273,12 +273,18 @@ class GroundTruth_SceneGraph_Encoder(nn.Module):
         x_sum = self.sg_vocab_embedding(g.x).sum(dim=-2)
         e_emb = self.sg_vocab_embedding(g.edge_attr)
         sym = getattr(g, "added_sym_edge", None)
-        if sym is not None and sym.numel() > 0:
-            # the reference negates rows `added_sym_edge` of the BATCHED edge array although the indices
-            # are graph-local (Batch.from_data_list does not offset them; pipeline_model_gat.py:590)
-            e_emb = e_emb.clone()
-            e_emb[sym, :, :] *= -1
-        e_sum = e_emb.sum(dim=-2)
+        sign = getattr(g, "edge_sign", None)
+        if sign is not None:
+            # wire format: the same negation as a per-edge sign vector of fixed shape (exact: a sign flip commutes
+            # with the sum over the token slots)
+            e_sum = e_emb.sum(dim=-2) * sign.unsqueeze(-1)
+        else:
+            if sym is not None and sym.numel() > 0:
+                # the reference negates rows `added_sym_edge` of the BATCHED edge array although the indices
+                # are graph-local (Batch.from_data_list does not offset them; pipeline_model_gat.py:590)
+                e_emb = e_emb.clone()
+                e_emb[sym, :, :] *= -1
+            e_sum = e_emb.sum(dim=-2)
         if csr is None:
             csr = _batch_csr(g, int(g.batch.max()) + 1 if getattr(g, "num_graphs", None) is None else g.num_graphs)
         x_enc, e_enc = self.scene_graph_encoding_layer(x_sum, g.edge_index, e_sum, csr)
@@ -328,11 +334,13 @@ class PipelineModel(nn.Module):
 
     variant = "gat"
 
-    def __init__(self, vocab: Optional[VocabSpec] = None):
+    def __init__(self, vocab: Optional[VocabSpec] = None, sg_emb_dim: int = 300):
+        """``sg_emb_dim``: width of the scene-graph features; 300 in the reference (pipeline_model_gat.py:560), a
+        parameter here because BASELINE.json's synthetic configs are quoted at feat_dim = 512."""
         super().__init__()
         vocab = vocab or VocabSpec.from_reference_dataset()
         self.vocab = vocab
-        self.scene_graph_encoder = GroundTruth_SceneGraph_Encoder(vocab.sg_vocab_size, vocab.sg_pad_idx)
+        self.scene_graph_encoder = GroundTruth_SceneGraph_Encoder(vocab.sg_vocab_size, vocab.sg_pad_idx, sg_emb_dim)
 
         text_emb_dim = 300
         self.text_vocab_embedding = nn.Embedding(vocab.text_vocab_size, text_emb_dim, padding_idx=vocab.text_pad_idx)
@@ -401,7 +409,7 @@ class PipelineModel(nn.Module):
         guarded = (self.strict_range and seq is not None and seq.projection == "3xf16"
                    and not torch.cuda.is_current_stream_capturing())
         if seq is not None:
-            seq.overflow_external = guarded or seq.overflow_external
+            seq.overflow_external = True      # this module (or the host runner above it) owns the range flag
         x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
         if guarded and seq._overflow is not None and int(seq._overflow) != 0:      # one host sync per call
             seq._overflow.zero_()

@@ -164,8 +164,10 @@ typedef struct gvqa_gat_hop_args {
   int32_t epilogue;        /* gvqa_epilogue                                                   */
   int32_t max_nodes_per_graph;    /* loader hints (0 = unknown) that size the shared-memory staged  */
   int32_t max_in_edges_per_graph; /* kernel; never a correctness input (oversize graphs fall back)   */
-  int32_t variant;         /* 0 = auto, 1 = warp-per-node gather, 2 = TMA smem-staged, 3 = block-phase gather,
-                              4 = persistent warp-specialised (producer warp prepares chunks, needs `sched`) */
+  int32_t variant;         /* 0 = auto (5 when slabs are given, else 3), 1 = warp-per-node gather, 2 = TMA smem-staged
+                              rows, 3 = block-phase gather, 4 = persistent warp-specialised (producer warp prepares
+                              chunks, needs `sched`), 5 = block-phase gather with the one-round-trip slab prologue
+                              (needs slab_idx / slab_f from gvqa_gat_hop_build_slabs_f32)                        */
   int64_t ld_graph_bias;   /* row stride of graph_bias in floats; 0 = dense (C); multiple of 4            */
   int64_t ld_a_graph;      /* row stride of a_graph in floats; 0 = dense (H).  Both terms may be column
                               blocks of one pre-pass GEMM output                                          */
@@ -173,6 +175,10 @@ typedef struct gvqa_gat_hop_args {
   float ln_eps;            /* GVQA_EPI_GRAPH_LN: eps (added to the standard deviation)                            */
   const float* ln_weight;  /* GVQA_EPI_GRAPH_LN: ONE float each on the device (the reference's parameters have    */
   const float* ln_bias;    /*   shape [1]), or both NULL for no affine                                            */
+  const int32_t* slab_idx; /* variant 5: the per-batch index slabs and THIS hop's logit-term slabs (slab_f + hop *  */
+  const float* slab_f;     /*   f_words_per_hop), see gvqa_gat_hop_build_slabs_f32; NULL otherwise.  max_nodes_per_graph
+                              sizes the a_node window the kernel stages (sources farther away are loaded from global
+                              memory: a hint, never a correctness input)                                          */
   int32_t* sched;          /* variant 4: two int32 of device scratch, zero before the first launch; the kernel
                               leaves them zero again (dynamic chunk scheduler); may be NULL otherwise.  Two
                               launches that may run concurrently need separate words                              */
@@ -187,6 +193,25 @@ typedef struct gvqa_gat_hop_args {
 #define GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR 1
 
 GVQA_API int gvqa_gat_hop_f32(const gvqa_gat_hop_args* args, void* stream);
+
+/* Per-batch slabs for hop variant 5.  Everything the hop kernel's index prologue gathers except a_node is
+ * hop-invariant per batch (topology, per-edge logit terms of all hops, per-graph logit terms), and the CTA partition
+ * depends on the node count only; this pass writes it once per batch in a per-CTA layout whose address depends on the
+ * block index alone, so each hop CTA fetches it with two TMA bulk copies (cp.async.bulk + mbarrier) in ONE round trip
+ * instead of three dependent ones (row pointers -> sources / edge ids -> logit terms).
+ *   a_edge [E, lde]: hop j's per-edge term at columns [j*H, (j+1)*H), original edge order (gathered through perm);
+ *   a_graph: hop j's per-graph term at a_graph + j*hop_stride_a_graph + g*ld_a_graph + h, or NULL.
+ * Buffers: slab_idx int32[plan.idx_words], slab_f float[hops * plan.f_words_per_hop], both 16-byte aligned. */
+typedef struct gvqa_gat_slab_plan {
+  int32_t nodes_per_cta, edge_capacity, num_ctas;
+  int64_t idx_words, f_words_per_hop;
+} gvqa_gat_slab_plan;
+GVQA_API int gvqa_gat_hop_slab_plan(int64_t num_nodes, int64_t num_edges, int32_t heads, gvqa_gat_slab_plan* plan);
+GVQA_API int gvqa_gat_hop_build_slabs_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
+                                          const int32_t* node_graph, const float* a_edge, int64_t lde,
+                                          const float* a_graph, int64_t ld_a_graph, int64_t hop_stride_a_graph,
+                                          int32_t hops, int64_t num_nodes, int64_t num_edges, int32_t heads,
+                                          int32_t* slab_idx, float* slab_f, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-graph LayerNorm (graph_utils/my_graph_layernorm.py:52-78): statistics over all

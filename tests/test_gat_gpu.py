@@ -98,7 +98,7 @@ def _run_both(o, e, args, variant=0, hints=None):
     return want, want_hops, got.cpu(), [h.cpu() for h in got_hops]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("f,d,heads,hops", [(300, 512, 4, 5), (512, 512, 4, 5), (64, 32, 1, 2), (128, 64, 8, 3),
                                             (36, 20, 2, 2)])
 def test_gat_seq_matches_oracle_random_graphs(f, d, heads, hops, variant):
@@ -127,7 +127,7 @@ def test_gat_seq_staged_oversize_units_fall_back(hints):
     assert (want - got).abs().max() <= TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_gat_seq_high_degree_hub(variant):
     # one hub node with in-degree > 32 exercises the chunked softmax path
     n = 60 if variant == 2 else 400          # 400: > 256 in-edges in one 16-node block (kernel 3 fallback)
@@ -141,7 +141,7 @@ def test_gat_seq_high_degree_hub(variant):
     assert (want - got).abs().max() <= TOL
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", [1, 3, 4, 5])
 def test_gat_seq_golden_small(golden, variant):
     fx = golden("gat_seq_small")
     e = eng.gat_seq(**fx["config"]).eval()
@@ -173,7 +173,7 @@ def test_gat_seq_golden_refdims(golden):
     assert (out - fx["out"]).abs().max() <= TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_gat_seq_cfg2_shape_and_determinism(variant):
     """BASELINE cfg2 (B=256, 30 nodes / 60 edges, F=512, 5 hops): parity vs oracle on a 16-graph
     slice, bitwise run-to-run determinism, and shard invariance (graphs are independent)."""
@@ -224,6 +224,57 @@ def test_host_runner_pipelined_matches_direct_call():
                     assert torch.equal(runner.result(tk), direct[idx])
         runner.drain()
         assert torch.equal(runner.result(tickets[-1][0]), direct[tickets[-1][1]])
+
+
+@pytest.mark.parametrize("variant", [3, 4, 5])
+def test_gat_seq_cfg2_full_batch_matches_oracle(variant):
+    """BASELINE cfg2 at its FULL size (256 graphs x 30 nodes / 60 edges, F=512, 4 heads, 5 hops): every hop's output
+    against the CPU oracle (the oracle takes ~0.5 s for the whole batch)."""
+    cfg = dict(in_channels=512, out_channels=512, edge_attr_dim=512, ins_dim=512, num_ins=5, gat_heads=4)
+    o, e = _pair(cfg, seed=81)
+    ei, batch, _ = synthetic_topology(256, 30, 60, seed=1234)
+    args = _inputs(ei, batch, 256, 512, 512, 512, 5, seed=82)
+    want, want_hops, got, got_hops = _run_both(o, e, args, variant)
+    for i, (a, c) in enumerate(zip(want_hops, got_hops)):
+        assert (a - c).abs().max() <= TOL, "hop %d: max|d|=%g" % (i, (a - c).abs().max())
+    assert (want - got).abs().max() <= TOL
+    e.check_overflow()
+
+
+@pytest.mark.parametrize("hint", [0, 3, 1000])
+def test_slab_hop_window_hint_is_only_a_hint(hint):
+    """variant 5 stages the a_node rows of `max_nodes_per_graph` nodes either side of a CTA's range; sources outside
+    the window (hint too small / unknown) are loaded from global memory, a hint larger than the kernel's window
+    capacity is clipped: the block kernel's result bit for bit in every case."""
+    cfg = dict(in_channels=128, out_channels=128, edge_attr_dim=128, ins_dim=32, num_ins=3, gat_heads=4)
+    o, e = _pair(cfg, seed=91)
+    ei, batch = random_graphs(12, 1, 60, 2.5, seed=10, isolated=True)
+    args = _inputs(ei, batch, 12, 128, 128, 32, 3, seed=92)
+    want, _, got5, _ = _run_both(o, e, args, variant=5, hints=(hint, 0))
+    _, _, got3, _ = _run_both(o, e, args, variant=3, hints=(hint, 0))
+    assert (want - got5).abs().max() <= TOL
+    assert torch.equal(got3, got5)
+
+
+def test_warp_specialised_hop_scheduler_words_return_to_zero():
+    """variant 4 claims chunks from two device words that the last CTA resets: back-to-back launches (also with
+    different sizes) must all see a zeroed scheduler and give the block kernel's result bit for bit."""
+    h, c = 4, 256
+    outs = {}
+    for graphs in (3, 40, 7):
+        ei, batch, mx = synthetic_topology(graphs, 30, 60, seed=graphs)
+        ei, batch = ei.to(DEV), batch.to(DEV)
+        n, e = batch.numel(), ei.size(1)
+        csr = GraphCSR.build(ei, batch, graphs, max_nodes_per_graph=mx)
+        g = torch.Generator().manual_seed(graphs)
+        a_node, a_edge = torch.randn(n, 2 * h, generator=g).to(DEV), torch.randn(e, h, generator=g).to(DEV)
+        x_l, prev = torch.randn(n, h * c, generator=g).to(DEV), torch.randn(n, c, generator=g).to(DEV)
+        for variant in (3, 4, 4):
+            out = torch.empty(n, c, device=DEV)
+            _cabi.gat_hop(x_l, a_node, a_edge, csr.as_dict(), h, c, out, h_prev=prev, variant=variant, **csr.hints())
+            outs.setdefault(graphs, []).append(out)
+        assert torch.equal(outs[graphs][0], outs[graphs][1]) and torch.equal(outs[graphs][1], outs[graphs][2])
+        assert _cabi.hop_sched(DEV).cpu().tolist() == [0, 0]
 
 
 def test_gat_seq_cfg4_shape_large_graphs():

@@ -1,0 +1,267 @@
+"""GPU parity (through the C ABI) of the steps either side of the hop stack -- SURVEY.md section 8 f1 (scene-graph
+encoder / MetaLayer), f2 (conditional attention pooling), f3 (wire format + host-built CSR) -- against the CPU oracle
+and the golden vectors of the unmodified reference, plus the graph-LayerNorm epilogue mode of the fused hop (N1)."""
+import importlib
+import types
+
+import pytest
+import torch
+
+from conftest import random_graphs
+from graphvqa_b200 import _cabi
+from graphvqa_b200 import gat_skip as eng
+from graphvqa_b200.graph_batch import GraphCSR, SceneGraphBatch, synthetic_topology
+from graphvqa_b200.my_graph_layernorm import LayerNorm
+from graphvqa_b200.pipeline_model_gat import MyConditionalGlobalAttention, PipelineModel, VocabSpec
+from oracle import graphvqa_oracle as orc
+from oracle import pyg_semantics as pyg
+from oracle.golden_utils import deterministic_fill, state_hash
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+# ---------------------------------------------------------------- isolated kernels (f1) ------------------------------
+@pytest.mark.parametrize("graphs,n_hi,f,idx", [(5, 9, 64, torch.int64), (7, 20, 300, torch.int32),
+                                               (256, 30, 512, torch.int32)])
+def test_gather_add_relu_and_segment_mean(graphs, n_hi, f, idx):
+    """first Linear of the encoder MLPs on the split concatenation + scatter_mean by target, incl. nodes without
+    in-edges (count clamped to 1, pipeline_model_gat.py:96) and both index widths."""
+    ei, batch = random_graphs(graphs, 1, n_hi, 2.0, seed=graphs, self_loops=False, isolated=True)
+    n, e = batch.numel(), ei.size(1)
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(n, f, generator=g), torch.randn(n, f, generator=g)
+    c, bias = torch.randn(e, f, generator=g), torch.randn(f, generator=g)
+    want = torch.relu(a[ei[0]] + b[ei[1]] + c + bias)
+    got = _cabi.gather_add_relu(a.to(DEV), b.to(DEV), c.to(DEV), bias.to(DEV), ei.to(DEV).to(idx)).cpu()
+    assert torch.equal(got, want)                       # same three additions in the same order: bit-exact
+    got2 = _cabi.gather_add_relu(a.to(DEV), None, c.to(DEV), None, ei.to(DEV).to(idx), relu=False).cpu()
+    assert torch.equal(got2, a[ei[0]] + c)
+    csr = GraphCSR.build(ei.to(DEV), batch.to(DEV), graphs)
+    deg = torch.bincount(ei[1], minlength=n)
+    assert int((deg == 0).sum()) > 0
+    mean = _cabi.segment_mean_rows(c.to(DEV), csr.as_dict(), mean=True).cpu()
+    assert (mean - pyg.scatter_mean(c, ei[1], n)).abs().max() <= 1e-5
+    total = _cabi.segment_mean_rows(c.to(DEV), csr.as_dict(), mean=False).cpu()
+    assert (total - pyg.scatter_sum(c, ei[1], n)).abs().max() <= 1e-5
+    assert float(mean[deg == 0].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- pooling (f2) ---------------------------------------
+def _graph_ptr(batch, size):
+    gp = torch.zeros(size + 1, dtype=torch.int32)
+    gp[1:] = torch.bincount(batch, minlength=size).cumsum(0).to(torch.int32)
+    return gp
+
+
+@pytest.mark.parametrize("c", [16, 300, 512])
+def test_attention_pool_kernels_edge_cases(c):
+    """per-graph softmax + weighted sum, with an EMPTY graph in the middle, one behind the last node, a single-node
+    graph and a 300-node graph; the fused variant also evaluates gate = <hid, w> + b itself."""
+    batch = torch.tensor([0] * 5 + [1] + [3] * 300 + [4] * 2)
+    size = 6
+    g = torch.Generator().manual_seed(c)
+    n = batch.numel()
+    x, hid = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    w, b0 = torch.randn(1, c, generator=g) / c ** 0.5, torch.randn(1, generator=g)
+    gate = hid @ w.t() + b0
+    alpha = pyg.segment_softmax(gate, batch, size)
+    want = pyg.scatter_sum(alpha * x, batch, size)
+    gp = _graph_ptr(batch, size).to(DEV)
+    got = _cabi.attention_pool(gate.to(DEV), x.to(DEV), gp, size).cpu()
+    assert (got - want).abs().max() <= 1e-5
+    got2, gate2 = _cabi.attention_pool_gate(hid.to(DEV), w.to(DEV), b0.to(DEV), x.to(DEV), gp, size)
+    assert (gate2.cpu() - gate.view(-1)).abs().max() <= 1e-5
+    assert (got2.cpu() - want).abs().max() <= 1e-5
+    assert float(got2[2].abs().max()) == 0.0 and float(got2[5].abs().max()) == 0.0
+
+
+def test_graph_scale_rows():
+    _, batch = random_graphs(9, 1, 12, 0.0, seed=2)
+    g = torch.Generator().manual_seed(3)
+    x, q = torch.randn(batch.numel(), 512, generator=g), torch.randn(9, 512, generator=g)
+    got = _cabi.graph_scale_rows(x.to(DEV), q.to(DEV), batch.to(DEV).to(torch.int32)).cpu()
+    assert torch.equal(got, q[batch] * x)
+
+
+def test_pooling_module_matches_reference_golden_edge_cases(golden):
+    p = golden("encoder_pool_edge")["pool"]
+    m = MyConditionalGlobalAttention(20, 16).eval()
+    m.load_state_dict(p["state"])
+    m = m.to(DEV)
+    with torch.no_grad():
+        out = m(p["x"].to(DEV), p["u"].to(DEV), p["batch"].to(DEV), size=p["size"]).cpu()
+        out5 = m(p["x"].to(DEV), p["u"][:5].to(DEV), p["batch"].to(DEV)).cpu()
+    assert (out - p["out"]).abs().max() <= 1e-5 and (out5 - p["out_default_size"]).abs().max() <= 1e-5
+    assert float(out[2].abs().max()) == 0.0 and float(out[5].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("graphs,nodes,f,d", [(256, 30, 300, 512), (16, 200, 512, 512)])
+def test_pooling_module_matches_oracle_at_baseline_sizes(graphs, nodes, f, d):
+    _, batch, _ = synthetic_topology(graphs, nodes, nodes, seed=5, jitter=3)
+    torch.manual_seed(6)
+    o = orc.MyConditionalGlobalAttention(f, d).eval()
+    m = MyConditionalGlobalAttention(f, d).eval()
+    m.load_state_dict(o.state_dict())
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(7)
+    x, u = torch.randn(batch.numel(), f, generator=g), torch.randn(graphs, d, generator=g)
+    with torch.no_grad():
+        want = o(x, u, batch, size=graphs)
+        got = m(x.to(DEV), u.to(DEV), batch.to(DEV), size=graphs).cpu()
+    assert (got - want).abs().max() <= TOL * max(1.0, float(want.abs().max()))
+
+
+# ---------------------------------------------------------------- encoder + whole graph side ------------------------
+def _pipeline(fx):
+    m = PipelineModel(VocabSpec(text_vocab_size=3657, sg_vocab_size=2577)).eval()
+    deterministic_fill(m, fx["fill_seed"])
+    if state_hash(m.state_dict()) != fx["state_sha256"]:
+        pytest.skip("seeded parameter fill differs on this torch build")
+    return m.to(DEV)
+
+
+def _batch(d, num_graphs):
+    return SceneGraphBatch(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], batch=d["batch"],
+                           added_sym_edge=d["added_sym_edge"], num_graphs=num_graphs).to(device=DEV)
+
+
+def test_encoder_and_graph_side_match_reference_goldens(golden):
+    base, fx, edge = golden("pipeline_gat"), golden("graph_side_gat"), golden("encoder_pool_edge")
+    m = _pipeline(fx)
+    with torch.no_grad():
+        # edge cases: single-node graphs, in-degree-0 nodes, un-offset added_sym_edge of 7 graphs
+        e = edge["enc"]
+        x_enc, e_enc, _ = m.scene_graph_encoder(_batch(e, e["num_graphs"]))
+        assert (x_enc.cpu() - e["x_encoded"]).abs().max() <= TOL
+        assert (e_enc.cpu() - e["edge_attr_encoded"]).abs().max() <= TOL * max(1.0, float(e["edge_attr_encoded"].abs().max()))
+        # the graph side from the reference's own intermediates
+        g = _batch(base, 4)
+        q_enc = fx["q0"].to(DEV).unsqueeze(0)
+        logits = m.graph_side(g, fx["instr_vectors"].to(DEV), q_enc, 4).cpu()
+        csr = g.csr()
+        enc = m.scene_graph_encoder(g, csr=csr)
+        x_exec = m.gat_seq(enc[0], g.edge_index, enc[1], fx["instr_vectors"].to(DEV), g.batch, csr=csr)
+        pooled = m.graph_global_attention_pooling(x_exec, fx["q0"].to(DEV), g.batch, size=4, graph_ptr=csr.graph_ptr,
+                                                  node_graph=csr.node_graph)
+    assert (x_exec.cpu() - fx["x_executed"]).abs().max() <= TOL * max(1.0, float(fx["x_executed"].abs().max()))
+    assert (pooled.cpu() - fx["pooled"]).abs().max() <= TOL * max(1.0, float(fx["pooled"].abs().max()))
+    assert (logits - base["short_answer_logits"]).abs().max() <= TOL
+
+
+def _random_scene_graph_tensors(num_graphs, seed, vocab=2577):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(num_graphs):
+        ei, _, _ = synthetic_topology(1, 12, 30, seed=seed * 100 + i, jitter=5)
+        n, e = int(ei.max()) + 1, ei.size(1)
+        x = torch.randint(4, vocab, (n, 12), generator=g)
+        x[torch.rand(n, 12, generator=g) < 0.5] = 1
+        sym = torch.randperm(e, generator=g)[:4]
+        out.append((x, ei, torch.randint(4, vocab, (e, 1), generator=g), sym))
+    return out
+
+
+def test_wire_format_runner_equals_reference_format_call(golden):
+    """f3: int32 wire batch + host-built CSR + edge_sign, through GraphSideHostRunner (eager, then CUDA-graph replay)
+    == the reference-format batch (int64 COO, added_sym_edge list, device CSR build) through graph_side."""
+    from graphvqa_b200.collate import WireCollator
+    from graphvqa_b200.host_api import GraphSideHostRunner
+    m = _pipeline(golden("graph_side_gat"))
+    b = 9
+    collator = WireCollator(depth=4)
+    runner = GraphSideHostRunner(m, DEV, depth=2, use_cuda_graph=True)
+    g = torch.Generator().manual_seed(1)
+    for rep in range(4):          # eager, capture, replay, replay (same shapes: same topology seed, new tokens)
+        graphs = _random_scene_graph_tensors(b, seed=3)
+        graphs = [(torch.randint(4, 2577, t[0].shape, generator=g), t[1], t[2], t[3]) for t in graphs]
+        wire = collator(graphs)
+        ins = torch.randn(5, b, 512, generator=g).pin_memory()
+        q0 = torch.randn(b, 512, generator=g).pin_memory()
+        got = runner(wire, ins, q0).clone()
+        # reference-format path
+        n_off, eis, batch = 0, [], []
+        for i, t in enumerate(graphs):
+            eis.append(t[1] + n_off); batch += [i] * t[0].size(0); n_off += t[0].size(0)
+        ref = SceneGraphBatch(x=torch.cat([t[0] for t in graphs]), edge_index=torch.cat(eis, 1),
+                              edge_attr=torch.cat([t[2] for t in graphs]), batch=torch.tensor(batch),
+                              added_sym_edge=torch.cat([t[3] for t in graphs]), num_graphs=b).to(device=DEV)
+        with torch.no_grad():
+            want = m.graph_side(ref, ins.to(DEV), q0.to(DEV).unsqueeze(0), b).cpu()
+        assert got.shape == (b, 1842)
+        assert (got - want).abs().max() <= 1e-5, rep
+    assert all(s.graph is not None for s in runner.slots)
+
+
+@pytest.mark.parametrize("graphs,n_hi,extra", [(1, 1, 0), (7, 12, 2.0), (64, 40, 3.0), (256, 30, 1.0)])
+def test_host_csr_equals_device_csr(graphs, n_hi, extra):
+    ei, batch = random_graphs(graphs, 1, n_hi, extra, seed=graphs, isolated=True)
+    dev = GraphCSR.build(ei.to(DEV), batch.to(DEV), graphs)
+    e = ei.size(1)
+    for idx in (torch.int64, torch.int32):
+        host = _cabi.build_csr_host(ei.to(idx), batch.to(idx), graphs)
+        assert torch.equal(host["rowptr"], dev.rowptr.cpu())
+        assert torch.equal(host["col_src"][:e], dev.col_src.cpu()[:e]) and torch.equal(host["perm"][:e], dev.perm.cpu()[:e])
+        assert torch.equal(host["graph_ptr"], dev.graph_ptr.cpu()) and torch.equal(host["node_graph"], dev.node_graph.cpu())
+        assert host["stats"][:4].tolist() == dev.stats.cpu()[:4].tolist()
+    moved = GraphCSR.from_host(host, DEV)
+    assert torch.equal(moved.rowptr, dev.rowptr) and moved.num_edges == e and moved.num_graphs == graphs
+
+
+def test_csr_flags_invalid_batch_ids():
+    ei = torch.tensor([[0, 1, 2], [1, 0, 2]])
+    bad = torch.tensor([0, 0, 5])                     # graph id 5 >= num_graphs 2
+    csr = GraphCSR.build(ei.to(DEV), bad.to(DEV), 2)
+    assert csr.read_stats()["bad_edges"] >= 1 and int(csr.node_graph.max()) <= 1
+    with pytest.raises(ValueError):
+        csr.check()
+    host = _cabi.build_csr_host(ei, bad, 2)
+    assert int(host["stats"][3]) == csr.read_stats()["bad_edges"] and int(host["node_graph"].max()) <= 1
+
+
+# ---------------------------------------------------------------- graph-LayerNorm epilogue (N1) ---------------------
+def _ln_pair(f, d, heads, hops, seed):
+    cfg = dict(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d, num_ins=hops, gat_heads=heads)
+    torch.manual_seed(seed)
+    o = orc.gat_seq(**cfg).eval()
+    e = eng.gat_seq(**cfg).eval()
+    e.load_state_dict(o.state_dict())
+    oln, eln = orc.LayerNorm(f), LayerNorm(f)
+    with torch.no_grad():
+        oln.weight.fill_(1.3); oln.bias.fill_(-0.2)
+    eln.load_state_dict(oln.state_dict())
+    e.set_interleaved_layernorm(eln.to(DEV))
+    return o, oln, e.to(DEV)
+
+
+@pytest.mark.parametrize("f,d,heads,hops,graphs,n_hi,extra,hint", [
+    (300, 512, 4, 3, 9, 24, 2.0, None),      # rows staged in shared memory
+    (512, 512, 4, 5, 256, 30, 1.0, None),    # cfg2 shape (synthetic: exactly 30 nodes)
+    (64, 32, 2, 2, 5, 3, 0.0, None),         # single-node graphs: variance 0 -> bias
+    (128, 64, 8, 2, 3, 150, 5.0, 8),         # hint too small -> rows through h_out; > 512 in-edges -> per-warp path
+])
+def test_graph_layernorm_epilogue_matches_oracle(f, d, heads, hops, graphs, n_hi, extra, hint):
+    o, oln, e = _ln_pair(f, d, heads, hops, seed=7)
+    if graphs == 256:
+        ei, batch, _ = synthetic_topology(256, 30, 60, seed=3)
+    else:
+        ei, batch = random_graphs(graphs, 1, n_hi, extra, seed=4, isolated=True)
+    g = torch.Generator().manual_seed(5)
+    args = (torch.randn(batch.numel(), f, generator=g), ei, torch.randn(ei.size(1), f, generator=g),
+            torch.randn(hops, graphs, d, generator=g), batch)
+    with torch.no_grad():
+        want, want_hops = o(*args, return_hops=True, interleaved_ln=oln)
+        dargs = [a.to(DEV) for a in args]
+        csr = GraphCSR.build(dargs[1], dargs[4], graphs, read_hints=True)
+        if hint is not None:
+            csr.max_nodes_per_graph = hint
+        got, got_hops = e(*dargs, csr=csr, return_hops=True)
+        again = e(*dargs, csr=csr)
+    for i, (a, c) in enumerate(zip(want_hops, got_hops)):
+        assert (a - c.cpu()).abs().max() <= TOL, "hop %d: %g" % (i, (a - c.cpu()).abs().max())
+    assert torch.equal(got, again)                                      # deterministic
+    # the normalised hops have zero mean / unit scale per graph up to the affine map
+    h0 = (got_hops[0].cpu() + 0.2) / 1.3
+    per_graph = torch.zeros(graphs).index_add_(0, batch, h0.sum(1)) / (torch.bincount(batch, minlength=graphs) * f)
+    assert per_graph.abs().max() <= 1e-4

@@ -135,3 +135,68 @@ def test_lcgn_seq_reference_dims_and_rng_draw():
         torch.manual_seed(12); want = o(x, ei, batch, q, lo)                  # reference-style CPU randn draw
         torch.manual_seed(12); got = e(x.to(DEV), ei.to(DEV), batch.to(DEV), q.to(DEV), lo.to(DEV)).cpu()
     assert (want - got).abs().max() <= TOL * max(1.0, float(want.abs().max()))
+
+
+# ---------------------------------------------------------------- BASELINE-size parity (cfg3, cfg5) ------------------
+def test_gine_and_gcn_conv_at_cfg3_size():
+    """BASELINE cfg3: the cfg2 batch (256 graphs x 30 nodes / 60 edges, F=512, D=512) through GINEConv / GCNConv --
+    the conv results the reference computes (and discards), against the CPU oracle at full size."""
+    from graphvqa_b200.graph_batch import synthetic_topology
+    b, f, d = 256, 512, 512
+    ei, batch, _ = synthetic_topology(b, 30, 60, seed=1234)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(batch.numel(), f, generator=g); ea = torch.randn(ei.size(1), f, generator=g)
+    ins = torch.randn(5, b, d, generator=g)
+    for name in ("gine", "gcn"):
+        torch.manual_seed(32)
+        o = getattr(orc, name + "_seq")(f, f, d).eval()
+        e = getattr(gcn_gine, name + "_seq")(f, f, d).eval()
+        e.load_state_dict(o.state_dict())
+        e = e.to(DEV)
+        with torch.no_grad():
+            if name == "gine":
+                want, want_conv = o(x, ei, ea, ins, batch, return_conv=True)
+                got, got_conv = e(x.to(DEV), ei.to(DEV), ea.to(DEV), ins.to(DEV), batch.to(DEV), return_conv=True)
+            else:
+                want, want_conv = o(x, ei, ins, batch, return_conv=True)
+                got, got_conv = e(x.to(DEV), ei.to(DEV), ins.to(DEV), batch.to(DEV), return_conv=True)
+        assert (want - got.cpu()).abs().max() <= TOL, name                       # bug-faithful sequence output
+        for i, (a, c) in enumerate(zip(want_conv, got_conv)):
+            scale = max(1.0, float(a.abs().max()))
+            assert (a - c.cpu()).abs().max() <= TOL * scale, "%s conv %d" % (name, i)
+
+
+def test_lcgn_seq_at_cfg5_per_gpu_size():
+    """BASELINE cfg5 per GPU: lcgn_seq(300 -> 512), 128 graphs x 30 nodes / 60 edges, L = 12 question tokens,
+    4 iterations, x_ctx injected; against the CPU oracle at full size."""
+    from graphvqa_b200.graph_batch import synthetic_topology
+    b = 128
+    ei, batch, _ = synthetic_topology(b, 30, 60, seed=77)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(batch.numel(), 300, generator=g)
+    q = torch.randn(b, 512, generator=g); lo = torch.randn(12, b, 512, generator=g)
+    x_ctx = torch.randn(batch.numel(), 512, generator=g)
+    torch.manual_seed(42)
+    o = orc.lcgn_seq(300, 512, 300, 5).eval()
+    e = lcgn.lcgn_seq(300, 512, 300, 5).eval()
+    e.load_state_dict(o.state_dict())
+    e = e.to(DEV)
+    with torch.no_grad():
+        want = o(x, ei, batch, q, lo, x_ctx_init=x_ctx)
+        got = e(x.to(DEV), ei.to(DEV), batch.to(DEV), q.to(DEV), lo.to(DEV), x_ctx_init=x_ctx.to(DEV)).cpu()
+    assert (want - got).abs().max() <= TOL * max(1.0, float(want.abs().max()))
+
+
+def test_affine_relu_kernel_is_batchnorm_eval_plus_relu():
+    g = torch.Generator().manual_seed(5)
+    bn = torch.nn.BatchNorm1d(300).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.1, generator=g)
+    x = torch.randn(777, 300, generator=g)
+    want = torch.relu(bn(x))
+    inv = torch.rsqrt(bn.running_var.double() + bn.eps)
+    scale = (bn.weight.double() * inv).float(); shift = (bn.bias.double() - bn.running_mean.double() * bn.weight.double() * inv).float()
+    from graphvqa_b200 import _cabi
+    got = _cabi.affine_relu(x.to(DEV), scale.to(DEV), shift.to(DEV)).cpu()
+    assert (got - want.detach()).abs().max() <= 2e-6
