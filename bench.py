@@ -225,7 +225,7 @@ def run_reference(args, rank, world):
         "graph_side": side,
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _bracketed(fn, flush, reps=24):
@@ -691,10 +691,38 @@ def run_engine(args, rank, local_rank, world):
         line["collate"] = collate
     if sharded is not None:
         line["extra"] = {"cfg4_sharded": sharded}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+class _OneJsonLine:
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner from
+    C code at communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the line goes to
+    the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.fd, (text.rstrip("\n") + "\n").encode())
+
+
+_OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
+    global _OUT
+    _OUT = _OneJsonLine()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -49,7 +49,7 @@ class GemmProblem(ctypes.Structure):
     _fields_ = [
         ("a", _c_vp), ("lda", _c_i64), ("stride_a", _c_i64), ("b_hi", _c_vp), ("b_lo", _c_vp), ("ldb", _c_i64),
         ("stride_b", _c_i64), ("c", _c_vp), ("ldc", _c_i64), ("stride_c", _c_i64), ("m", _c_i64),
-        ("n", _c_i32), ("k", _c_i32), ("batch", _c_i32),
+        ("n", _c_i32), ("k", _c_i32), ("batch", _c_i32), ("relu", _c_i32), ("bias", _c_vp),
     ]
 
 
@@ -81,6 +81,8 @@ SIGNATURES = {
     "gvqa_split_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp]),
     "gvqa_proj_gemm_3xf16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                             _c_i32, _c_vp, _c_vp]),
+    "gvqa_linear_3xf16": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_vp, _c_i32, _c_vp, _c_i64, _c_i64, _c_i32,
+                                         _c_i32, _c_vp, _c_vp]),
     "gvqa_proj_gemm_3xf16_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64,
                                                     _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
     "gvqa_proj_gemm_3xf16_grouped": (ctypes.c_int, [ctypes.POINTER(GemmProblem), _c_i32, _c_vp, _c_vp]),
@@ -91,6 +93,7 @@ SIGNATURES = {
                                               _c_i32, _c_vp]),
     "gvqa_gather_add_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_gather_add_relu_i32_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_embedding_sum_f32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_affine_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_graph_scale_rows_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp]),
     "gvqa_attention_pool_gate_f32": (ctypes.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
@@ -357,7 +360,9 @@ def split_tf32(w):
 def proj_gemm_3xtf32(a, b_hi, b_lo, out=None):
     """out[M,N] = a[M,K] @ b[N,K]^T with fp32-level accuracy on the tcgen05 tensor cores."""
     require_cuda(a, b_hi, b_lo)
-    require_f32c(b_hi=b_hi, b_lo=b_lo, out=out)
+    require_f32c(b_hi=b_hi, b_lo=b_lo)
+    if out is not None and (out.dtype != torch.float32 or out.dim() != 2 or out.stride(1) != 1):
+        raise ValueError("proj_gemm_3xtf32: out must be float32 [M,N] with unit column stride")
     if a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
         raise ValueError("proj_gemm_3xtf32: a must be float32 [M,K] with unit column stride")
     m, k = a.shape
@@ -386,10 +391,12 @@ def split_f16(w):
     return hi[:, :cols], lo[:, :cols]
 
 
-def proj_gemm_3xf16(a, b_hi, b_lo, out=None, overflow=None):
-    """out[M,N] = a[M,K] @ b[N,K]^T, fp32-level accuracy from fp16 tensor-core operands (|a| < 65504).
-    ``overflow``: optional int32[1] device tensor, set to 1 when an element of ``a`` does not fit fp16."""
-    require_cuda(a, b_hi, b_lo, overflow)
+def proj_gemm_3xf16(a, b_hi, b_lo, out=None, overflow=None, bias=None, relu=False):
+    """out[M,N] = act(a[M,K] @ b[N,K]^T + bias), fp32-level accuracy from fp16 tensor-core operands (|a| < 65504).
+    ``overflow``: optional int32[1] device tensor, set to 1 when an element of ``a`` does not fit fp16.
+    ``bias`` [N] / ``relu``: the nn.Linear epilogue fused into the GEMM's store."""
+    require_cuda(a, b_hi, b_lo, overflow, bias)
+    require_f32c(bias=bias)
     if a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
         raise ValueError("proj_gemm_3xf16: a must be float32 [M,K] with unit column stride")
     for t in (b_hi, b_lo):
@@ -400,9 +407,14 @@ def proj_gemm_3xf16(a, b_hi, b_lo, out=None, overflow=None):
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib().gvqa_proj_gemm_3xf16(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
-                                         ptr(out), out.stride(0), m, n, k, ptr(overflow), stream_handle(a.device)),
-              "gvqa_proj_gemm_3xf16")
+        if bias is None and not relu:
+            check(lib().gvqa_proj_gemm_3xf16(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
+                                             ptr(out), out.stride(0), m, n, k, ptr(overflow), stream_handle(a.device)),
+                  "gvqa_proj_gemm_3xf16")
+        else:
+            check(lib().gvqa_linear_3xf16(ptr(a), a.stride(0) if m > 1 else k, ptr(b_hi), ptr(b_lo), b_hi.stride(0),
+                                          ptr(bias), 1 if relu else 0, ptr(out), out.stride(0), m, n, k, ptr(overflow),
+                                          stream_handle(a.device)), "gvqa_linear_3xf16")
     return out
 
 
@@ -494,6 +506,22 @@ def gather_add_relu(a, b, c, bias, edge_index, relu=True):
     with torch.cuda.device(a.device):
         check(fn(ptr(a), ptr(b), ptr(c), ptr(bias), ptr(edge_index.contiguous()), ptr(out), e, f, 1 if relu else 0,
                  stream_handle(a.device)), "gvqa_gather_add_relu_f32")
+    return out
+
+
+def embedding_sum(table, tokens, sign=None):
+    """out[n] = sign[n] * sum_t table[tokens[n, t]] for tokens [N, T] (or [N]) int32 / int64; table [V, F] float32."""
+    require_cuda(table, tokens, sign)
+    require_f32c(table=table, sign=sign)
+    if tokens.dtype not in (torch.int32, torch.int64):
+        raise TypeError("embedding_sum: tokens must be int32 or int64")
+    tokens = tokens.contiguous()
+    n = tokens.size(0)
+    t = tokens.numel() // max(n, 1) if n else 1
+    out = torch.empty(n, table.size(1), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        check(lib().gvqa_embedding_sum_f32(ptr(table), table.size(0), ptr(tokens), tokens.element_size(), ptr(sign), ptr(out),
+                                           n, max(t, 1), table.size(1), stream_handle(table.device)), "gvqa_embedding_sum_f32")
     return out
 
 

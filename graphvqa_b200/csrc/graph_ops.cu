@@ -82,6 +82,33 @@ __global__ void __launch_bounds__(256) graph_scale_rows_kernel(const float* __re
   }
 }
 
+// out[n,:] = sign[n] * sum_t table[tokens[n,t],:]  -- the token-embedding sums that open the scene-graph encoder
+// (pipeline_model_gat.py:583-594: sg_vocab_embedding(x).sum(-2); the `added_sym_edge` negation of edge rows as a
+// per-row sign).  The reference materialises [N, T, F] (189 MB at cfg2) and reduces it; here one warp per row reads
+// the T table rows (the table is L2-resident) and writes F floats.
+template <typename Index>
+__global__ void __launch_bounds__(256) embedding_sum_kernel(const float* __restrict__ table, const Index* __restrict__ tokens,
+                                                            const float* __restrict__ sign, float* __restrict__ out,
+                                                            int64_t N, int T, int F, int64_t vocab) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const Index* tk = tokens + i * T;
+  const float sg = sign ? sign[i] : 1.0f;
+  for (int c4 = lane; c4 < (F >> 2); c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      int64_t id = (int64_t)tk[t];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);      // out-of-range ids are a caller bug: clamp, never fault
+      const float4 v = ldg_cached(table + id * F + 4 * c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (sign) { acc.x *= sg; acc.y *= sg; acc.z *= sg; acc.w *= sg; }
+    stg_stream(out + i * F + 4 * c4, acc);
+  }
+}
+
 // out[n,c] = act(x[n,c] * scale[c] + shift[c])  -- BatchNorm1d(eval) folded to an affine map + ReLU, the whole
 // bug-faithful GCN / GINE hop (the conv result is discarded by the reference, pipeline_model_gcn.py:660-668)
 __global__ void __launch_bounds__(256) affine_relu_kernel(const float* __restrict__ x, const float* __restrict__ scale,
@@ -195,6 +222,26 @@ extern "C" GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float
     return GVQA_ERR_MISALIGNED;
   gather_add_relu_kernel<int32_t><<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       a, b, c, bias, edge_index, out, num_edges, feat, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_embedding_sum_f32(const float* table, int64_t vocab, const void* tokens, int32_t token_bytes,
+                                               const float* sign, float* out, int64_t num_rows, int32_t tokens_per_row,
+                                               int32_t feat, void* stream_) {
+  if (num_rows < 0 || tokens_per_row <= 0 || feat <= 0 || vocab <= 0) return GVQA_ERR_BAD_SHAPE;
+  if (num_rows == 0) return GVQA_OK;
+  if (!table || !tokens || !out) return GVQA_ERR_NULL_POINTER;
+  if ((feat & 3) || (token_bytes != 4 && token_bytes != 8)) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(table) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const unsigned grid = (unsigned)((num_rows + 7) / 8);
+  if (token_bytes == 8)
+    embedding_sum_kernel<int64_t><<<grid, 256, 0, stream>>>(table, static_cast<const int64_t*>(tokens), sign, out, num_rows,
+                                                            tokens_per_row, feat, vocab);
+  else
+    embedding_sum_kernel<int32_t><<<grid, 256, 0, stream>>>(table, static_cast<const int32_t*>(tokens), sign, out, num_rows,
+                                                            tokens_per_row, feat, vocab);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }

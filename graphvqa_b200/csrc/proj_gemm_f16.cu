@@ -144,6 +144,8 @@ struct alignas(64) GroupedParams {
   int M[kMaxProblems], N[kMaxProblems], K[kMaxProblems];
   int tiles_per_batch[kMaxProblems], n_tiles[kMaxProblems];
   int tile_end[kMaxProblems];      // exclusive prefix of tiles
+  const float* bias[kMaxProblems]; // optional epilogue: C[m, n] += bias[n], then ReLU when relu != 0
+  int relu[kMaxProblems];
   int count;
   long long* trace;   // debug only (gvqa_debug_set_gemm_trace): CTA 0 records clock64() per k-block and role
   int dbg;   // debug only (gvqa_debug_set_gemm_flags): bit0 no TMA loads, bit1 converters idle, bit2 no epilogue, bit3 no MMAs
@@ -472,6 +474,18 @@ proj_gemm_3xf16_kernel(const __grid_constant__ GroupedParams g, int32_t* __restr
         mbar_arrive_leader<PAIR>(&big_empty[buf]);
       }
       if (live) {
+        // optional Linear-layer epilogue (bias, ReLU): every thread of the warp reads the same bias words (broadcast)
+        const float* bias = t.p == 0 ? g.bias[0] : (t.p == 1 ? g.bias[1] : g.bias[2]);
+        const int relu = t.p == 0 ? g.relu[0] : (t.p == 1 ? g.relu[1] : g.relu[2]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (col0 + e < N) acc[e] += __ldg(bias + col0 + e);
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) acc[e] = fmaxf(acc[e], 0.f);
+        }
         const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -577,6 +591,7 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* pr
         !make_map_3d(&g.map_c[live], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.c, q.batch, q.m, q.n, q.ldc, sc, 32, 32))
       return GVQA_ERR_CUDA;
     g.M[live] = (int)q.m; g.N[live] = q.n; g.K[live] = q.k;
+    g.bias[live] = q.bias; g.relu[live] = q.relu;
     g.n_tiles[live] = (q.n + kBN - 1) / kBN;
     g.tiles_per_batch[live] = (int)((q.m + kBM * pair - 1) / (kBM * pair)) * g.n_tiles[live];
     tiles += (int64_t)g.tiles_per_batch[live] * q.batch;
@@ -650,6 +665,17 @@ extern "C" GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda
   gvqa_gemm_problem q;
   q.a = a; q.lda = lda; q.stride_a = stride_a; q.b_hi = b_hi; q.b_lo = b_lo; q.ldb = ldb; q.stride_b = stride_b;
   q.c = c; q.ldc = ldc; q.stride_c = stride_c; q.m = m; q.n = n; q.k = k; q.batch = batch;
+  q.bias = nullptr; q.relu = 0;
+  return gvqa_proj_gemm_3xf16_grouped(&q, 1, overflow, stream_);
+}
+
+extern "C" GVQA_API int gvqa_linear_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                                          const float* bias, int32_t relu, float* c, int64_t ldc, int64_t m, int32_t n,
+                                          int32_t k, int32_t* overflow, void* stream_) {
+  gvqa_gemm_problem q;
+  q.a = a; q.lda = lda; q.stride_a = 0; q.b_hi = b_hi; q.b_lo = b_lo; q.ldb = ldb; q.stride_b = 0;
+  q.c = c; q.ldc = ldc; q.stride_c = 0; q.m = m; q.n = n; q.k = k; q.batch = 1;
+  q.bias = bias; q.relu = relu;
   return gvqa_proj_gemm_3xf16_grouped(&q, 1, overflow, stream_);
 }
 

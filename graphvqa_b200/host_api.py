@@ -67,6 +67,16 @@ class _PipelinedRunner:
         seq = self._range_seq()
         return None if seq is None else getattr(seq, "_overflow", None)
 
+    def _forward_full_range(self, dev):
+        """``_forward`` with the tf32-split projection (full fp32 range)."""
+        seq = self._range_seq()
+        prev = seq.projection
+        seq.projection = "3xtf32"
+        try:
+            return self._forward(dev)
+        finally:
+            seq.projection = prev
+
     @torch.no_grad()
     def submit(self, host):
         """Enqueue one batch (dict of CPU tensors, ideally pinned).  Returns a ticket."""
@@ -130,16 +140,10 @@ class _PipelinedRunner:
             # weight pack stays alive (gat_seq keeps one pack per projection kind), so the slots' captured graphs,
             # which hold raw pointers into it, remain valid.
             slot.flag_host.zero_()
-            seq = self._range_seq()
-            prev = seq.projection
-            seq.projection = "3xtf32"
-            try:
-                with torch.no_grad(), torch.cuda.stream(self.s_compute):
-                    dev = {k: slot.host_in[k].to(self.device, non_blocking=True) for k in self._keys}
-                    slot.out_host.copy_(self._forward(dev))
-                self.s_compute.synchronize()
-            finally:
-                seq.projection = prev
+            with torch.no_grad(), torch.cuda.stream(self.s_compute):
+                dev = {k: slot.host_in[k].to(self.device, non_blocking=True) for k in self._keys}
+                slot.out_host.copy_(self._forward_full_range(dev))
+            self.s_compute.synchronize()
         return slot.out_host
 
     def drain(self):
@@ -190,9 +194,15 @@ class GraphSideHostRunner(_PipelinedRunner):
         super().__init__(device, depth, use_cuda_graph)
 
     def _range_seq(self):
-        return getattr(self.model, "gat_seq", None)
+        return None          # the model owns one flag for gat_seq and the dense layers (see _flag)
 
-    def _forward(self, d):
+    def _flag(self):
+        return self.model._range_flag
+
+    def _forward_full_range(self, d):
+        return self._forward(d, full_range=True)
+
+    def _forward(self, d, full_range=False):
         n, b = d["rowptr"].numel() - 1, d["graph_ptr"].numel() - 1
         e = d["edge_index"].size(1)
         hints = self._hints
@@ -204,7 +214,7 @@ class GraphSideHostRunner(_PipelinedRunner):
         model = self.model
         strict, model.strict_range = model.strict_range, False      # the flag travels with the result instead
         try:
-            return model.graph_side(g, d["instr_vectors"], d["q0"].unsqueeze(0), b, csr=csr)
+            return model.graph_side(g, d["instr_vectors"], d["q0"].unsqueeze(0), b, csr=csr, full_range=full_range)
         finally:
             model.strict_range = strict
 

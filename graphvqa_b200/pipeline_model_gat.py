@@ -254,7 +254,7 @@ class _MetaLayer(nn.Module):
         agg = _cabi.segment_mean_rows(msg, d, mean=True)
         # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns
         w1 = nm.node_mlp_2[0].weight
-        hid = torch.relu_(lin(x, w1[:, :nf]).add_(lin(agg, w1[:, nf:])).add_(nm.node_mlp_2[0].bias))
+        hid = torch.relu_(lin(x, w1[:, :nf], nm.node_mlp_2[0].bias).add_(lin(agg, w1[:, nf:])))
         return lin(hid, nm.node_mlp_2[2].weight, nm.node_mlp_2[2].bias), e_new
 
 
@@ -270,21 +270,18 @@ class GroundTruth_SceneGraph_Encoder(nn.Module):
 
     def forward(self, gt_scene_graphs, csr=None):
         g = gt_scene_graphs
-        x_sum = self.sg_vocab_embedding(g.x).sum(dim=-2)
-        e_emb = self.sg_vocab_embedding(g.edge_attr)
-        sym = getattr(g, "added_sym_edge", None)
+        table = self.sg_vocab_embedding.weight.detach()
+        # token-embedding sums in one kernel each ([N,12,F] / [E,1,F] are never materialised).  The reference negates
+        # rows `added_sym_edge` of the BATCHED edge array although the indices are graph-local (Batch.from_data_list
+        # does not offset them; pipeline_model_gat.py:590): carried as a per-edge sign -- a sign flip commutes with
+        # the sum over the token slots, so this is exact.  The wire format ships that vector (`edge_sign`).
+        x_sum = _cabi.embedding_sum(table, g.x)
         sign = getattr(g, "edge_sign", None)
-        if sign is not None:
-            # wire format: the same negation as a per-edge sign vector of fixed shape (exact: a sign flip commutes
-            # with the sum over the token slots)
-            e_sum = e_emb.sum(dim=-2) * sign.unsqueeze(-1)
-        else:
-            if sym is not None and sym.numel() > 0:
-                # the reference negates rows `added_sym_edge` of the BATCHED edge array although the indices
-                # are graph-local (Batch.from_data_list does not offset them; pipeline_model_gat.py:590)
-                e_emb = e_emb.clone()
-                e_emb[sym, :, :] *= -1
-            e_sum = e_emb.sum(dim=-2)
+        sym = getattr(g, "added_sym_edge", None)
+        if sign is None and sym is not None and sym.numel() > 0:
+            sign = torch.ones(g.edge_attr.size(0), dtype=torch.float32, device=table.device)
+            sign[sym.long()] = -1.0
+        e_sum = _cabi.embedding_sum(table, g.edge_attr, sign)
         if csr is None:
             csr = _batch_csr(g, int(g.batch.max()) + 1 if getattr(g, "num_graphs", None) is None else g.num_graphs)
         x_enc, e_enc = self.scene_graph_encoding_layer(x_sum, g.edge_index, e_sum, csr)
@@ -311,8 +308,8 @@ class MyConditionalGlobalAttention(nn.Module):
         size = u.size(0) if size is None else size
         lin = self._lin                                    # node-level Linear layers on the tensor-core GEMM
         nn_, gn, qn = self.node_nn, self.gate_nn, self.ques_nn
-        x = lin(torch.relu_(lin(x, nn_[0].weight, nn_[0].bias)), nn_[2].weight, nn_[2].bias)
-        q = qn(u).contiguous()                             # [B, c]: per graph, tiny
+        x = lin(lin(x, nn_[0].weight, nn_[0].bias, relu=True), nn_[2].weight, nn_[2].bias)
+        q = lin(lin(u, qn[0].weight, qn[0].bias, relu=True), qn[2].weight, qn[2].bias)       # [B, c]
         if graph_ptr is None:
             counts = torch.bincount(batch, minlength=size)
             graph_ptr = torch.zeros(size + 1, dtype=torch.int32, device=x.device)
@@ -320,7 +317,7 @@ class MyConditionalGlobalAttention(nn.Module):
         if node_graph is None:
             node_graph = batch.to(torch.int32)
         # q[batch] * x without materialising q[batch]; then gate_nn's hidden layer on the tensor-core GEMM
-        hid = torch.relu_(lin(_cabi.graph_scale_rows(x.contiguous(), q, node_graph), gn[0].weight, gn[0].bias))
+        hid = lin(_cabi.graph_scale_rows(x.contiguous(), q, node_graph), gn[0].weight, gn[0].bias, relu=True)
         # gate_nn's Linear(c,1) + per-graph softmax (PyG semantics) + weighted sum in ONE kernel
         # (replaces a GEMV launch, scatter_max / exp / scatter_add / gathers)
         pooled, _ = _cabi.attention_pool_gate(hid, gn[2].weight, gn[2].bias, x.contiguous(),
@@ -380,6 +377,11 @@ class PipelineModel(nn.Module):
     # tf32 split when it is set -- the caller never sees an invalid result (the reference's validate() synchronises
     # per batch anyway, mainExplain_gat.py:782).  False: no sync; call ``model.gat_seq.check_overflow()`` yourself.
     strict_range = True
+    # dense_projection: the kernel behind the graph side's Linear layers (encoder MLPs, pooling, answer head):
+    # "3xf16" (default, guarded by the same device flag as gat_seq's projection) or "3xtf32" (full fp32 range)
+    dense_projection = "3xf16"
+    _range_flag = None
+    _head_lin = None
     # overlap_text: the Transformer text side (question encoder + program decoder) runs on a second CUDA stream
     # beside the scene-graph encoder and the CSR build; they join before the hop stack.
     overlap_text = True
@@ -396,33 +398,71 @@ class PipelineModel(nn.Module):
             programs_output, instr = self.program_decoder.sample(memory=questions_encoded, tgt=programs_input)
         return questions_encoded, programs_output, instr
 
-    def graph_side(self, gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr=None, encoded=None):
+    def _dense_layers(self):
+        """Every TensorCoreLinear of the graph side this module owns."""
+        if self._head_lin is None:
+            self._head_lin = _TensorCoreLinear()
+        return [self.scene_graph_encoder.scene_graph_encoding_layer._lin, self.graph_global_attention_pooling._lin,
+                self._head_lin]
+
+    def _set_projection(self, device, full_range):
+        """Point gat_seq and the dense layers at ONE device range flag and select the split: fp16 (fast) or, for
+        ``full_range``, tf32."""
+        if self._range_flag is None or self._range_flag.device != torch.device(device):
+            self._range_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        seq = getattr(self, "gat_seq", None)
+        if seq is not None:
+            seq._overflow = self._range_flag
+            seq.overflow_external = True      # this module (or the host runner above it) owns the range flag
+            if full_range and seq.projection == "3xf16":
+                self._seq_projection, seq.projection = "3xf16", "3xtf32"
+            elif not full_range and self._seq_projection is not None:
+                seq.projection, self._seq_projection = self._seq_projection, None
+        for lin in self._dense_layers():
+            lin.flag = self._range_flag
+            lin.mode = "3xtf32" if full_range else self.dense_projection
+
+    _seq_projection = None
+
+    def range_flag_set(self):
+        """Synchronising read-and-clear of the fp16 range flag (True = the last results are invalid)."""
+        if self._range_flag is None:
+            return False
+        bad = int(self._range_flag) != 0
+        if bad:
+            self._range_flag.zero_()
+        return bad
+
+    def _graph_side_once(self, g, instr_vectors, questions_encoded, num_graphs, csr, encoded):
+        if encoded is None:
+            encoded = self.scene_graph_encoder(g, csr=csr)
+        x_executed = self._execute(encoded[0], encoded[1], g, instr_vectors, questions_encoded, csr)
+        q0 = questions_encoded[0]
+        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=g.batch, size=num_graphs,
+                                                     graph_ptr=csr.graph_ptr, node_graph=csr.node_graph)
+        # logit_fc (Dropout -> Linear -> ELU -> Dropout -> Linear, :722-728; dropout is the identity in eval mode)
+        # with its two Linear layers on the tensor-core GEMM
+        fc, lin = self.logit_fc, self._head_lin
+        hid = torch.nn.functional.elu(lin(torch.cat((pooled, q0, pooled * q0), dim=-1), fc[1].weight, fc[1].bias))
+        return lin(hid, fc[4].weight, fc[4].bias).contiguous()      # (1842 columns live in a 1844-wide buffer)
+
+    def graph_side(self, gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr=None, encoded=None,
+                   full_range=False):
         """Everything between the text stack and the answer: scene-graph encoder -> hop stack -> conditional
         attention pooling -> logit_fc (pipeline_model_gat.py:751, 791-816).  ``questions_encoded`` [L,B,D] (only
         row 0 is used by the GAT / GCN / GINE variants).  Returns short_answer_logits [B, 1842]."""
         if csr is None:
             csr = _batch_csr(gt_scene_graphs, num_graphs)
-        if encoded is None:
-            encoded = self.scene_graph_encoder(gt_scene_graphs, csr=csr)
-        x_encoded, edge_attr_encoded = encoded[0], encoded[1]
-        seq = getattr(self, "gat_seq", None)
-        guarded = (self.strict_range and seq is not None and seq.projection == "3xf16"
-                   and not torch.cuda.is_current_stream_capturing())
-        if seq is not None:
-            seq.overflow_external = True      # this module (or the host runner above it) owns the range flag
-        x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors, questions_encoded, csr)
-        if guarded and seq._overflow is not None and int(seq._overflow) != 0:      # one host sync per call
-            seq._overflow.zero_()
-            seq.projection = "3xtf32"
+        self._set_projection(instr_vectors.device, full_range)
+        guarded = self.strict_range and not full_range and not torch.cuda.is_current_stream_capturing()
+        logits = self._graph_side_once(gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr, encoded)
+        if guarded and self.range_flag_set():          # one host sync per call; inputs outside fp16's range:
+            self._set_projection(instr_vectors.device, True)              # redo the graph side with the tf32 split
             try:
-                x_executed = self._execute(x_encoded, edge_attr_encoded, gt_scene_graphs, instr_vectors,
-                                           questions_encoded, csr)
+                logits = self._graph_side_once(gt_scene_graphs, instr_vectors, questions_encoded, num_graphs, csr, None)
             finally:
-                seq.projection = "3xf16"
-        q0 = questions_encoded[0]
-        pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=gt_scene_graphs.batch, size=num_graphs,
-                                                     graph_ptr=csr.graph_ptr, node_graph=csr.node_graph)
-        return self.logit_fc(torch.cat((pooled, q0, pooled * q0), dim=-1))
+                self._set_projection(instr_vectors.device, False)
+        return logits
 
     def _run(self, questions, gt_scene_graphs, programs_input, mode):
         _cabi.require_cuda(questions, gt_scene_graphs.edge_index)

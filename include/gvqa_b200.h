@@ -264,9 +264,16 @@ typedef struct gvqa_gemm_problem {
   int64_t ldc, stride_c;
   int64_t m;
   int32_t n, k, batch;     /* batch >= 1; the strides are ignored when batch == 1 */
+  int32_t relu;            /* != 0: C = max(C, 0) after the bias                                      */
+  const float* bias;       /* [n] added to every row of C (nn.Linear's bias), or NULL                 */
 } gvqa_gemm_problem;
 GVQA_API int gvqa_proj_gemm_3xf16_grouped(const gvqa_gemm_problem* problems, int32_t count, int32_t* overflow,
                                           void* stream);
+/* nn.Linear (+ ReLU) in one launch: C = act(A @ B^T + bias), bias [n] or NULL, relu 0/1 -- the dense layers of the
+ * scene-graph encoder, the attention pooling and the answer head (pipeline_model_gat.py:65-98, 126-128, 722-728). */
+GVQA_API int gvqa_linear_3xf16(const float* a, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                               const float* bias, int32_t relu, float* c, int64_t ldc, int64_t m, int32_t n, int32_t k,
+                               int32_t* overflow, void* stream);
 GVQA_API int gvqa_proj_gemm_3xf16_batched(const float* a, int64_t lda, int64_t stride_a, const void* b_hi,
                                           const void* b_lo, int64_t ldb, int64_t stride_b, float* c, int64_t ldc,
                                           int64_t stride_c, int64_t m, int32_t n, int32_t k, int32_t batch,
@@ -344,6 +351,13 @@ GVQA_API int gvqa_attention_pool_f32(const float* gate, const float* x, const in
  *  gvqa_attention_pool_gate_f32: gate[n] = <hid[n,:], w_gate> + *b_gate (gate_nn's last Linear(C,1)), then the
  *     per-graph softmax and the weighted sum of gvqa_attention_pool_f32 in the same kernel.  gate_scratch: [N]
  *     floats of device scratch (holds the gates afterwards); b_gate: ONE device float or NULL. */
+/* Token-embedding sum that opens the scene-graph encoder (pipeline_model_gat.py:583-594):
+ *   out[n,:] = (sign ? sign[n] : 1) * sum_t table[tokens[n*T + t], :]
+ * tokens: int32 (token_bytes 4, wire format) or int64 (8, the reference's layout); sign: the `added_sym_edge`
+ * negation of edge rows (:590) as a per-row +-1 vector, or NULL.  The reference materialises [N, T, F]. */
+GVQA_API int gvqa_embedding_sum_f32(const float* table, int64_t vocab, const void* tokens, int32_t token_bytes,
+                                    const float* sign, float* out, int64_t num_rows, int32_t tokens_per_row,
+                                    int32_t feat, void* stream);
 /* out[n,c] = x[n,c]*scale[c] + shift[c], then ReLU when relu != 0: BatchNorm1d(eval)+ReLU of the GCN / GINE
  * sequences (pipeline_model_gcn.py:666-668), whose conv results the reference discards.  In-place allowed. */
 GVQA_API int gvqa_affine_relu_f32(const float* x, const float* scale, const float* shift, float* out,

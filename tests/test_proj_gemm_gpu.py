@@ -79,6 +79,30 @@ def test_proj_gemm_3xf16_matches_fp64(m, n, k):
     assert err <= max(4 * float(err32), 2e-6 * scale), "3xF16 err %g vs fp32 err %g (scale %g)" % (err, err32, scale)
 
 
+@pytest.mark.parametrize("m,n,k,relu", [(256, 512, 512, True), (7680, 512, 512, False), (59, 1842, 512, True),
+                                        (15360, 300, 900, True), (256, 1842, 1536, False)])
+def test_linear_epilogue_bias_relu_in_the_gemm(m, n, k, relu):
+    """gvqa_linear_3xf16 = nn.Linear (+ ReLU) in one launch, incl. N not a multiple of 4 / 64 (the answer head's 1842
+    columns live in a 1844-wide buffer) and ragged M: against float64, and the plain product + eager epilogue."""
+    from graphvqa_b200.tc_linear import TensorCoreLinear
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    lin = TensorCoreLinear(mode="3xf16")
+    lin.flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    got = lin(a.to(DEV), w.to(DEV), b.to(DEV), relu=relu)
+    assert got.shape == (m, n) and int(lin.flag) == 0
+    want = a.double() @ w.double().t() + b.double()
+    if relu:
+        want = want.clamp(min=0)
+    assert (got.cpu().double() - want).abs().max() <= 2e-5
+    plain = lin(a.to(DEV), w.to(DEV)) + b.to(DEV)
+    assert torch.equal(got, torch.relu(plain) if relu else plain)       # same accumulators, same single rounding
+    ref = TensorCoreLinear(mode="3xtf32")(a.to(DEV), w.to(DEV), b.to(DEV), relu=relu)
+    assert (ref - got).abs().max() <= 2e-5
+
+
 def test_proj_gemm_3xf16_small_and_large_magnitudes():
     """Blocks of A/B in fp16's subnormal range (values ~1e-6) next to blocks of order 1e3-1e4: the error stays at
     fp32 level relative to each output row (tiny operands lose relative, not absolute, precision)."""
