@@ -71,6 +71,104 @@ __global__ void __launch_bounds__(kLnThreads) graph_layernorm_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Cluster version (default): a thread-block CLUSTER of S CTAs owns one graph, each CTA stages 1/S of the graph's rows in
+// its shared memory (single HBM read also for graphs far too large for one CTA: 8 x ~200 KB) and the two statistics
+// cross the cluster through distributed shared memory (mapa + ld.shared::cluster).  With one CTA per graph, 256 GQA
+// graphs are 1.7 CTAs per SM -- an unbalanced, latency-bound launch (34 % of the HBM peak at cfg2); S = 2..8 gives the
+// scheduler 512..2048 smaller CTAs.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(const float* local_smem, uint32_t rank) {
+  uint32_t addr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(smem_u32(local_smem)), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+constexpr int kLnClThreads = 256;
+
+__device__ __forceinline__ float block_sum_n(float v, float* scratch, int nwarps) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float t = lane < nwarps ? scratch[lane] : 0.f;
+  return warp_sum(t);
+}
+
+__global__ void __launch_bounds__(kLnClThreads) graph_layernorm_cluster_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ graph_ptr, const float* __restrict__ weight,
+    const float* __restrict__ bias, float* __restrict__ out, int C, float eps, int smem_floats, int S) {
+  extern __shared__ __align__(16) float buf[];
+  __shared__ float scratch[32];
+  __shared__ float part[2];              // this CTA's partial sum / partial centred square sum (read by its peers)
+  const uint32_t rank = cluster_ctarank();
+  const int g = blockIdx.x / S;
+  const int n0 = graph_ptr[g], n1 = graph_ptr[g + 1], n = n1 - n0;
+  // rows [r0, r1) of the graph belong to this CTA (balanced split; empty for tiny graphs)
+  const int per = (n + S - 1) / S;
+  const int r0 = min(n, (int)rank * per), r1 = min(n, r0 + per);
+  const int64_t count4 = (int64_t)(r1 - r0) * (C >> 2);
+  const float* xg = x + (int64_t)(n0 + r0) * C;
+  float* og = out + (int64_t)(n0 + r0) * C;
+  const bool staged = count4 * 4 <= smem_floats;
+
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < count4; i += kLnClThreads) {
+    const float4 v = ldg_stream(xg + 4 * i);
+    if (staged) *reinterpret_cast<float4*>(buf + 4 * i) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  s = block_sum_n(s, scratch, kLnClThreads / 32);
+  if (threadIdx.x == 0) part[0] = s;
+  cluster_barrier();
+  float total = 0.f;
+  for (int r = 0; r < S; ++r) total += ld_cluster_f32(&part[0], (uint32_t)r);     // same order in every CTA
+  const float norm = (float)max(n, 1) * (float)C;     // degree.clamp(min=1) * F
+  const float mean = total / norm;
+
+  float q = 0.f;
+  for (int64_t i = threadIdx.x; i < count4; i += kLnClThreads) {
+    const float4 v = staged ? *reinterpret_cast<const float4*>(buf + 4 * i)
+                            : __ldg(reinterpret_cast<const float4*>(xg + 4 * i));
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  q = block_sum_n(q, scratch, kLnClThreads / 32);
+  if (threadIdx.x == 0) part[1] = q;
+  cluster_barrier();
+  float qt = 0.f;
+  for (int r = 0; r < S; ++r) qt += ld_cluster_f32(&part[1], (uint32_t)r);
+  cluster_barrier();                     // nobody leaves (and frees its shared memory) while a peer may still read it
+  const float denom = sqrtf(qt / norm) + eps;
+  const bool affine = weight != nullptr && bias != nullptr;
+  const float w = affine ? __ldg(weight) : 1.f;
+  const float b0 = affine ? __ldg(bias) : 0.f;
+  for (int64_t i = threadIdx.x; i < count4; i += kLnClThreads) {
+    const float4 v = staged ? *reinterpret_cast<const float4*>(buf + 4 * i)
+                            : __ldg(reinterpret_cast<const float4*>(xg + 4 * i));
+    float4 o;
+    o.x = (v.x - mean) / denom; o.y = (v.y - mean) / denom;
+    o.z = (v.z - mean) / denom; o.w = (v.w - mean) / denom;
+    if (affine) {
+      o.x = o.x * w + b0; o.y = o.y * w + b0; o.z = o.z * w + b0; o.w = o.w * w + b0;
+    }
+    stg_stream(og + 4 * i, o);
+  }
+}
+
 }  // namespace gvqa
 
 extern "C" GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* graph_ptr, const float* weight,
@@ -84,6 +182,56 @@ extern "C" GVQA_API int gvqa_graph_layernorm_f32(const float* x, const int32_t* 
   if (channels & 3) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(out)) return GVQA_ERR_MISALIGNED;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // GVQA_LN_CLUSTER = S > 0 selects the cluster kernel with S CTAs per graph (-1: automatic S).  Default off: at cfg2
+  // (256 graphs of 30 x 512 floats) it measured 16.4 / 16.4 / 18.5 / 26.6 us for S = 1 / 2 / 4 / 8 against 14.3 us of
+  // the one-CTA-per-graph kernel below (profiles/r02/kernel_roofline_block_vs_warp.txt); it is the single-HBM-read
+  // path for graphs beyond one CTA's shared memory (> ~100 nodes at F = 512), where it is selected automatically.
+  static const int env_cluster = [] {
+    const char* e = getenv("GVQA_LN_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  const bool big_graphs = max_nodes_per_graph > 0 && (size_t)max_nodes_per_graph * channels * 4 > 200 * 1024;
+  if (env_cluster != 0 || big_graphs) {
+    // cluster size: enough CTAs for ~4 per SM, at most 8 (the portable maximum), and no more than the rows allow
+    const int64_t rows = max_nodes_per_graph > 0 ? max_nodes_per_graph : (num_nodes + num_graphs - 1) / num_graphs;
+    int S = 1;
+    while (S < 8 && num_graphs * S < 4 * kNumSMs && rows >= 4 * S) S *= 2;
+    // a graph that does not fit S x 200 KB needs the largest cluster
+    while (S < 8 && (size_t)((rows + S - 1) / S) * channels * 4 > 200 * 1024) S *= 2;
+    if (env_cluster > 0) S = env_cluster;
+    size_t want = (size_t)((rows + S - 1) / S) * channels * 4;
+    if (want > 200 * 1024) want = 96 * 1024;        // slices that do not fit are re-read from L2
+    if (want < 16) want = 16;
+    want = (want + 15) & ~(size_t)15;
+    static size_t configured = 0;
+    if (want > 48 * 1024 && want > configured) {
+      if (cudaFuncSetAttribute(graph_layernorm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+          cudaSuccess) {
+        (void)cudaGetLastError();
+        return GVQA_ERR_CUDA;
+      }
+      configured = 200 * 1024;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_graphs * S));
+    cfg.blockDim = dim3(kLnClThreads);
+    cfg.dynamicSmemBytes = want;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, graph_layernorm_cluster_kernel, x, graph_ptr, weight, bias, out, (int)channels, eps,
+                           (int)(want / 4), S) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return GVQA_ERR_CUDA;
+    }
+    GVQA_LAUNCH_CHECK();
+    return GVQA_OK;
+  }
   // staged buffer: the hinted largest graph if it fits, else a 96 KB default (2 CTAs/SM)
   size_t want = max_nodes_per_graph > 0 ? (size_t)max_nodes_per_graph * channels * 4 : 96 * 1024;
   if (want > 200 * 1024) want = 96 * 1024;
