@@ -28,8 +28,8 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-hop launch at cfg2 from the committed ncu --set full
 # capture (cold L2; the 15.7 MB output is still dirty in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES = 87152384
-NCU_TRAFFIC_SOURCE = "profiles/r01/hop_final_ncu_raw.csv"
+NCU_TRAFFIC_BYTES = 85176576          # 80.934 MB read + 4.242 MB written (gat_hop_slab_kernel<4,4,0>, first captured launch)
+NCU_TRAFFIC_SOURCE = "profiles/r02/hop_slab_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
 UNIT = "questions/s"
@@ -653,7 +653,10 @@ def run_engine(args, rank, local_rank, world):
         # products ride in hop 0's projection launch (grouped) or cost two launches of their own
         "gpu_launches": args.steps * (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
                                       + (1 if model.use_slabs and args.variant in (0, 5) else 0)),
-        "roofline": {"bound": "hbm", "kernel": "gat_hop_block_kernel (gvqa_gat_hop_f32)",
+        "roofline": {"bound": "hbm",
+                     "kernel": ("gat_hop_slab_kernel (gvqa_gat_hop_f32; hops 1-4; hop 0 runs gat_hop_block_kernel while the "
+                                "slabs are built)" if (model.use_slabs and args.variant in (0, 5)) else
+                                "gvqa_gat_hop_f32, variant %d" % args.variant),
                      "achieved": primary_achieved, "peak": peak, "unit": "GB/s", "frac": primary_achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo, "avg_launch_us": primary_us, "method": primary_method,
@@ -662,7 +665,8 @@ def run_engine(args, rank, local_rank, world):
                      "in_graph_bracketed_us": hop_graph_bracket_us,
                      "note": "in_graph_differential: median over 15 interleaved rounds of (CUDA events around K replays of "
                              "the step graph minus K replays of the same graph captured without the 5 fused-hop "
-                             "launches), per hop (the launch as it runs in the timed region); in_graph_us_min_max = "
+                             "launches and without the per-batch slab build that serves them), per hop (the launch as it "
+                             "runs in the timed region); in_graph_us_min_max = "
                              "smallest and largest round.  bracketed_*: eager launches with an event pair around every hop "
                              "launch of K steps; an event pair around an empty stream position already reads ~2.7 us "
                              "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"},

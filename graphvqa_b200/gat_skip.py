@@ -94,6 +94,7 @@ class gat(nn.Module):
         else:
             self.register_parameter("bias", None)
         self._packed = None
+        self._lin = None
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -132,8 +133,14 @@ class gat(nn.Module):
         pk = self.packed()
         x = x.contiguous().float()
         edge_attr = edge_attr.contiguous().float()
-        with _strict_fp32_matmul():
-            x_l = torch.mm(x, self.lin_l.weight.t())
+        if x.size(1) % 4 == 0:      # fp32-accurate tcgen05 GEMM (tf32 split: the full fp32 range, no flag to watch)
+            if self._lin is None:
+                from .tc_linear import TensorCoreLinear
+                self._lin = TensorCoreLinear()
+            x_l = self._lin(x, self.lin_l.weight)
+        else:                       # widths the TMA descriptors cannot address: strict-fp32 library GEMM
+            with _strict_fp32_matmul():
+                x_l = torch.mm(x, self.lin_l.weight.t())
         a_node = _cabi.skinny_matmul(x, pk["v_node"])
         a_edge = _cabi.skinny_matmul(edge_attr, pk["v_edge"]) if e > 0 else x.new_zeros(1, h)
         out = torch.empty(n, c, dtype=torch.float32, device=x.device)
