@@ -884,13 +884,21 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) gat_hop_slab_k
     mbar_fence_init();
   }
   __syncthreads();
-  pdl_wait();
-  pdl_launch_dependents();
+  // the slabs are per-batch data: under programmatic dependent launch (GVQA_PDL bit 1) with the caller's promise that
+  // they are older than the predecessor kernel, their fetch starts while that kernel (the projection GEMM) drains
+  if (!p.early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   if (tid == 0) {
     const uint32_t bytes_i = (uint32_t)g.idx_stride * 4u, bytes_f = (uint32_t)g.f_stride * 4u;
     mbar_expect_tx(bar, bytes_i + bytes_f);
     bulk_g2s(idx_s, slab_idx + (size_t)blockIdx.x * g.idx_stride, bytes_i, bar);
     bulk_g2s(f_s, slab_f + (size_t)blockIdx.x * g.f_stride, bytes_f, bar);
+  }
+  if (p.early) {
+    pdl_wait();              // a_node (and x_l, h_prev below) come out of the predecessor
+    pdl_launch_dependents();
   }
   // the same trip: a_node rows of the window [w0, w1) (source logit terms a_l of every node a source can be, and the
   // target terms a_r of the CTA's own nodes)

@@ -173,22 +173,38 @@ __global__ void __launch_bounds__(256) attention_pool_kernel(float* __restrict__
   sum = 0.f;
   for (int w = 0; w < 8; ++w) sum += red[w];
   const float denom = sum + 1e-16f;
-  // pass 2: weighted sum over nodes in node order, chunks of 256 nodes staged in smem
+  // pass 2: weighted sum over the graph's nodes.  The 256 threads form G = 256 / C4 groups (2 at C = 512, 3 at 300);
+  // group r sums nodes r, r+G, ... of every 256-node chunk with eight independent row loads in flight per thread, the
+  // G partial rows are added in group order through shared memory (deterministic).  One group walking all nodes with
+  // four loads in flight was ~8 serial round trips for a 30-node graph.
+  __shared__ __align__(16) float part_s[256 * 4];
   const int C4 = C >> 2;
   for (int c_base = 0; c_base < C4; c_base += 256) {            // all threads take part in the barriers
-    const int c4 = c_base + tid;
+    const int w4 = min(256, C4 - c_base);
+    const int G = max(1, min(8, 256 / w4));
+    const int grp = tid / w4, c4 = c_base + (tid - grp * w4);
+    const bool active = grp < G;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = 0; base < n; base += 256) {
       __syncthreads();
       if (base + tid < n) w_s[tid] = expf(__ldcg(gate + n0 + base + tid) - mx) / denom;
       __syncthreads();
-      if (c4 < C4) {
+      if (active) {
         const int lim = min(256, n - base);
-#pragma unroll 4
-        for (int i = 0; i < lim; ++i) fma4(acc, w_s[i], ldg_stream(x + (int64_t)(n0 + base + i) * C + 4 * c4));
+#pragma unroll 8
+        for (int i = grp; i < lim; i += G) fma4(acc, w_s[i], ldg_stream(x + (int64_t)(n0 + base + i) * C + 4 * c4));
       }
     }
-    if (c4 < C4) stg_stream(out + (int64_t)g * C + 4 * c4, acc);
+    __syncthreads();
+    if (active) *reinterpret_cast<float4*>(part_s + 4 * tid) = acc;
+    __syncthreads();
+    if (grp == 0) {
+      for (int r = 1; r < G; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(part_s + 4 * (r * w4 + tid));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      stg_stream(out + (int64_t)g * C + 4 * c4, acc);
+    }
   }
 }
 

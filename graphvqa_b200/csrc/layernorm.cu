@@ -36,11 +36,27 @@ __global__ void __launch_bounds__(kLnThreads) graph_layernorm_kernel(
   const int64_t count4 = count >> 2;  // C % 4 == 0
   const bool staged = count <= smem_floats;
 
+  // the graph is one dependent chain (load -> mean -> variance -> store), so the load phase must be ONE round trip:
+  // eight independent 128-bit loads per thread are requested before the first is consumed (a GQA graph of 30 x 512
+  // floats is 7.5 per thread; one load per iteration left 8 KB in flight per CTA, i.e. ~8 serial DRAM latencies --
+  // ncu: 11.7 us, No Eligible 55 %, DRAM 16 %, profiles/r02/ncu_k2_layernorm.txt)
+  constexpr int kLnBatch = 8;
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < count4; i += kLnThreads) {
-    const float4 v = ldg_stream(xg + 4 * i);
-    if (staged) *reinterpret_cast<float4*>(buf + 4 * i) = v;
-    s += (v.x + v.y) + (v.z + v.w);
+  for (int64_t base = threadIdx.x; base < count4; base += (int64_t)kLnThreads * kLnBatch) {
+    float4 v[kLnBatch];
+#pragma unroll
+    for (int u = 0; u < kLnBatch; ++u) {
+      const int64_t i = base + (int64_t)u * kLnThreads;
+      v[u] = i < count4 ? ldg_stream(xg + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kLnBatch; ++u) {
+      const int64_t i = base + (int64_t)u * kLnThreads;
+      if (i < count4) {
+        if (staged) *reinterpret_cast<float4*>(buf + 4 * i) = v[u];
+        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+      }
+    }
   }
   const float norm = (float)count;  // degree.clamp(min=1) * F; count > 0 here
   const float mean = block_sum(s, scratch) / norm;
