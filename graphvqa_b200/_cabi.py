@@ -95,6 +95,8 @@ SIGNATURES = {
     "gvqa_gather_add_relu_i32_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_embedding_sum_f32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i32, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_affine_relu_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp]),
+    "gvqa_gather_add_relu_strided_f32": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_i32, _c_vp,
+                                                        _c_i64, _c_i32, _c_i32, _c_vp]),
     "gvqa_graph_scale_rows_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_vp]),
     "gvqa_attention_pool_gate_f32": (ctypes.c_int, [_c_vp, _c_i32, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64,
                                                     _c_i32, _c_vp]),
@@ -446,8 +448,12 @@ def proj_gemm_3xf16_grouped(problems, overflow=None):
     arr = (GemmProblem * len(problems))()
     outs = []
     device = problems[0][0].device
-    for q, (a, b_hi, b_lo, out) in zip(arr, problems):
-        require_cuda(a, b_hi, b_lo, out, overflow)
+    for q, prob in zip(arr, problems):
+        a, b_hi, b_lo, out = prob[:4]
+        bias, relu = (prob[4], prob[5]) if len(prob) > 4 else (None, False)      # optional Linear epilogue
+        require_cuda(a, b_hi, b_lo, out, overflow, bias)
+        require_f32c(bias=bias)
+        q.bias, q.relu = ptr(bias), 1 if relu else 0
         if a.dtype != torch.float32 or a.dim() not in (2, 3) or a.stride(-1) != 1 or a.device != device:
             raise ValueError("proj_gemm_3xf16_grouped: a must be float32 [M,K] or [Z,M,K] with unit column stride")
         for t in (b_hi, b_lo):
@@ -467,7 +473,7 @@ def proj_gemm_3xf16_grouped(problems, overflow=None):
             (m, k), z = a.shape, 1
             n = b_hi.size(0)
             if out is None:
-                out = torch.empty(m, n, dtype=torch.float32, device=device)
+                out = torch.empty(m, (n + 3) // 4 * 4, dtype=torch.float32, device=device)[:, :n]
             q.lda, q.stride_a, q.ldb, q.stride_b, q.ldc, q.stride_c = (a.stride(0) if m > 1 else k), 0, b_hi.stride(0), 0, \
                 out.stride(0), 0
         q.a, q.b_hi, q.b_lo, q.c, q.m, q.n, q.k, q.batch = ptr(a), ptr(b_hi), ptr(b_lo), ptr(out), m, n, k, z
@@ -495,17 +501,22 @@ def l2_window(tensor, device, hit_ratio=1.0):
 
 def gather_add_relu(a, b, c, bias, edge_index, relu=True):
     """out[k] = act(a[src_k] + b[dst_k] + c[k] + bias); edge_index [2,E] int64 (reference layout) or int32 (the
-    loader-side wire format)."""
+    loader-side wire format); a / b / c float32 [., F] with unit column stride (row-strided views are fine)."""
     require_cuda(a, b, c, bias, edge_index)
-    require_f32c(a=a, b=b, c=c, bias=bias)
+    require_f32c(bias=bias)
+    for name, t in (("a", a), ("b", b), ("c", c)):
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError("gather_add_relu: %s must be float32 [., F] with unit column stride" % name)
     if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise TypeError("gather_add_relu: edge_index must be int64 or int32 [2, E]")
     e, f = edge_index.size(1), a.size(1)
     out = torch.empty(e, f, dtype=torch.float32, device=a.device)
-    fn = lib().gvqa_gather_add_relu_f32 if edge_index.dtype == torch.int64 else lib().gvqa_gather_add_relu_i32_f32
+    ld = lambda t: 0 if t is None else (t.stride(0) if t.size(0) > 1 else f)
     with torch.cuda.device(a.device):
-        check(fn(ptr(a), ptr(b), ptr(c), ptr(bias), ptr(edge_index.contiguous()), ptr(out), e, f, 1 if relu else 0,
-                 stream_handle(a.device)), "gvqa_gather_add_relu_f32")
+        check(lib().gvqa_gather_add_relu_strided_f32(ptr(a), ld(a), ptr(b), ld(b), ptr(c), ld(c), ptr(bias),
+                                                     ptr(edge_index.contiguous()), edge_index.element_size(), ptr(out), e, f,
+                                                     1 if relu else 0, stream_handle(a.device)),
+              "gvqa_gather_add_relu_strided_f32")
     return out
 
 

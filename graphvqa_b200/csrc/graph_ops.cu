@@ -14,8 +14,8 @@ namespace gvqa {
 
 template <typename Index>
 __global__ void __launch_bounds__(256) gather_add_relu_kernel(
-    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-    const float* __restrict__ bias, const Index* __restrict__ edge_index, float* __restrict__ out, int64_t E,
+    const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, const float* __restrict__ c,
+    int64_t ldc, const float* __restrict__ bias, const Index* __restrict__ edge_index, float* __restrict__ out, int64_t E,
     int F, int relu) {
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -23,13 +23,13 @@ __global__ void __launch_bounds__(256) gather_add_relu_kernel(
   const int64_t src = edge_index[k], dst = edge_index[E + k];
   const int F4 = F >> 2;
   for (int c4 = lane; c4 < F4; c4 += 32) {
-    float4 v = ldg_cached(a + src * F + 4 * c4);
+    float4 v = ldg_cached(a + src * lda + 4 * c4);
     if (b) {
-      const float4 u = ldg_cached(b + dst * F + 4 * c4);
+      const float4 u = ldg_cached(b + dst * ldb + 4 * c4);
       v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
     }
     if (c) {
-      const float4 u = ldg_stream(c + k * F + 4 * c4);
+      const float4 u = ldg_stream(c + k * ldc + 4 * c4);
       v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
     }
     if (bias) {
@@ -212,34 +212,39 @@ __global__ void __launch_bounds__(256) attention_pool_kernel(float* __restrict__
 
 using namespace gvqa;
 
+extern "C" GVQA_API int gvqa_gather_add_relu_strided_f32(const float* a, int64_t lda, const float* b, int64_t ldb,
+                                                         const float* c, int64_t ldc, const float* bias,
+                                                         const void* edge_index, int32_t index_bytes, float* out,
+                                                         int64_t num_edges, int32_t feat, int32_t relu, void* stream_) {
+  if (num_edges < 0 || feat <= 0 || lda < feat || (b && ldb < feat) || (c && ldc < feat)) return GVQA_ERR_BAD_SHAPE;
+  if (num_edges == 0) return GVQA_OK;
+  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
+  if ((feat & 3) || (index_bytes != 4 && index_bytes != 8)) return GVQA_ERR_UNSUPPORTED;
+  if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)) ||
+      (lda & 3) || (ldb & 3) || (ldc & 3))
+    return GVQA_ERR_MISALIGNED;
+  const unsigned grid = (unsigned)((num_edges + 7) / 8);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (index_bytes == 8)
+    gather_add_relu_kernel<int64_t><<<grid, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, bias,
+                                                             static_cast<const int64_t*>(edge_index), out, num_edges, feat, relu);
+  else
+    gather_add_relu_kernel<int32_t><<<grid, 256, 0, stream>>>(a, lda, b, ldb, c, ldc, bias,
+                                                             static_cast<const int32_t*>(edge_index), out, num_edges, feat, relu);
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
 extern "C" GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b, const float* c, const float* bias,
                                                  const int64_t* edge_index, float* out, int64_t num_edges,
                                                  int32_t feat, int32_t relu, void* stream_) {
-  if (num_edges < 0 || feat <= 0) return GVQA_ERR_BAD_SHAPE;
-  if (num_edges == 0) return GVQA_OK;
-  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
-  if (feat & 3) return GVQA_ERR_UNSUPPORTED;
-  if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)))
-    return GVQA_ERR_MISALIGNED;
-  gather_add_relu_kernel<int64_t><<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      a, b, c, bias, edge_index, out, num_edges, feat, relu);
-  GVQA_LAUNCH_CHECK();
-  return GVQA_OK;
+  return gvqa_gather_add_relu_strided_f32(a, feat, b, feat, c, feat, bias, edge_index, 8, out, num_edges, feat, relu, stream_);
 }
 
 extern "C" GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float* b, const float* c, const float* bias,
                                                      const int32_t* edge_index, float* out, int64_t num_edges,
                                                      int32_t feat, int32_t relu, void* stream_) {
-  if (num_edges < 0 || feat <= 0) return GVQA_ERR_BAD_SHAPE;
-  if (num_edges == 0) return GVQA_OK;
-  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
-  if (feat & 3) return GVQA_ERR_UNSUPPORTED;
-  if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)))
-    return GVQA_ERR_MISALIGNED;
-  gather_add_relu_kernel<int32_t><<<(unsigned)((num_edges + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      a, b, c, bias, edge_index, out, num_edges, feat, relu);
-  GVQA_LAUNCH_CHECK();
-  return GVQA_OK;
+  return gvqa_gather_add_relu_strided_f32(a, feat, b, feat, c, feat, bias, edge_index, 4, out, num_edges, feat, relu, stream_);
 }
 
 extern "C" GVQA_API int gvqa_embedding_sum_f32(const float* table, int64_t vocab, const void* tokens, int32_t token_bytes,

@@ -242,19 +242,23 @@ class _MetaLayer(nn.Module):
         d = csr.as_dict()
         em, nm = self.edge_model.edge_mlp, self.node_model
         lin = self._lin
+        w1e, w1n, w1m = em[0].weight, nm.node_mlp_1[0].weight, nm.node_mlp_2[0].weight
+        # every first-layer term that reads x -- edge model source / target halves, node model 1's source half, node
+        # model 2's own-node half -- is ONE GEMM over the stacked weights; the edge-feature term of the edge model is
+        # independent of it and rides in the same persistent launch
+        wx = lin.stacked([w1e[:, :nf], w1e[:, nf:2 * nf], w1n[:, :nf], w1m[:, :nf]])
+        c = w1e.size(0)
+        bx = lin.stacked_bias([c, c, w1n.size(0), nm.node_mlp_2[0].bias])
+        px, ec = lin.group([(x, wx, bx, False), (edge_attr, w1e[:, 2 * nf:], None, False)])
+        xa, xb, x1, x2 = px[:, :c], px[:, c:2 * c], px[:, 2 * c:2 * c + nf], px[:, 2 * c + nf:]
         # edge model: e' = W2 relu(W1 [x_src | x_dst | e] + b1) + b2
-        w1 = em[0].weight
-        xa, xb = lin(x, w1[:, :nf]), lin(x, w1[:, nf:2 * nf])
-        ec = lin(edge_attr, w1[:, 2 * nf:])
         e_new = lin(_cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index), em[2].weight, em[2].bias)
         # node model 1 on the UPDATED edges, mean over in-edges, node model 2 on [x | agg]
-        w1 = nm.node_mlp_1[0].weight
-        msg = lin(_cabi.gather_add_relu(lin(x, w1[:, :nf]), None, lin(e_new, w1[:, nf:]), nm.node_mlp_1[0].bias,
-                                        edge_index), nm.node_mlp_1[2].weight, nm.node_mlp_1[2].bias)
+        msg = lin(_cabi.gather_add_relu(x1, None, lin(e_new, w1n[:, nf:]), nm.node_mlp_1[0].bias, edge_index),
+                  nm.node_mlp_1[2].weight, nm.node_mlp_1[2].bias)
         agg = _cabi.segment_mean_rows(msg, d, mean=True)
-        # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns
-        w1 = nm.node_mlp_2[0].weight
-        hid = torch.relu_(lin(x, w1[:, :nf], nm.node_mlp_2[0].bias).add_(lin(agg, w1[:, nf:])))
+        # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns (x2 carries b1)
+        hid = torch.relu_(lin(agg, w1m[:, nf:]).add_(x2))
         return lin(hid, nm.node_mlp_2[2].weight, nm.node_mlp_2[2].bias), e_new
 
 
@@ -308,8 +312,9 @@ class MyConditionalGlobalAttention(nn.Module):
         size = u.size(0) if size is None else size
         lin = self._lin                                    # node-level Linear layers on the tensor-core GEMM
         nn_, gn, qn = self.node_nn, self.gate_nn, self.ques_nn
-        x = lin(lin(x, nn_[0].weight, nn_[0].bias, relu=True), nn_[2].weight, nn_[2].bias)
-        q = lin(lin(u, qn[0].weight, qn[0].bias, relu=True), qn[2].weight, qn[2].bias)       # [B, c]
+        # node_nn on the nodes and ques_nn on the questions are independent: layer by layer they share one launch
+        x, q = lin.group([(x, nn_[0].weight, nn_[0].bias, True), (u, qn[0].weight, qn[0].bias, True)])
+        x, q = lin.group([(x, nn_[2].weight, nn_[2].bias, False), (q, qn[2].weight, qn[2].bias, False)])   # q: [B, c]
         if graph_ptr is None:
             counts = torch.bincount(batch, minlength=size)
             graph_ptr = torch.zeros(size + 1, dtype=torch.int32, device=x.device)

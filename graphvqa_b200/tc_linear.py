@@ -23,6 +23,50 @@ class TensorCoreLinear:
         self.mode = mode
         self.flag = None
 
+    def _split(self, weight, f16):
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()), f16)
+        split = self._cache.get(key)
+        if split is None:
+            if len(self._cache) > 128:
+                self._cache.clear()
+            w = weight.detach().contiguous().float()
+            split = self._cache[key] = _cabi.split_f16(w) if f16 else _cabi.split_tf32(w)
+        return split
+
+    def stacked(self, weights):
+        """Row-wise concatenation of several [N_i, K] weights (cached per parameter version): Linear layers that read
+        the SAME input become one GEMM whose output columns are sliced afterwards."""
+        key = ("stack",) + tuple((w.data_ptr(), w._version, tuple(w.shape), tuple(w.stride())) for w in weights)
+        hit = self._cache.get(key)
+        if hit is None:
+            hit = self._cache[key] = torch.cat([w.detach() for w in weights]).contiguous().float()
+        return hit
+
+    def stacked_bias(self, parts):
+        """Bias of a stacked Linear: ``parts`` = tensors or ints (that many zeros), cached per parameter version."""
+        key = ("bias",) + tuple(p if isinstance(p, int) else (p.data_ptr(), p._version, p.numel()) for p in parts)
+        hit = self._cache.get(key)
+        if hit is None:
+            ref = next(p for p in parts if not isinstance(p, int))
+            hit = self._cache[key] = torch.cat([ref.new_zeros(p) if isinstance(p, int) else p.detach().float()
+                                                for p in parts]).contiguous()
+        return hit
+
+    def group(self, problems):
+        """Up to three INDEPENDENT Linear layers in one persistent launch (fp16-split mode; their tiles share the
+        waves).  ``problems``: (x, weight, bias, relu) tuples.  Returns the outputs in order."""
+        f16 = self.mode == "3xf16" and self.flag is not None
+        if not f16 or len(problems) == 1 or len(problems) > _cabi.MAX_GROUPED_PROBLEMS or \
+                any(p[0].size(0) == 0 or p[1].size(1) % 4 for p in problems):
+            return [self(*p) for p in problems]
+        packed = []
+        for x, weight, bias, relu in problems:
+            _cabi.require_cuda(x, weight, bias)
+            hi, lo = self._split(weight, True)
+            packed.append((x.contiguous().float(), hi, lo, None,
+                           None if bias is None else bias.detach().contiguous().float(), relu))
+        return _cabi.proj_gemm_3xf16_grouped(packed, overflow=self.flag)
+
     def __call__(self, x, weight, bias=None, relu=False):
         """x [M, K] float32 CUDA, weight [N, K] (any strides), bias [N] or None -> act(x @ weight^T + bias) [M, N]."""
         n, k = weight.shape
@@ -35,13 +79,7 @@ class TensorCoreLinear:
         if bias is not None:
             bias = bias.detach().contiguous().float()
         f16 = self.mode == "3xf16" and self.flag is not None
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()), f16)
-        split = self._cache.get(key)
-        if split is None:
-            if len(self._cache) > 128:
-                self._cache.clear()
-            w = weight.detach().contiguous().float()
-            split = self._cache[key] = _cabi.split_f16(w) if f16 else _cabi.split_tf32(w)
+        split = self._split(weight, f16)
         x = x.contiguous().float()
         # the kernels need a leading dimension that is a multiple of 4: pad the row stride, hand back a view
         out = None

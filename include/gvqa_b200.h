@@ -339,6 +339,12 @@ GVQA_API int gvqa_gather_add_relu_f32(const float* a, const float* b, const floa
 GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float* b, const float* c, const float* bias,
                                           const int32_t* edge_index, float* out, int64_t num_edges,
                                           int32_t feat, int32_t relu, void* stream);
+/* general form: a / b / c are row-strided views (lda, ldb, ldc floats, multiples of 4), e.g. column blocks of one
+ * stacked GEMM output; index_bytes 4 or 8 */
+GVQA_API int gvqa_gather_add_relu_strided_f32(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
+                                              int64_t ldc, const float* bias, const void* edge_index,
+                                              int32_t index_bytes, float* out, int64_t num_edges, int32_t feat,
+                                              int32_t relu, void* stream);
 GVQA_API int gvqa_segment_mean_rows_f32(const float* values, const int32_t* perm, const int32_t* rowptr,
                                         float* out, int64_t num_segments, int32_t feat, int32_t mean,
                                         void* stream);
