@@ -246,7 +246,7 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     return h_out
 
 
-def build_hop_slabs(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
+def build_hop_slabs(csr, a_edge_all, a_graph_all, hops, heads, num_nodes, l2_persist=False):
     """Per-batch slabs of the one-round-trip hop prologue (hop variant 5).  ``a_edge_all`` [E, >= hops*H] (hop j at
     columns j*H..), ``a_graph_all`` None or a [hops, B, H] view with unit column stride (row / hop strides free).
     Returns (slab_idx int32, slab_f float32 [hops, f_words_per_hop])."""
@@ -255,8 +255,12 @@ def build_hop_slabs(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
     plan = GatSlabPlan()
     check(lib().gvqa_gat_hop_slab_plan(num_nodes, e, heads, ctypes.byref(plan)), "gvqa_gat_hop_slab_plan")
     dev = a_edge_all.device
-    slab_idx = torch.empty(plan.idx_words, dtype=torch.int32, device=dev)
-    slab_f = torch.empty(hops, plan.f_words_per_hop, dtype=torch.float32, device=dev)
+    # one allocation (index slabs first, then the per-hop term slabs): a single L2 access-policy window can cover it
+    buf = torch.empty(plan.idx_words + hops * plan.f_words_per_hop, dtype=torch.float32, device=dev)
+    slab_idx = buf[:plan.idx_words].view(torch.int32)
+    slab_f = buf[plan.idx_words:].view(hops, plan.f_words_per_hop)
+    if l2_persist:
+        l2_window(buf, dev, 1.0)
     if a_graph_all is not None and (a_graph_all.dim() != 3 or a_graph_all.stride(2) != 1 or a_graph_all.dtype != torch.float32):
         raise ValueError("build_hop_slabs: a_graph_all must be a float32 [hops, B, H] view with unit column stride")
     with torch.cuda.device(dev):
@@ -265,6 +269,8 @@ def build_hop_slabs(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
             a_edge_all.stride(0), ptr(a_graph_all), 0 if a_graph_all is None else a_graph_all.stride(1),
             0 if a_graph_all is None else a_graph_all.stride(0), hops, num_nodes, e, heads, ptr(slab_idx), ptr(slab_f),
             stream_handle(dev)), "gvqa_gat_hop_build_slabs_f32")
+    if l2_persist:
+        l2_window(None, dev)
     return slab_idx, slab_f
 
 

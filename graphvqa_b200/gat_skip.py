@@ -196,6 +196,7 @@ class gat_seq(nn.Module):
         self.hop_events = None      # set to a list to collect (start, end) CUDA events per fused-hop launch
         self._packed = None
         self.__dict__["_interleaved_ln"] = None
+        self._slab_l2_on = None
 
     def set_interleaved_layernorm(self, layer_norm):
         """Use ``layer_norm`` (a ``my_graph_layernorm.LayerNorm``; None restores the default) instead of
@@ -366,7 +367,8 @@ class gat_seq(nn.Module):
             sstream = self._side_stream(x.device)
             sstream.wait_stream(cur)            # the pre-pass products (and, without a side CSR build, the topology)
             with torch.cuda.stream(sstream):
-                slab_idx, slab_f = _cabi.build_hop_slabs(csr_d, a_edge_all, ag3, num_hops, heads, n)
+                slab_idx, slab_f = _cabi.build_hop_slabs(csr_d, a_edge_all, ag3, num_hops, heads, n,
+                                                         l2_persist=self._slab_l2(x.device))
                 slab_ready = torch.cuda.Event()
                 slab_ready.record(sstream)
             for t in (slab_idx, slab_f):
@@ -434,6 +436,13 @@ class gat_seq(nn.Module):
         if self.projection == "3xf16" and not capturing and not self.overflow_external:
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
+
+    def _slab_l2(self, device):
+        """GVQA_SLAB_L2=1 (experiment): the slab build writes its ~6 MB through a persisting L2 access-policy window,
+        so the hop kernels' slab fetch (one per CTA, on the critical path of the prologue) hits L2 instead of DRAM."""
+        if self._slab_l2_on is None:
+            self._slab_l2_on = os.environ.get("GVQA_SLAB_L2", "0") != "0" and _cabi.l2_persist_limit(16 << 20, device) > 0
+        return self._slab_l2_on
 
     def _side_stream(self, device):
         if self._side is None or self._side.device != device:
