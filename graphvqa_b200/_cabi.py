@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgvqa_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU, EPI_GRAPH_LN = 0, 1, 2, 3
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_BLOCK, VARIANT_WS, VARIANT_SLAB = 0, 1, 2, 3, 4, 5
@@ -35,6 +35,18 @@ class GatHopArgs(ctypes.Structure):
         ("max_nodes_per_graph", _c_i32), ("max_in_edges_per_graph", _c_i32), ("variant", _c_i32),
         ("ld_graph_bias", _c_i64), ("ld_a_graph", _c_i64), ("flags", _c_i32), ("ln_eps", _c_f32),
         ("ln_weight", _c_vp), ("ln_bias", _c_vp), ("slab_idx", _c_vp), ("slab_f", _c_vp), ("sched", _c_vp),
+    ]
+
+
+class GatFusedArgs(ctypes.Structure):
+    """Mirror of ``struct gvqa_gat_fused_args``."""
+    _fields_ = [
+        ("h_in", _c_vp), ("ld_h", _c_i64), ("w_pack", _c_vp), ("tiles", _c_vp), ("tile_count", _c_vp),
+        ("rowptr", _c_vp), ("col_src", _c_vp), ("node_graph", _c_vp), ("alpha", _c_vp),
+        ("skip", _c_vp), ("ld_skip", _c_i64), ("graph_bias", _c_vp), ("ld_graph_bias", _c_i64),
+        ("bias", _c_vp), ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("overflow", _c_vp),
+        ("num_nodes", _c_i64), ("in_channels", _c_i32), ("channels", _c_i32), ("heads", _c_i32),
+        ("epilogue", _c_i32), ("window", _c_i32),
     ]
 
 
@@ -70,6 +82,17 @@ SIGNATURES = {
     "gvqa_gat_hop_slab_plan": (ctypes.c_int, [_c_i64, _c_i64, _c_i32, ctypes.POINTER(GatSlabPlan)]),
     "gvqa_gat_hop_build_slabs_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
                                                     _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
+    "gvqa_gat_fused_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32]),
+    "gvqa_gat_fused_pack_halves": (_c_i64, [_c_i32, _c_i32, _c_i32]),
+    "gvqa_gat_fused_pack_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
+    "gvqa_gat_fused_max_tiles": (_c_i64, [_c_i64, _c_i64]),
+    "gvqa_gat_fused_window": (_c_i32, [_c_i32]),
+    "gvqa_gat_fused_plan": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "gvqa_gat_fused_plan_host": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64]),
+    "gvqa_gat_alpha_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+                                          _c_f32, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
+    "gvqa_gat_fused_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatFusedArgs), _c_vp]),
+    "gvqa_debug_set_fused_trace": (None, [_c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
     "gvqa_debug_set_gemm_trace": (None, [_c_vp]),
@@ -243,6 +266,92 @@ def gat_hop(x_l, a_node, a_edge, csr, heads, channels, h_out, *, ldx=None, lde=N
     a.slab_idx, a.slab_f = ptr(slab_idx), ptr(slab_f)
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_hop_f32")
+    return h_out
+
+
+# ---- fused aggregate-project hop (gvqa_gat_fused_*) -------------------------------------------------------------
+def fused_supported(heads, in_channels, channels):
+    return bool(lib().gvqa_gat_fused_supported(heads, in_channels, channels))
+
+
+def fused_pack(w, heads, channels, in_channels):
+    """lin_l.weight ([H*C, >= F] fp32, only the first ``in_channels`` columns are used) -> packed fp16 operand of
+    gvqa_gat_fused_hop_f32."""
+    require_cuda(w)
+    if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1 or w.size(0) != heads * channels:
+        raise ValueError("fused_pack: w must be float32 [heads*channels, >= in_channels] with unit column stride")
+    out = torch.empty(lib().gvqa_gat_fused_pack_halves(heads, channels, in_channels), dtype=torch.float16, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().gvqa_gat_fused_pack_f16(ptr(w), w.stride(0), heads, channels, in_channels, ptr(out),
+                                            stream_handle(w.device)), "gvqa_gat_fused_pack_f16")
+    return out
+
+
+def fused_window(max_nodes_per_graph):
+    return lib().gvqa_gat_fused_window(int(max_nodes_per_graph))
+
+
+def fused_plan(graph_ptr, num_nodes, num_graphs, window):
+    """Per-batch row tiles of the fused hop: (tiles int32 [max_tiles, 4], count int32 [1]) on graph_ptr's device."""
+    require_cuda(graph_ptr)
+    max_tiles = lib().gvqa_gat_fused_max_tiles(num_nodes, num_graphs)
+    tiles = torch.empty(max_tiles, 4, dtype=torch.int32, device=graph_ptr.device)
+    count = torch.empty(1, dtype=torch.int32, device=graph_ptr.device)
+    with torch.cuda.device(graph_ptr.device):
+        check(lib().gvqa_gat_fused_plan(ptr(graph_ptr), num_graphs, window, ptr(tiles), ptr(count), max_tiles,
+                                        stream_handle(graph_ptr.device)), "gvqa_gat_fused_plan")
+    return tiles, count
+
+
+def fused_plan_host(graph_ptr, num_nodes, num_graphs, window, pin=False):
+    """The same plan from a host int32 graph_ptr (loader side, wire format)."""
+    if graph_ptr.is_cuda or graph_ptr.dtype != torch.int32 or not graph_ptr.is_contiguous():
+        raise ValueError("fused_plan_host: graph_ptr must be a contiguous host int32 tensor")
+    max_tiles = lib().gvqa_gat_fused_max_tiles(num_nodes, num_graphs)
+    tiles = torch.zeros(max_tiles, 4, dtype=torch.int32, pin_memory=pin)
+    count = torch.zeros(1, dtype=torch.int32, pin_memory=pin)
+    check(lib().gvqa_gat_fused_plan_host(graph_ptr.data_ptr(), num_graphs, window, tiles.data_ptr(), count.data_ptr(),
+                                         max_tiles), "gvqa_gat_fused_plan_host")
+    return tiles, count
+
+
+def gat_alpha(a_node, a_edge, csr, heads, *, lde=None, a_graph=None, negative_slope=0.2, out=None, alpha_out=None):
+    """Softmax weights of all in-edges, CSR order: alpha [E, heads]."""
+    require_cuda(a_node, a_edge, a_graph, out, alpha_out)
+    n = csr["rowptr"].numel() - 1
+    e = csr["num_edges"]
+    if out is None:
+        out = torch.empty(max(e, 1), heads, dtype=torch.float32, device=a_node.device)
+    with torch.cuda.device(a_node.device):
+        check(lib().gvqa_gat_alpha_f32(ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"]), ptr(csr["node_graph"]),
+                                       ptr(a_node), a_node.stride(0) if a_node.size(0) > 1 else a_node.size(1),
+                                       ptr(a_edge), a_edge.stride(0) if lde is None else lde,
+                                       ptr(a_graph), (a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else heads),
+                                       negative_slope, n, heads, ptr(out), ptr(alpha_out), stream_handle(a_node.device)),
+              "gvqa_gat_alpha_f32")
+    return out
+
+
+def gat_fused_hop(h_in, w_pack, plan, csr, alpha, heads, channels, h_out, *, window, skip=None, graph_bias=None,
+                  bias=None, ep_scale=None, ep_shift=None, epilogue=EPI_NONE, overflow=None):
+    require_cuda(h_in, w_pack, alpha, h_out, skip, graph_bias, bias, ep_scale, ep_shift, overflow)
+    require_f32c(h_out=h_out, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift)
+    for name, t in (("h_in", h_in), ("skip", skip), ("graph_bias", graph_bias)):
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError("gat_fused_hop: %s must be float32 2-D with unit column stride" % name)
+    a = GatFusedArgs()
+    a.h_in, a.ld_h = ptr(h_in), (h_in.stride(0) if h_in.size(0) > 1 else h_in.size(1))
+    a.w_pack, a.tiles, a.tile_count = ptr(w_pack), ptr(plan[0]), ptr(plan[1])
+    a.rowptr, a.col_src, a.node_graph, a.alpha = ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["node_graph"]), ptr(alpha)
+    a.skip = ptr(skip)
+    a.ld_skip = skip.stride(0) if skip is not None and skip.size(0) > 1 else 0
+    a.graph_bias = ptr(graph_bias)
+    a.ld_graph_bias = graph_bias.stride(0) if graph_bias is not None and graph_bias.size(0) > 1 else 0
+    a.bias, a.ep_scale, a.ep_shift, a.h_out, a.overflow = ptr(bias), ptr(ep_scale), ptr(ep_shift), ptr(h_out), ptr(overflow)
+    a.num_nodes, a.in_channels, a.channels, a.heads = h_out.size(0), h_in.size(1), channels, heads
+    a.epilogue, a.window = epilogue, window
+    with torch.cuda.device(h_out.device):
+        check(lib().gvqa_gat_fused_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_fused_hop_f32")
     return h_out
 
 

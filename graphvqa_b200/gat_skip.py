@@ -186,6 +186,10 @@ class gat_seq(nn.Module):
         # "3xf16" only: hop 0's projection and the two pre-pass products share ONE persistent launch (their short
         # tiles fill the projection's last, partially empty wave); False = three launches
         self.group_prepass = os.environ.get("GVQA_GROUP_PREPASS", "1") != "0"
+        # "fused": one tensor-core kernel per hop that aggregates the INPUT rows per head and projects the aggregate
+        # (gvqa_gat_fused_hop_f32; x_l [N, H*C] is never materialised); "split": projection GEMM + hop kernel.
+        # Shapes the fused kernel does not take (heads 8, ...) and the other projection kinds use "split".
+        self.hop_mode = os.environ.get("GVQA_HOP_MODE", "split")
         self._overflow, self._overflow_pending = None, []
         self.overflow_external = False   # True: the caller reads / clears the fp16 range flag itself (host runner)
         self._side = None
@@ -257,7 +261,10 @@ class gat_seq(nn.Module):
             ins_rows = [pad16(torch.cat([wi.t(), vg.t()])) for wi, vg in zip(w_ins, v_graph)]
             ins_split = split(torch.cat(ins_rows).contiguous())
             ins_ld = ins_rows[0].size(0)
-        pack = dict(w_h=w_h, w_split=w_split, w_ins=torch.stack(w_ins), v_node=v_node,
+        w_fused = None
+        if w_h[0].is_cuda and self.projection == "3xf16" and _cabi.fused_supported(heads, f, c):
+            w_fused = [_cabi.fused_pack(w, heads, c, f) for w in w_h]
+        pack = dict(w_h=w_h, w_split=w_split, w_fused=w_fused, w_ins=torch.stack(w_ins), v_node=v_node,
                     v_graph=torch.stack(v_graph), v_edge=v_edge_all, edge_split=edge_split,
                     ins_split=ins_split, ins_ld=ins_ld if ins_split is not None else 0,
                     scale=scale, shift=shift)
@@ -308,6 +315,10 @@ class gat_seq(nn.Module):
         else:
             def gemm(a, split, out=None):
                 return _cabi.proj_gemm_3xtf32(a, split[0], split[1], out=out)
+        if self.hop_mode == "fused" and pk.get("w_fused") is not None and self._interleaved_ln is None and n > 0 \
+                and self.gemm_events is None and not self.skip_hop_launch:
+            return self._forward_fused(x, edge_attr, ins, csr, side, csr_ready if side is not None else None, pk, flag,
+                                       return_hops)
         hc = heads * c
         fused_logits = tensor_core
         ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
@@ -434,6 +445,65 @@ class gat_seq(nn.Module):
         if self.l2_persist:
             _cabi.l2_window(None, x.device)
         if self.projection == "3xf16" and not capturing and not self.overflow_external:
+            self._queue_overflow_check()
+        return (h, hops) if return_hops else h
+
+    def _forward_fused(self, x, edge_attr, ins, csr, side, csr_ready, pk, flag, return_hops):
+        """Hops as ONE kernel each (hop_mode "fused"): per hop the collapsed node logits (skinny matvec), the softmax
+        weights of all in-edges (gvqa_gat_alpha_f32) and gvqa_gat_fused_hop_f32."""
+        num_hops = len(self.convs)
+        n, e, b = x.size(0), csr.num_edges, ins.size(1)
+        heads, c = self.convs[0].heads, self.convs[0].out_channels
+        cur = torch.cuda.current_stream(x.device)
+        # per-batch: row tiles (beside the CSR build when that runs on the side stream), pre-pass products
+        window = _cabi.fused_window(csr.max_nodes_per_graph or 256)
+        if side is not None:
+            with torch.cuda.stream(side):
+                plan = csr.fused_plan(window)
+                plan_ready = torch.cuda.Event()
+                plan_ready.record(side)
+            for t in plan:
+                t.record_stream(cur)
+        else:
+            plan, plan_ready = csr.fused_plan(window), None
+        ld = pk["ins_ld"]
+        bh, bl = (t.unflatten(0, (num_hops, ld)) for t in pk["ins_split"])
+        problems = [(ins, bh, bl, None)]
+        if e > 0:
+            problems.append((edge_attr, pk["edge_split"][0], pk["edge_split"][1], None))
+        outs = _cabi.proj_gemm_3xf16_grouped(problems, overflow=flag)
+        g_all = outs[0]
+        a_edge_all = outs[1] if e > 0 else x.new_zeros(1, num_hops * heads)
+        csr_d = csr.as_dict()
+        alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)
+        a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        h, hops = x, []
+        for i in range(num_hops):
+            _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
+            if i == 0:
+                if csr_ready is not None:
+                    cur.wait_event(csr_ready)
+                if plan_ready is not None:
+                    cur.wait_event(plan_ready)
+            _cabi.gat_alpha(a_node, a_edge_all[:, i * heads:], csr_d, heads, lde=a_edge_all.stride(0),
+                            a_graph=g_all[i, :, c:c + heads], negative_slope=self.convs[i].negative_slope, out=alpha)
+            last = i == num_hops - 1
+            epi = dict(epilogue=_cabi.EPI_NONE) if last else \
+                dict(epilogue=_cabi.EPI_AFFINE_RELU, ep_scale=pk["scale"][i], ep_shift=pk["shift"][i])
+            h_out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+            if self.hop_events is not None:
+                ext = torch.cuda.is_current_stream_capturing()
+                ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
+                ev[0].record()
+            _cabi.gat_fused_hop(h, pk["w_fused"][i], plan, csr_d, alpha, heads, c, h_out, window=window, skip=h,
+                                graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag, **epi)
+            if self.hop_events is not None:
+                ev[1].record()
+                self.hop_events.append(ev)
+            h = h_out
+            if return_hops:
+                hops.append(h)
+        if not torch.cuda.is_current_stream_capturing() and not self.overflow_external:
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
 

@@ -26,6 +26,13 @@ class GraphCSR:
         # loader hints (0 = unknown): they size the shared-memory staged kernels, never correctness
         self.max_nodes_per_graph = max_nodes_per_graph
         self.max_in_edges_per_graph = max_in_edges_per_graph
+        self._fused_plans = {}
+
+    def fused_plan(self, window):
+        """Row tiles of the fused aggregate-project hop (gvqa_gat_fused_plan), built once per batch and window."""
+        if window not in self._fused_plans:
+            self._fused_plans[window] = _cabi.fused_plan(self.graph_ptr, self.num_nodes, self.num_graphs, window)
+        return self._fused_plans[window]
 
     def hints(self):
         return dict(max_nodes_per_graph=self.max_nodes_per_graph,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GVQA_ABI_VERSION 4
+#define GVQA_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define GVQA_API __attribute__((visibility("default")))
@@ -212,6 +212,67 @@ GVQA_API int gvqa_gat_hop_build_slabs_f32(const int32_t* rowptr, const int32_t* 
                                           const float* a_graph, int64_t ld_a_graph, int64_t hop_stride_a_graph,
                                           int32_t hops, int64_t num_nodes, int64_t num_edges, int32_t heads,
                                           int32_t* slab_idx, float* slab_f, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One GAT hop as ONE tensor-core kernel ("aggregate, then project"; gat_skip.py:133-168 + :270-275).
+ * The projection lin_l is linear, so  sum_k alpha[k,h] (W_h h[src_k]) = W_h (sum_k alpha[k,h] h[src_k]):
+ * the kernel builds z[i,h,:] = sum_k alpha[k,h] h[src_k,:] tile by tile from a TMA-staged window of h rows
+ * (never stored), runs  Z[N, H*F] @ W'[C, H*F]^T  on tcgen05 with the fp16 split of gvqa_proj_gemm_3xf16, and
+ * applies the hop epilogue (head mean, graph_bias for rows with in-edges, bias, skip, affine / ReLU) to the
+ * accumulators.  x_l[N, H*C] is never materialised.  Pieces:
+ *   gvqa_gat_fused_pack_f16   once per checkpoint: lin_l.weight[:, :F] ([H*C, ldw] fp32, row h*C + c) -> packed fp16
+ *                             [C, H * Fp * 2] (Fp = F rounded up to 32; per 32 input channels 32 hi then 32 lo');
+ *                             gvqa_gat_fused_pack_halves gives the element count;
+ *   gvqa_gat_fused_plan       once per batch: row tiles {first row, rows, first window row, 0} (int32 x 4 each) from
+ *                             graph_ptr: whole graphs packed greedily into <= 128 rows; larger graphs are cut into
+ *                             128-row chunks.  `window` = gvqa_gat_fused_window(max nodes per graph) (128 or 256 rows
+ *                             of h staged per tile; sources outside it are read from global memory: never a
+ *                             correctness input).  tiles: 16-byte aligned, gvqa_gat_fused_max_tiles entries; count: one
+ *                             int32 on the device.  _host: the same plan built by the loader (wire format);
+ *   gvqa_gat_alpha_f32        per hop: softmax weights of all in-edges in CSR order, alpha[k, h] (PyG semantics,
+ *                             gat_skip.py:183-192); a_node [N, >= 2H] = (a_l | a_r), a_edge gathered through perm,
+ *                             a_graph per graph or NULL; alpha_out (optional): the same in original edge order;
+ *   gvqa_gat_fused_hop_f32    per hop.  heads in {1, 2, 4}, in_channels and channels multiples of 4
+ *                             (gvqa_gat_fused_supported), epilogue NONE / AFFINE / AFFINE_RELU.  `overflow` as in
+ *                             gvqa_proj_gemm_3xf16 (OR-ed with 1 when an aggregated input does not fit fp16). */
+typedef struct gvqa_gat_fused_args {
+  const float* h_in;        /* [N, in_channels] node states, row stride ld_h (0 = dense)                 */
+  int64_t ld_h;
+  const void* w_pack;       /* gvqa_gat_fused_pack_f16 output                                             */
+  const int32_t* tiles;     /* gvqa_gat_fused_plan                                                        */
+  const int32_t* tile_count;
+  const int32_t* rowptr;    /* destination-CSR (gvqa_build_csr)                                           */
+  const int32_t* col_src;
+  const int32_t* node_graph;
+  const float* alpha;       /* [E, heads] from gvqa_gat_alpha_f32                                         */
+  const float* skip;        /* [N, channels] added to every row (gat_skip.py:270), row stride ld_skip; or NULL */
+  int64_t ld_skip;
+  const float* graph_bias;  /* [B, channels] per-graph instruction term (rows with in-edges only) or NULL */
+  int64_t ld_graph_bias;
+  const float* bias;        /* [channels] or NULL                                                         */
+  const float* ep_scale;    /* [channels] for GVQA_EPI_AFFINE(_RELU)                                      */
+  const float* ep_shift;
+  float* h_out;             /* [N, channels] dense                                                        */
+  int32_t* overflow;        /* device int32 or NULL                                                       */
+  int64_t num_nodes;
+  int32_t in_channels, channels, heads, epilogue, window;
+} gvqa_gat_fused_args;
+GVQA_API int gvqa_gat_fused_supported(int32_t heads, int32_t in_channels, int32_t channels);
+GVQA_API int64_t gvqa_gat_fused_pack_halves(int32_t heads, int32_t channels, int32_t in_channels);
+GVQA_API int gvqa_gat_fused_pack_f16(const float* w, int64_t ldw, int32_t heads, int32_t channels,
+                                     int32_t in_channels, void* packed, void* stream);
+GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t num_graphs);
+GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph);
+GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t num_graphs, int32_t window, int32_t* tiles,
+                                 int32_t* count, int64_t max_tiles, void* stream);
+GVQA_API int gvqa_gat_fused_plan_host(const int32_t* graph_ptr_host, int64_t num_graphs, int32_t window,
+                                      int32_t* tiles_host, int32_t* count_host, int64_t max_tiles);
+GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
+                                const int32_t* node_graph, const float* a_node, int64_t ld_a_node,
+                                const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
+                                float negative_slope, int64_t num_nodes, int32_t heads, float* alpha,
+                                float* alpha_out, void* stream);
+GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-graph LayerNorm (graph_utils/my_graph_layernorm.py:52-78): statistics over all

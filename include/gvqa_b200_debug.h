@@ -23,6 +23,11 @@ GVQA_API void gvqa_debug_set_gemm_flags(int flags);
  * chunks processed, SM id, finish time of consumer warps 0..3.  NULL disables (profiles/microbench/hop_trace.py). */
 GVQA_API void gvqa_debug_set_hop_trace(unsigned long long* device_buffer);
 
+/* device buffer of 1100*8 uint64 that CTA 0 of the fused aggregate-project hop fills with clock64() stamps
+ * ([stage][0] producer, [1] converter past tma_full, [2] aggregated, [3] stored, [4]/[5] MMA past a_ready of the two
+ * sub-blocks, [7] committed; [1024 + item][0..4] accumulator hand-over); NULL = off */
+GVQA_API void gvqa_debug_set_fused_trace(unsigned long long* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif
