@@ -43,10 +43,13 @@ class GatFusedArgs(ctypes.Structure):
     _fields_ = [
         ("h_in", _c_vp), ("ld_h", _c_i64), ("w_pack", _c_vp), ("tiles", _c_vp), ("tile_count", _c_vp),
         ("rowptr", _c_vp), ("col_src", _c_vp), ("node_graph", _c_vp), ("alpha", _c_vp),
+        ("logit_terms", _c_vp), ("a_node", _c_vp), ("a_node_part_stride", _c_i64), ("a_node_parts", _c_i32),
+        ("negative_slope", _c_f32),
         ("skip", _c_vp), ("ld_skip", _c_i64), ("graph_bias", _c_vp), ("ld_graph_bias", _c_i64),
         ("bias", _c_vp), ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("overflow", _c_vp),
         ("num_nodes", _c_i64), ("in_channels", _c_i32), ("channels", _c_i32), ("heads", _c_i32),
-        ("epilogue", _c_i32), ("window", _c_i32),
+        ("epilogue", _c_i32), ("window", _c_i32), ("w_scale", _c_f32),
+        ("v_next", _c_vp), ("a_part", _c_vp), ("a_part_blocks", _c_i32),
     ]
 
 
@@ -84,14 +87,17 @@ SIGNATURES = {
                                                     _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
     "gvqa_gat_fused_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32]),
     "gvqa_gat_fused_pack_halves": (_c_i64, [_c_i32, _c_i32, _c_i32]),
-    "gvqa_gat_fused_pack_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_vp]),
+    "gvqa_gat_fused_pack_f16": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_f32, _c_vp, _c_vp]),
     "gvqa_gat_fused_max_tiles": (_c_i64, [_c_i64, _c_i64]),
+    "gvqa_gat_fused_part_blocks": (_c_i32, [_c_i64, _c_i32]),
     "gvqa_gat_fused_window": (_c_i32, [_c_i32]),
     "gvqa_gat_fused_plan": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_gat_fused_plan_host": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64]),
-    "gvqa_gat_alpha_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+    "gvqa_gat_alpha_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
                                           _c_f32, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
     "gvqa_gat_fused_hop_f32": (ctypes.c_int, [ctypes.POINTER(GatFusedArgs), _c_vp]),
+    "gvqa_gat_fused_logit_terms_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i32,
+                                                      _c_i64, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp]),
     "gvqa_debug_set_fused_trace": (None, [_c_vp]),
     "gvqa_graph_layernorm_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i32,
                                                 _c_f32, _c_i32, _c_vp]),
@@ -274,17 +280,22 @@ def fused_supported(heads, in_channels, channels):
     return bool(lib().gvqa_gat_fused_supported(heads, in_channels, channels))
 
 
-def fused_pack(w, heads, channels, in_channels):
-    """lin_l.weight ([H*C, >= F] fp32, only the first ``in_channels`` columns are used) -> packed fp16 operand of
-    gvqa_gat_fused_hop_f32."""
+def fused_pack(w, heads, channels, in_channels, scale=None):
+    """lin_l.weight ([H*C, >= F] fp32, only the first ``in_channels`` columns are used) -> (packed fp16 operand of
+    gvqa_gat_fused_hop_f32, scale).  ``scale``: power of two applied before the fp16 split (default: max|W| lands in
+    [2^8, 2^9), so the unscaled low parts stay in fp16's normal range); the hop divides it out."""
     require_cuda(w)
     if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1 or w.size(0) != heads * channels:
         raise ValueError("fused_pack: w must be float32 [heads*channels, >= in_channels] with unit column stride")
+    if scale is None:
+        import math
+        mx = float(w[:, :in_channels].abs().max()) if w.numel() else 0.0
+        scale = 2.0 ** max(-14, min(24, 8 - math.floor(math.log2(mx)))) if mx > 0 and math.isfinite(mx) else 1.0
     out = torch.empty(lib().gvqa_gat_fused_pack_halves(heads, channels, in_channels), dtype=torch.float16, device=w.device)
     with torch.cuda.device(w.device):
-        check(lib().gvqa_gat_fused_pack_f16(ptr(w), w.stride(0), heads, channels, in_channels, ptr(out),
+        check(lib().gvqa_gat_fused_pack_f16(ptr(w), w.stride(0), heads, channels, in_channels, scale, ptr(out),
                                             stream_handle(w.device)), "gvqa_gat_fused_pack_f16")
-    return out
+    return out, scale
 
 
 def fused_window(max_nodes_per_graph):
@@ -315,33 +326,66 @@ def fused_plan_host(graph_ptr, num_nodes, num_graphs, window, pin=False):
     return tiles, count
 
 
+def fused_part_blocks(num_nodes, channels):
+    return lib().gvqa_gat_fused_part_blocks(num_nodes, channels)
+
+
 def gat_alpha(a_node, a_edge, csr, heads, *, lde=None, a_graph=None, negative_slope=0.2, out=None, alpha_out=None):
-    """Softmax weights of all in-edges, CSR order: alpha [E, heads]."""
+    """Softmax weights of all in-edges, CSR order: alpha [E, heads].  ``a_node``: [N, >= 2H] node logits, or
+    [parts, N, 2H] partial sums (the fused hop's ``a_part``)."""
     require_cuda(a_node, a_edge, a_graph, out, alpha_out)
     n = csr["rowptr"].numel() - 1
     e = csr["num_edges"]
     if out is None:
         out = torch.empty(max(e, 1), heads, dtype=torch.float32, device=a_node.device)
+    parts, part_stride = 1, 0
+    if a_node.dim() == 3:
+        parts, part_stride = a_node.size(0), a_node.stride(0)
+        a_node = a_node[0]
     with torch.cuda.device(a_node.device):
         check(lib().gvqa_gat_alpha_f32(ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["perm"]), ptr(csr["node_graph"]),
                                        ptr(a_node), a_node.stride(0) if a_node.size(0) > 1 else a_node.size(1),
-                                       ptr(a_edge), a_edge.stride(0) if lde is None else lde,
+                                       parts, part_stride, ptr(a_edge), a_edge.stride(0) if lde is None else lde,
                                        ptr(a_graph), (a_graph.stride(0) if a_graph is not None and a_graph.size(0) > 1 else heads),
                                        negative_slope, n, heads, ptr(out), ptr(alpha_out), stream_handle(a_node.device)),
               "gvqa_gat_alpha_f32")
     return out
 
 
+def fused_logit_terms(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
+    """Hop-invariant logit terms of all hops in CSR order: [hops, E, heads] (gvqa_gat_fused_logit_terms_f32).
+    ``a_edge_all`` [E, >= hops*heads]; ``a_graph_all`` [hops, B, heads] (any strides with unit last stride) or None."""
+    require_cuda(a_edge_all, a_graph_all)
+    e = csr["num_edges"]
+    out = torch.empty(hops, (max(e, 1) + 3) // 4 * 4, heads, dtype=torch.float32, device=a_edge_all.device)
+    if a_graph_all is not None and (a_graph_all.dim() != 3 or a_graph_all.stride(2) != 1):
+        raise ValueError("fused_logit_terms: a_graph_all must be [hops, B, heads] with unit last stride")
+    with torch.cuda.device(out.device):
+        check(lib().gvqa_gat_fused_logit_terms_f32(
+            ptr(csr["rowptr"]), ptr(csr["perm"]), ptr(csr["node_graph"]), ptr(a_edge_all), a_edge_all.stride(0),
+            ptr(a_graph_all), a_graph_all.stride(1) if a_graph_all is not None else 0,
+            a_graph_all.stride(0) if a_graph_all is not None else 0, hops, num_nodes, e, heads, ptr(out), out.stride(0),
+            stream_handle(out.device)), "gvqa_gat_fused_logit_terms_f32")
+    return out
+
+
 def gat_fused_hop(h_in, w_pack, plan, csr, alpha, heads, channels, h_out, *, window, skip=None, graph_bias=None,
-                  bias=None, ep_scale=None, ep_shift=None, epilogue=EPI_NONE, overflow=None):
-    require_cuda(h_in, w_pack, alpha, h_out, skip, graph_bias, bias, ep_scale, ep_shift, overflow)
+                  bias=None, ep_scale=None, ep_shift=None, epilogue=EPI_NONE, overflow=None, v_next=None, a_part=None,
+                  logit_terms=None, a_node=None, negative_slope=0.2):
+    """``alpha`` [E, heads]: the softmax weights (gat_alpha) -- or, with ``logit_terms`` ([E, heads], this hop's block of
+    fused_logit_terms) and ``a_node`` ([N, 2*heads] or [parts, N, 2*heads] partial sums), scratch: the kernel computes
+    the weights in its tile prologues.  ``v_next`` [2*heads, channels] + ``a_part`` [fused_part_blocks, N, 2*heads]: the
+    epilogue also emits the next hop's node logits as partial sums."""
+    require_cuda(h_in, w_pack[0], alpha, h_out, skip, graph_bias, bias, ep_scale, ep_shift, overflow, v_next, a_part,
+                 logit_terms, a_node)
+    require_f32c(v_next=v_next, a_part=a_part, logit_terms=logit_terms, a_node=a_node, alpha=alpha)
     require_f32c(h_out=h_out, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift)
     for name, t in (("h_in", h_in), ("skip", skip), ("graph_bias", graph_bias)):
         if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
             raise ValueError("gat_fused_hop: %s must be float32 2-D with unit column stride" % name)
     a = GatFusedArgs()
     a.h_in, a.ld_h = ptr(h_in), (h_in.stride(0) if h_in.size(0) > 1 else h_in.size(1))
-    a.w_pack, a.tiles, a.tile_count = ptr(w_pack), ptr(plan[0]), ptr(plan[1])
+    a.w_pack, a.w_scale, a.tiles, a.tile_count = ptr(w_pack[0]), w_pack[1], ptr(plan[0]), ptr(plan[1])
     a.rowptr, a.col_src, a.node_graph, a.alpha = ptr(csr["rowptr"]), ptr(csr["col_src"]), ptr(csr["node_graph"]), ptr(alpha)
     a.skip = ptr(skip)
     a.ld_skip = skip.stride(0) if skip is not None and skip.size(0) > 1 else 0
@@ -350,6 +394,14 @@ def gat_fused_hop(h_in, w_pack, plan, csr, alpha, heads, channels, h_out, *, win
     a.bias, a.ep_scale, a.ep_shift, a.h_out, a.overflow = ptr(bias), ptr(ep_scale), ptr(ep_shift), ptr(h_out), ptr(overflow)
     a.num_nodes, a.in_channels, a.channels, a.heads = h_out.size(0), h_in.size(1), channels, heads
     a.epilogue, a.window = epilogue, window
+    a.v_next, a.a_part, a.a_part_blocks = ptr(v_next), ptr(a_part), (a_part.size(0) if a_part is not None else 0)
+    a.logit_terms, a.a_node, a.negative_slope = ptr(logit_terms), ptr(a_node), negative_slope
+    a.a_node_parts, a.a_node_part_stride = 1, 0
+    if a_node is not None:
+        if a_node.size(-1) != 2 * heads:
+            raise ValueError("gat_fused_hop: a_node must be [N, 2*heads] or [parts, N, 2*heads]")
+        if a_node.dim() == 3:
+            a.a_node_parts, a.a_node_part_stride = a_node.size(0), a_node.stride(0)
     with torch.cuda.device(h_out.device):
         check(lib().gvqa_gat_fused_hop_f32(ctypes.byref(a), stream_handle(h_out.device)), "gvqa_gat_fused_hop_f32")
     return h_out

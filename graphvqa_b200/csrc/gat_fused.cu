@@ -21,11 +21,13 @@
 //   warp 0       TMA producer: per k-slice of 32 input channels one stage = the [WIN x 32] fp32 window of h rows
 //                (128B swizzle) + for each head the CTA's half of the [128 x (32 hi | 32 lo')] fp16 weight tile
 //   warp 1       MMA issuer (leader CTA, one elected lane): per 16-channel sub-block 3 x H MMAs
-//   warps 2-9    converters, thread = one destination row: sum of alpha[k,h] * (16 channels of source row k) over
+//   warps 4-11   converters, thread = one destination row: sum of alpha[k,h] * (16 channels of source row k) over
 //                the in-edges for all H heads at once (packed FFMA2 from shared memory), fp16 split, tcgen05.st into
-//                a two-slot tensor-memory ring; two groups of four warps own the two sub-blocks of a stage
-//   warps 10-17  epilogue: tcgen05.ld, TMEM released, per-warp transpose through shared memory, then the hop epilogue
-//                with coalesced loads of skip / graph_bias rows and coalesced stores of h_out
+//                a four-slot tensor-memory ring; two groups of four warps alternate stages.  At the start of an item
+//                they also compute the tile's softmax weights (PyG semantics) from the hop-invariant logit terms and
+//                the node logits the previous hop's epilogue emitted
+//   warps 12-15  epilogue: tcgen05.ld, per-warp transpose through shared memory, then the hop epilogue on full
+//                128-byte row segments (skip rows prefetched by cp.async), and the NEXT hop's node logits
 // Work items = (pair of row tiles, column tile), dealt round-robin to the 74 pairs; the row tiles come from a
 // per-batch plan (gvqa_gat_fused_plan: greedy packing of whole graphs into <= 128 rows; graphs larger than 128 nodes
 // are cut into chunks that stage the whole graph as their window).
@@ -37,32 +39,37 @@
 namespace gvqa {
 namespace fused {
 
-constexpr int kBM = 128, kBN = 128, kKS = 32;
-constexpr int kStages = 3;
-constexpr int kConvWarps = 8, kEpiWarps = 8;
+constexpr int kBM = 128;
+constexpr int kKB = 16;                            // input channels per stage (x H heads)
+constexpr int kMaxNB = 256;                        // output columns per work item (one MMA column block)
+constexpr int kASlots = 4;                         // tensor-memory ring of split A sub-blocks
+constexpr int kConvWarps = 8, kEpiWarps = 4;
 constexpr int kConvThreads = kConvWarps * 32, kEpiThreads = kEpiWarps * 32;
-// Warpgroup 0 = {TMA producer, MMA issuer, two idle warps}, warpgroups 1-2 = converters, 3-4 = epilogue.  The
-// register file is per SM sub-partition (5 warps each here: 96 registers per thread at launch); warpgroup 0 hands
-// 64 registers per thread to the converters (setmaxnreg), whose 64 packed accumulators do not fit 96.
+// warps 0-3 = {TMA producer, MMA issuer, two idle warps}, 4-11 = converters, 12-15 = epilogue: 16 warps = four per SM
+// sub-partition, i.e. 128 registers per thread (the register file is per sub-partition; the converters' 64 packed
+// accumulators need ~120)
 constexpr int kFirstConvWarp = 4;
 constexpr int kFirstEpiWarp = kFirstConvWarp + kConvWarps;
-constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);     // 640
-constexpr int kRegsLean = 32, kRegsConv = 128;
-constexpr int kEdgeCap = 768;                      // in-edges of a tile staged in shared memory (more: read from global)
-constexpr uint32_t kBHeadBytes = 64 * 128;         // one head's half tile: 64 weight rows x (32 hi | 32 lo') fp16
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);     // 512
+constexpr int kEdgeCap = 640;                      // in-edges of a tile staged in shared memory (more: read from global)
+constexpr uint32_t kBBoxBytes = 128 * 128;         // one head pair's half tile: <= 128 weight rows x 2 x (16 hi | 16 lo) fp16
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemLo = 2 * kBN, kTmemA = 3 * kBN;     // accumulators [0,128) [128,256) hi*hi, [256,384) lo terms
-constexpr uint32_t kEpiStageBytes = 32 * 64;       // per epilogue warp: 32 rows x 16 columns fp32
-constexpr float kLoScale = 2048.0f, kLoUnscale = 1.0f / 2048.0f;
+constexpr uint32_t kTmemA = kMaxNB;                // accumulator [0,256), A ring [256,512)
+constexpr uint32_t kEpiStageBytes = 2 * 32 * 128;  // per epilogue warp: 32 rows x 32 columns fp32, accumulators + skip rows
 
 template <int WIN, int H>
 struct Cfg {
-  static constexpr uint32_t kABytes = WIN * 128;                        // [WIN x 32] fp32
-  static constexpr uint32_t kStageBytes = kABytes + H * kBHeadBytes;
+  static_assert(H == 2 || H == 4, "heads are staged in pairs");
+  static constexpr int kStages = WIN == 128 ? 4 : 3;                    // shared-memory ring
+  static constexpr uint32_t kABytes = WIN * 64;                         // [WIN x 16] fp32
+  static constexpr uint32_t kStageBytes = kABytes + (H / 2) * kBBoxBytes;
   static constexpr uint32_t kListBytes = kEdgeCap * (4 * H + 4) + (kBM + 4) * 4;
-  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kListBytes + 256;
+  static constexpr uint32_t kNodeLogitBytes = WIN * 2 * H * 4;          // a_l | a_r of the window rows
+  static constexpr uint32_t kConstBytes = (3 + 2 * H) * kMaxNB * 4;     // bias, scale, shift, next hop's logit vectors
+  static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kEpiWarps * kEpiStageBytes + kListBytes +
+                                  kNodeLogitBytes + kConstBytes + 256;
   static_assert(kSmem <= 232448, "shared memory budget of one CTA");
-  static_assert(kTmemA + 2 * 16 * H <= kTmemCols, "tensor-memory budget");
+  static_assert(kTmemA + kASlots * 16 * H <= kTmemCols, "tensor-memory budget");
 };
 
 struct Params {
@@ -71,7 +78,12 @@ struct Params {
   const int32_t* tile_count;
   const int32_t* rowptr;
   const int32_t* col_src;
-  const float* alpha;              // [E, H] softmax weights, CSR order
+  float* alpha;                    // [E, H] softmax weights, CSR order: input (logit_terms == NULL) or scratch
+  const float* logit_terms;        // [E, H] hop-invariant logit terms, CSR order: softmax in the tile prologue
+  const float* a_node;             // [parts][N][2H] node logits a_l | a_r (partial sums)
+  int64_t a_node_part_stride;
+  int32_t a_node_parts;
+  float slope;
   const int32_t* node_graph;
   const float* h_in;               // [N, F] (also reached through map_a); global path for sources outside the window
   int64_t ld_h;
@@ -84,8 +96,10 @@ struct Params {
   const float* ep_shift;
   float* h_out;                    // [N, C]
   int32_t* overflow;
-  int32_t N, F, C, Fp, n_ct, ks, epilogue;
-  float inv_heads;
+  int32_t N, F, C, n_ct, nb, ks, epilogue;
+  float out_scale;                 // 1 / (heads * weight scale)
+  const float* v_next;             // [2H, C] collapsed logit vectors of the NEXT hop, or NULL
+  float* a_part;                   // [n_ct][N][2H] partial node logits of the next hop (one block per column block)
   unsigned long long* trace;       // debug only
 };
 
@@ -101,11 +115,6 @@ __device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 
 __device__ __forceinline__ u64 fsub2(u64 a, u64 b) {
   u64 r;
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
-  u64 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
 __device__ __forceinline__ void lds_2x64(uint32_t addr, u64& a, u64& b) {
@@ -155,13 +164,20 @@ __device__ __forceinline__ void mma_pair(uint32_t tmem_d, uint32_t tmem_a, uint6
       : "memory");
 }
 __device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// The staged window holds [WIN x 16] fp32 = 64-byte rows under the 64-byte TMA swizzle (address bits 4-5 ^= bits 7-8):
+// 16-byte chunk c of row L lives at chunk c ^ ((L / 2) & 3) of its row.
+__device__ __forceinline__ uint32_t win_addr(uint32_t stage_a, int L, int c) {
+  return stage_a + (uint32_t)L * 64u + ((((uint32_t)c) ^ (((uint32_t)L >> 1) & 3u)) << 4);
+}
 
 // One destination row's share of a [16-channel x H-head] A sub-block: acc[h][i] = channels (2i, 2i+1) of
-// sum_k alpha[k,h] * h[src_k, 32 j + 16 c + ...].
+// sum_k alpha[k,h] * h[src_k, 16 j + ...].
 // FAST: the tile's in-edge lists are staged in shared memory and every source row lies in the staged window.
 template <int WIN, int H>
 __device__ __forceinline__ void aggregate_fast(u64 (&acc)[H][8], int eb, int ee, const int32_t* src_s, const float* alpha_s,
-                                               uint32_t stage_a, int c) {
+                                               uint32_t stage_a) {
 #pragma unroll 2
   for (int e = eb; e < ee; ++e) {
     const int L = src_s[e];
@@ -176,11 +192,10 @@ __device__ __forceinline__ void aggregate_fast(u64 (&acc)[H][8], int eb, int ee,
     u64 a2[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) a2[h] = pack2(a[h], a[h]);
-    const uint32_t ra = stage_a + (uint32_t)L * 128u, sw = (uint32_t)L & 7u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       u64 v01, v23;
-      lds_2x64(ra + ((((uint32_t)(4 * c + q)) ^ sw) << 4), v01, v23);
+      lds_2x64(win_addr(stage_a, L, q), v01, v23);
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         ffma2(acc[h][2 * q], a2[h], v01);
@@ -194,25 +209,24 @@ __device__ __forceinline__ void aggregate_fast(u64 (&acc)[H][8], int eb, int ee,
 // read from global memory
 template <int WIN, int H>
 __device__ __forceinline__ void aggregate_any(u64 (&acc)[H][8], int eb, int ee, const Params& p, int e0, int win0,
-                                              uint32_t stage_a, int c, int j) {
+                                              uint32_t stage_a, int j) {
 #pragma unroll 1
   for (int e = eb; e < ee; ++e) {
     const int L = __ldg(p.col_src + e0 + e) - win0;
     u64 a2[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      const float a = __ldg(p.alpha + (int64_t)(e0 + e) * H + h);
+      const float a = p.alpha[(int64_t)(e0 + e) * H + h];     // (may have been written by this CTA: no ld.global.nc)
       a2[h] = pack2(a, a);
     }
     const bool inside = (unsigned)L < (unsigned)WIN;
-    const uint32_t ra = stage_a + (uint32_t)L * 128u, sw = (uint32_t)L & 7u;
-    const int col = kKS * j + 16 * c;
+    const int col = kKB * j;
     const float* gp = p.h_in + (int64_t)(win0 + L) * p.ld_h + col;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       u64 v01 = 0ull, v23 = 0ull;
       if (inside) {
-        lds_2x64(ra + ((((uint32_t)(4 * c + q)) ^ sw) << 4), v01, v23);
+        lds_2x64(win_addr(stage_a, L, q), v01, v23);
       } else if (col + 4 * q < p.F) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(gp + 4 * q));
         v01 = pack2(v.x, v.y);
@@ -234,6 +248,7 @@ template <int WIN, int H>
 __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid_constant__ Params p) {
   using C_ = Cfg<WIN, H>;
   constexpr uint32_t kABytes = C_::kABytes, kStageBytes = C_::kStageBytes;
+  constexpr int kStages = C_::kStages;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* epi_stage = smem + (size_t)kStages * kStageBytes;
@@ -241,12 +256,14 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   int32_t* src_s = reinterpret_cast<int32_t*>(alpha_s + kEdgeCap * H);                     // [kEdgeCap] window-local
   int32_t* rp_s = src_s + kEdgeCap;                                                        // [kBM + 1], then a flag word
   int32_t* far_s = rp_s + kBM + 2;                        // != 0: some source of the tile lies outside the window
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rp_s + kBM + 4);
+  float* an_s = reinterpret_cast<float*>(rp_s + kBM + 4);                                  // [WIN][2H] a_l | a_r
+  float* cst_s = an_s + WIN * 2 * H;                      // [3 + 2H][kMaxNB]: bias, scale, shift, next hop's V rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cst_s + (3 + 2 * H) * kMaxNB);
   uint64_t* tma_full = bars;                    // [kStages]
   uint64_t* smem_empty = bars + kStages;        // [kStages]
-  uint64_t* a_ready = bars + 2 * kStages;       // [2]
-  uint64_t* a_empty = a_ready + 2;              // [2]
-  uint64_t* acc_full = a_empty + 2;
+  uint64_t* a_ready = bars + 2 * kStages;       // [kASlots]
+  uint64_t* a_empty = a_ready + kASlots;        // [kASlots]
+  uint64_t* acc_full = a_empty + kASlots;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       mbar_init(&tma_full[s], 1);
       mbar_init(&smem_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kASlots; ++s) {
       mbar_init(&a_ready[s], 128 * 2);            // four warps of each CTA of the pair
       mbar_init(&a_empty[s], 1);
     }
@@ -285,81 +302,75 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   const int items = ((T + 1) >> 1) * n_ct;
 
   if (warp < kFirstConvWarp) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLean));
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      uint32_t it = 0;
-      for (int item = pair_id; item < items; item += npairs) {
-        const int prt = item / n_ct, ct = item - prt * n_ct;
-        const int te = 2 * prt + rank;
-        const int win0 = te < T ? __ldg(&p.tiles[te].z) : 0;
-        const int n0 = ct * kBN;
-        const int ncols = min(kBN, (p.C - n0 + 31) & ~31);
-        const int nb0 = n0 + rank * (ncols >> 1);        // this CTA stages its half of the weight tile's rows
-        for (int j = 0; j < ks; ++j, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
-          unsigned char* st = smem + (size_t)s * kStageBytes;
-          GVQA_FUSED_TRACE(it, 0);
-          mbar_expect_tx(&tma_full[s], kStageBytes);
-          tma_load_2d(st, &p.map_a, &tma_full[s], kKS * j, win0);
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        uint32_t it = 0;
+        const uint32_t stage_tx = kABytes + (uint32_t)(H / 2) * (uint32_t)(p.nb >> 1) * 128u;
+        for (int item = pair_id; item < items; item += npairs) {
+          const int prt = item / n_ct, ct = item - prt * n_ct;
+          const int te = 2 * prt + rank;
+          const int win0 = te < T ? __ldg(&p.tiles[te].z) : 0;
+          const int n0 = ct * p.nb;
+          const int ncols = min(p.nb, (p.C - n0 + 31) & ~31);
+          const int nb0 = n0 + rank * (ncols >> 1);        // this CTA stages its half of the weight tile's rows
+          for (int j = 0; j < ks; ++j, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&smem_empty[s], ((it / kStages) & 1) ^ 1);
+            unsigned char* st = smem + (size_t)s * kStageBytes;
+            GVQA_FUSED_TRACE(it, 0);
+            mbar_expect_tx(&tma_full[s], stage_tx);
+            tma_load_2d(st, &p.map_a, &tma_full[s], kKB * j, win0);
 #pragma unroll
-          for (int h = 0; h < H; ++h)
-            tma_load_2d(st + kABytes + h * kBHeadBytes, &p.map_b, &tma_full[s], (h * p.Fp + kKS * j) * 2, nb0);
+            for (int hp = 0; hp < H / 2; ++hp)
+              tma_load_2d(st + kABytes + hp * kBBoxBytes, &p.map_b, &tma_full[s], (j * (H / 2) + hp) * 64, nb0);
+          }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
-    if (rank == 0 && elect_one()) {
-      uint32_t it = 0, item_it = 0;
-      const uint64_t desc0 = umma_desc(smem_u32(smem));
-      const uint32_t d_lo = tmem_base + kTmemLo;
-      for (int item = pair_id; item < items; item += npairs, ++item_it) {
-        const int ct = item % n_ct;
-        const int ncols = min(kBN, (p.C - ct * kBN + 31) & ~31);
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)((kBM * 2) >> 4) << 24);
-        GVQA_FUSED_TRACE(1024 + item_it, 0);
-        mbar_wait(acc_empty, (item_it & 1) ^ 1);
-        GVQA_FUSED_TRACE(1024 + item_it, 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int j = 0; j < ks; ++j, ++it) {
-          const uint32_t s = it % kStages;
-          const uint32_t d_big = tmem_base + ((j & 1) ? (uint32_t)kBN : 0u);
-          const uint64_t bstage = desc0 + (uint64_t)((s * kStageBytes + kABytes) >> 4);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            mbar_wait(&a_ready[c], it & 1);        // implies tma_full[s] in both CTAs: the converters waited on it
-            GVQA_FUSED_TRACE(it, 4 + c);
+    } else if (warp == 1) {
+      // ===================== MMA issuer (leader CTA) =====================
+      if (rank == 0 && elect_one()) {
+        uint32_t it = 0, item_it = 0;
+        const uint64_t desc0 = umma_desc(smem_u32(smem));
+        for (int item = pair_id; item < items; item += npairs, ++item_it) {
+          const int ct = item % n_ct;
+          const int ncols = min(p.nb, (p.C - ct * p.nb + 31) & ~31);
+          const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)((kBM * 2) >> 4) << 24);
+          GVQA_FUSED_TRACE(1024 + item_it, 0);
+          mbar_wait(acc_empty, (item_it & 1) ^ 1);
+          GVQA_FUSED_TRACE(1024 + item_it, 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int j = 0; j < ks; ++j, ++it) {
+            const uint32_t s = it % kStages, slot = it % kASlots;
+            const uint64_t bstage = desc0 + (uint64_t)((s * kStageBytes + kABytes) >> 4);
+            mbar_wait(&a_ready[slot], (it / kASlots) & 1);     // implies tma_full[s] in both CTAs
+            GVQA_FUSED_TRACE(it, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_slot = tmem_base + kTmemA + (uint32_t)(c * 16 * H);
+            const uint32_t a_slot = tmem_base + kTmemA + slot * (uint32_t)(16 * H);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-              const uint64_t b_hi = bstage + (uint64_t)((h * kBHeadBytes) >> 4) + 2 * c, b_lo = b_hi + 4;
+              // head pair box h/2, within a 128-byte row: head (h & 1) at +64 bytes, hi at +0, lo at +32
+              const uint64_t b_hi = bstage + (uint64_t)(((h >> 1) * kBBoxBytes) >> 4) + 4 * (h & 1), b_lo = b_hi + 2;
               const uint32_t a_hi = a_slot + 16 * h, a_lo = a_hi + 8;
-              mma_pair(d_lo, a_lo, b_hi, idesc, (j | c | h) != 0);
-              mma_pair(d_lo, a_hi, b_lo, idesc, 1);
-              mma_pair(d_big, a_hi, b_hi, idesc, !(j < 2 && c == 0 && h == 0));
+              mma_pair(tmem_base, a_lo, b_hi, idesc, (j | h) != 0);
+              mma_pair(tmem_base, a_hi, b_lo, idesc, 1);
+              mma_pair(tmem_base, a_hi, b_hi, idesc, 1);
             }
-            commit_pair(&a_empty[c]);
+            commit_pair(&a_empty[slot]);
+            commit_pair(&smem_empty[s]);
+            if (j == ks - 1) commit_pair(acc_full);
+            GVQA_FUSED_TRACE(it, 7);
           }
-          commit_pair(&smem_empty[s]);
-          if (j == ks - 1) commit_pair(acc_full);
-          GVQA_FUSED_TRACE(it, 7);
         }
       }
-    }
-  }                                                        // (two idle warps complete warpgroup 0)
+    }                                                      // (two idle warps complete warpgroup 0)
   } else if (warp < kFirstEpiWarp) {
     // ===================== converters: thread = one destination row of the tile =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConv));
     const int quarter = warp & 3;                          // TMEM lane quarter a warp may touch = warp id % 4
-    const int grp = (warp - kFirstConvWarp) >> 2;          // which 16-channel sub-block of every stage
+    const int grp = (warp - kFirstConvWarp) >> 2;          // group g converts the stages with (stage & 1) == g
     const int ctid = threadIdx.x - kFirstConvWarp * 32;
     const int r = quarter * 32 + lane;
-    const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemA + (uint32_t)(grp * 16 * H);
-    const u64 scale2 = pack2(kLoScale, kLoScale);
+    const uint32_t ta0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemA;
     uint32_t it = 0;
     float amax = 0.f;
     for (int item = pair_id; item < items; item += npairs) {
@@ -368,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       int4 tile = make_int4(0, 0, 0, 0);
       if (te < T) tile = __ldg(&p.tiles[te]);
       const int row0 = tile.x, nrows = tile.y, win0 = tile.z;
+      if (ctid == 0) GVQA_FUSED_TRACE(1060, 0);
       conv_bar_sync();                                     // the previous item's lists are no longer read
       if (ctid == 0) *far_s = 0;
       int e0 = 0, ne = 0;
@@ -377,26 +389,110 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       }
       for (int t = ctid; t <= nrows; t += kConvThreads) rp_s[t] = __ldg(p.rowptr + row0 + t) - e0;
       const bool staged = ne <= kEdgeCap;
+      const bool softmax_here = p.logit_terms != nullptr;
+      const float* lsrc = softmax_here ? p.logit_terms : p.alpha;   // what the staged list starts from
       if (staged) {
         int far = 0;
         for (int k = ctid; k < ne; k += kConvThreads) {
           const int L = __ldg(p.col_src + e0 + k) - win0;
           src_s[k] = L;
           far |= (unsigned)L >= (unsigned)WIN;
-#pragma unroll
-          for (int h = 0; h < H; ++h) alpha_s[k * H + h] = __ldg(p.alpha + (int64_t)(e0 + k) * H + h);
+          if constexpr (H == 4) {
+            *reinterpret_cast<float4*>(alpha_s + 4 * k) = __ldg(reinterpret_cast<const float4*>(lsrc) + e0 + k);
+          } else {
+            *reinterpret_cast<float2*>(alpha_s + 2 * k) = __ldg(reinterpret_cast<const float2*>(lsrc) + e0 + k);
+          }
         }
         if (far) *far_s = 1;                               // (benign race: every writer stores 1)
       }
+      if (softmax_here && nrows > 0) {
+        // node logits of the window rows, partial sums added in fixed order
+        for (int t = ctid; t < WIN * 2 * H / 4; t += kConvThreads) {
+          const int L = t / (2 * H / 4), part4 = t - L * (2 * H / 4);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (win0 + L < p.N) {
+            const float* src = p.a_node + (int64_t)(win0 + L) * (2 * H) + 4 * part4;
+            v = __ldg(reinterpret_cast<const float4*>(src));
+            for (int pt = 1; pt < p.a_node_parts; ++pt) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(src + pt * p.a_node_part_stride));
+              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+          }
+          *reinterpret_cast<float4*>(an_s + 4 * t) = v;
+        }
+      }
       conv_bar_sync();
+      if (ctid == 0) GVQA_FUSED_TRACE(1060, 1);
       const bool fast = staged && *far_s == 0;
+      if (softmax_here) {
+        if (fast) {
+          // PyG softmax per (row, head) over the row's in-edges (gat_skip.py:183-192), in place in alpha_s
+          for (int pr = ctid; pr < nrows * H; pr += kConvThreads) {
+            const int row = pr / H, h = pr - row * H;
+            const int kb = rp_s[row], ke = rp_s[row + 1];
+            const float ar = an_s[(row0 - win0 + row) * (2 * H) + H + h];
+            auto logit = [&](int k) {
+              return leaky_relu((alpha_s[k * H + h] + an_s[src_s[k] * (2 * H) + h]) + ar, p.slope);
+            };
+            if (ke - kb <= 6) {                            // the common case: every logit and exponential once
+              float l[6];
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                l[i] = kb + i < ke ? logit(kb + i) : -INFINITY;
+                mx = fmaxf(mx, l[i]);
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                l[i] = kb + i < ke ? expf(l[i] - mx) : 0.f;
+                sum += l[i];
+              }
+              const float inv = 1.0f / (sum + 1e-16f);
+#pragma unroll
+              for (int i = 0; i < 6; ++i)
+                if (kb + i < ke) alpha_s[(kb + i) * H + h] = l[i] * inv;
+            } else {
+              float mx = -INFINITY;
+              for (int k = kb; k < ke; ++k) mx = fmaxf(mx, logit(k));
+              float sum = 0.f;
+              for (int k = kb; k < ke; ++k) sum += expf(logit(k) - mx);
+              const float inv = 1.0f / (sum + 1e-16f);
+              for (int k = kb; k < ke; ++k) alpha_s[k * H + h] = expf(logit(k) - mx) * inv;
+            }
+          }
+        } else if (ctid < nrows) {
+          // generic path: one thread per row, everything from global memory, weights to the scratch array
+          auto node_term = [&](int64_t node, int col) {
+            float t = __ldg(p.a_node + node * (2 * H) + col);
+            for (int pt = 1; pt < p.a_node_parts; ++pt) t += __ldg(p.a_node + pt * p.a_node_part_stride + node * (2 * H) + col);
+            return t;
+          };
+          const int kb = e0 + rp_s[ctid], ke = e0 + rp_s[ctid + 1];
+          for (int h = 0; h < H; ++h) {
+            const float ar = node_term(row0 + ctid, H + h);
+            auto logit = [&](int k) {
+              return leaky_relu((__ldg(p.logit_terms + (int64_t)k * H + h) + node_term(__ldg(p.col_src + k), h)) + ar, p.slope);
+            };
+            float mx = -INFINITY;
+            for (int k = kb; k < ke; ++k) mx = fmaxf(mx, logit(k));
+            float sum = 0.f;
+            for (int k = kb; k < ke; ++k) sum += expf(logit(k) - mx);
+            const float inv = 1.0f / (sum + 1e-16f);
+            for (int k = kb; k < ke; ++k) p.alpha[(int64_t)k * H + h] = expf(logit(k) - mx) * inv;
+          }
+        }
+        conv_bar_sync();
+      }
+      if (ctid == 0) GVQA_FUSED_TRACE(1060, 2);
       int eb = 0, ee = 0;
       if (r < nrows) {
         eb = rp_s[r];
         ee = rp_s[r + 1];
       }
       for (int j = 0; j < ks; ++j, ++it) {
-        const int s = it % kStages;
+        if ((int)(it & 1) != grp) continue;
+        const uint32_t s = it % kStages, slot = it % kASlots;
         mbar_wait(&tma_full[s], (it / kStages) & 1);
         if (threadIdx.x == kFirstConvWarp * 32) GVQA_FUSED_TRACE(it, 1);
         const uint32_t stage_a = smem_u32(smem + (size_t)s * kStageBytes);
@@ -405,14 +501,15 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
         for (int h = 0; h < H; ++h)
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[h][i] = 0ull;
-        if (fast) aggregate_fast<WIN, H>(acc, eb, ee, src_s, alpha_s, stage_a, grp);
-        else aggregate_any<WIN, H>(acc, eb, ee, p, e0, win0, stage_a, grp, j);
+        if (fast) aggregate_fast<WIN, H>(acc, eb, ee, src_s, alpha_s, stage_a);
+        else aggregate_any<WIN, H>(acc, eb, ee, p, e0, win0, stage_a, j);
         if (threadIdx.x == kFirstConvWarp * 32) GVQA_FUSED_TRACE(it, 2);
-        mbar_wait(&a_empty[grp], (it & 1) ^ 1);            // the MMAs of the previous stage's sub-block have read the slot
+        mbar_wait(&a_empty[slot], ((it / kASlots) & 1) ^ 1);   // the MMAs that read this slot four stages ago are done
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = ta0 + slot * (uint32_t)(16 * H);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          uint32_t pk[16];                                 // [0,8) hi, [8,16) lo'; two k elements per word
+          uint32_t pk[16];                                 // [0,8) hi, [8,16) lo; two k elements per word
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float x0, x1, d0, d1;
@@ -420,25 +517,37 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
             amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
             const uint32_t h2 = pack_half2(x0, x1);
             const float2 f = unpack_half2(h2);
-            const u64 d = fmul2(fsub2(acc[h][i], pack2(f.x, f.y)), scale2);
-            unpack2(d, d0, d1);
+            unpack2(fsub2(acc[h][i], pack2(f.x, f.y)), d0, d1);
             pk[i] = h2;
-            pk[8 + i] = pack_half2(d0, d1);
+            pk[8 + i] = pack_half2(d0, d1);                // unscaled: fp16 subnormals keep 2^-24 absolute resolution
           }
           GVQA_TMEM_ST16(ta + 16 * h, pk, 0);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive_cta(&a_ready[grp], 0);
+        mbar_arrive_cta(&a_ready[slot], 0);
         if (threadIdx.x == kFirstConvWarp * 32) GVQA_FUSED_TRACE(it, 3);
       }
     }
     if (p.overflow != nullptr && !(amax <= 65000.0f)) atomicOr(p.overflow, 1);   // also catches NaN / inf
   } else {
-    // ===================== epilogue: thread = one accumulator row, 64 of the item's 128 columns =====================
+    // ===================== epilogue: warp = 32 accumulator rows x all columns of the item =====================
+    // 32 accumulator columns per pass: tcgen05.ld (thread = row) -> transpose through shared memory -> lane = (row
+    // sub-index, float4 column): every global access of a warp covers four full 128-byte row segments.  The skip
+    // rows of pass n+1 travel global -> shared by cp.async while pass n is finished; per-column constants are staged
+    // once per item (the L1 left beside ~220 KB of shared memory does not hold them).  With v_next the final values
+    // go back through the staging block and thread = row accumulates the NEXT hop's collapsed node logits
+    // a_l | a_r = h_out . V  (gat_skip.py:134-135): a_part[column block][row][2H].
     const int quarter = warp & 3;
-    const int chalf = (warp - kFirstEpiWarp) >> 2;
-    const uint32_t stage = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
+    const int etid = threadIdx.x - kFirstEpiWarp * 32;
+    const uint32_t accbuf = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
+    const uint32_t skipbuf = accbuf + 4096u;
+    const int rsub = lane >> 3, f4 = lane & 7;
+    const float* __restrict__ skip = p.skip;
+    const float* __restrict__ gbias = p.graph_bias;
+    float* __restrict__ h_out = p.h_out;
+    const bool affine = p.epilogue == GVQA_EPI_AFFINE || p.epilogue == GVQA_EPI_AFFINE_RELU;
+    const bool relu = p.epilogue == GVQA_EPI_AFFINE_RELU;
     uint32_t item_it = 0;
     for (int item = pair_id; item < items; item += npairs, ++item_it) {
       const int prt = item / n_ct, ct = item - prt * n_ct;
@@ -446,89 +555,144 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       int4 tile = make_int4(0, 0, 0, 0);
       if (te < T) tile = __ldg(&p.tiles[te]);
       const int row0 = tile.x, nrows = tile.y;
-      const int r = quarter * 32 + lane;
-      int gid = 0, has_in = 0;
-      if (r < nrows) {                                     // requested before the accumulators are ready
-        gid = __ldg(p.node_graph + row0 + r);
-        has_in = __ldg(p.rowptr + row0 + r + 1) > __ldg(p.rowptr + row0 + r);
+      const int colb = ct * p.nb;                          // first column of the item
+      const int col_end = min(p.C, colb + p.nb);
+      const int npass = (col_end - colb + 31) >> 5;
+      const int nr_w0 = nrows - quarter * 32;
+      const float* skip_base = skip ? skip + (int64_t)(row0 + quarter * 32 + rsub) * p.ld_skip + colb + 4 * f4 : p.h_in;
+      auto issue_skip = [&](int pass) {                    // skip rows of `pass` -> skipbuf (zero-filled where there is none)
+        const bool cok = skip != nullptr && colb + pass * 32 + 4 * f4 < col_end;
+        const float* src0 = skip_base + pass * 32;
+#pragma unroll
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int row = it8 * 4 + rsub;
+          const bool ok = cok && row < nr_w0;
+          const float* src = ok ? src0 + (int64_t)it8 * 4 * p.ld_skip : p.h_in;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(skipbuf + (uint32_t)row * 128u +
+                                                                            (uint32_t)((f4 ^ (row & 7)) << 4)),
+                       "l"(src), "r"(ok ? 16 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (npass > 0) issue_skip(0);
+      epi_bar_sync();                                      // the previous item's constants are no longer read
+      for (int c = etid; c < p.nb; c += kEpiThreads) {
+        const int col = colb + c;
+        const bool ok = col < p.C;
+        cst_s[c] = (ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+        cst_s[kMaxNB + c] = (ok && affine) ? __ldg(p.ep_scale + col) : 1.f;
+        cst_s[2 * kMaxNB + c] = (ok && affine) ? __ldg(p.ep_shift + col) : 0.f;
+#pragma unroll
+        for (int v = 0; v < 2 * H; ++v) cst_s[(3 + v) * kMaxNB + c] = (ok && p.v_next) ? __ldg(p.v_next + (int64_t)v * p.C + col) : 0.f;
       }
-      const int col0 = ct * kBN + chalf * 64;
-      const bool live = col0 < p.C;
+      int gid = -1;                                        // graph of the thread's own row when it takes a graph_bias
+      const int r = quarter * 32 + lane;
+      if (r < nrows && gbias && __ldg(p.rowptr + row0 + r + 1) > __ldg(p.rowptr + row0 + r)) gid = __ldg(p.node_graph + row0 + r);
+      epi_bar_sync();
+      const int nr_w = nrows - quarter * 32;               // rows of the tile in this warp's quarter
+      int grow8[8];                                        // graph (or -1) of the eight rows this lane finishes per pass
+#pragma unroll
+      for (int it8 = 0; it8 < 8; ++it8) grow8[it8] = __shfl_sync(kFull, gid, it8 * 4 + rsub);
+      float4 gbv[8];
+      auto request_gb = [&](int pass) {                    // graph_bias segments of `pass` (rows with in-edges only)
+        const int col = colb + pass * 32 + 4 * f4;
+#pragma unroll
+        for (int it8 = 0; it8 < 8; ++it8) {
+          gbv[it8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow8[it8] >= 0 && col < col_end) gbv[it8] = __ldg(reinterpret_cast<const float4*>(gbias + (int64_t)grow8[it8] * p.ldgb + col));
+        }
+      };
+      if (npass > 0) request_gb(0);
+      u64 part2[2 * H];                                    // (sum over even, over odd columns) of the logit dot products
+#pragma unroll
+      for (int v = 0; v < 2 * H; ++v) part2[v] = 0ull;
       mbar_wait(acc_full, item_it & 1);
       if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float acc[64];
-      if (live) {
-        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64);
-        const bool two = ks >= 2;
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          uint32_t rs[16], r0[16];
-          GVQA_TMEM_LD16(rs, tcol + kTmemLo + (uint32_t)(pc * 16));
-          GVQA_TMEM_LD16(r0, tcol + (uint32_t)(pc * 16));
+      const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int pass = 0; pass < npass; ++pass) {
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 0);
+        {
+          uint32_t v32[32];
+          GVQA_TMEM_LD32(v32, tcol + (uint32_t)(pass * 32));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int e = 0; e < 16; ++e) acc[pc * 16 + e] = __uint_as_float(r0[e]);
-          if (two) {
-            GVQA_TMEM_LD16(r0, tcol + kBN + (uint32_t)(pc * 16));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int e = 0; e < 16; ++e) acc[pc * 16 + e] += __uint_as_float(r0[e]);
+          if (pass == npass - 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cta(acc_empty, 0);                 // TMEM is free: the next item's MMAs may start
+            if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 3);
           }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) acc[pc * 16 + e] = fmaf(__uint_as_float(rs[e]), kLoUnscale, acc[pc * 16 + e]);
+          for (int c = 0; c < 8; ++c)
+            sts128(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), __uint_as_float(v32[4 * c]),
+                   __uint_as_float(v32[4 * c + 1]), __uint_as_float(v32[4 * c + 2]), __uint_as_float(v32[4 * c + 3]));
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive_cta(acc_empty, 0);                       // TMEM is free: the next item's MMAs may start
-      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 3);
-      if (live) {
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 2);
+        const int cl = pass * 32 + 4 * f4;                 // column inside the item
+        const int col = colb + cl;
+        const bool cvalid = col < col_end;
+        const float4 bi = *reinterpret_cast<const float4*>(cst_s + cl);
+        const float4 sc = *reinterpret_cast<const float4*>(cst_s + kMaxNB + cl);
+        const float4 sh = *reinterpret_cast<const float4*>(cst_s + 2 * kMaxNB + cl);
+        float* outp = h_out + (int64_t)(row0 + quarter * 32 + rsub) * p.C + col;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int cpass = col0 + pass * 16;
-          if (cpass < p.C) {                               // warp-uniform
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int row = it8 * 4 + rsub;
+          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((f4 ^ (row & 7)) << 4);
+          float4 t = lds128(accbuf + off);
+          const float4 sk = lds128(skipbuf + off);
+          t.x = fmaf(t.x, p.out_scale, gbv[it8].x) + bi.x + sk.x;
+          t.y = fmaf(t.y, p.out_scale, gbv[it8].y) + bi.y + sk.y;
+          t.z = fmaf(t.z, p.out_scale, gbv[it8].z) + bi.z + sk.z;
+          t.w = fmaf(t.w, p.out_scale, gbv[it8].w) + bi.w + sk.w;
+          t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);      // (scale 1, shift 0 without an affine epilogue)
+          t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+          if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+          if (row < nr_w && cvalid) *reinterpret_cast<float4*>(outp + (int64_t)it8 * 4 * p.C) = t;
+          if (p.v_next) sts128(accbuf + off, t.x, t.y, t.z, t.w);        // final values for the logit dot products
+        }
+        __syncwarp();
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 3);
+        if (pass + 1 < npass) {                            // skipbuf is free; both land while the logits are accumulated
+          issue_skip(pass + 1);
+          request_gb(pass + 1);
+        }
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 4);
+        if (p.v_next) {
+          u64 x[8][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              sts128(stage + (uint32_t)lane * 64u + (uint32_t)((q ^ ((lane >> 1) & 3)) << 4), acc[pass * 16 + 4 * q],
-                     acc[pass * 16 + 4 * q + 1], acc[pass * 16 + 4 * q + 2], acc[pass * 16 + 4 * q + 3]);
-            __syncwarp();
-            const int q = lane & 3, col = cpass + 4 * q;
+          for (int c = 0; c < 8; ++c) lds_2x64(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), x[c][0], x[c][1]);
+          const uint32_t vb = smem_u32(cst_s) + (uint32_t)(3 * kMaxNB + pass * 32) * 4u;
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const int row = i4 * 8 + (lane >> 2);
-              float4 o = lds128(stage + (uint32_t)row * 64u + (uint32_t)((q ^ ((row >> 1) & 3)) << 4));
-              const int g = __shfl_sync(kFull, gid, row), hin = __shfl_sync(kFull, has_in, row);
-              const int tr = quarter * 32 + row;
-              if (tr < nrows && col < p.C) {
-                const int64_t grow = row0 + tr;
-                o.x *= p.inv_heads; o.y *= p.inv_heads; o.z *= p.inv_heads; o.w *= p.inv_heads;
-                if (p.graph_bias && hin) {
-                  const float4 gb = __ldg(reinterpret_cast<const float4*>(p.graph_bias + (int64_t)g * p.ldgb + col));
-                  o.x += gb.x; o.y += gb.y; o.z += gb.z; o.w += gb.w;
-                }
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (p.skip) {
-                  const float4 sk = ldg_stream(p.skip + grow * p.ld_skip + col);
-                  o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
-                }
-                if (p.epilogue == GVQA_EPI_AFFINE || p.epilogue == GVQA_EPI_AFFINE_RELU) {
-                  const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ep_scale + col));
-                  const float4 sh = __ldg(reinterpret_cast<const float4*>(p.ep_shift + col));
-                  o.x = fmaf(o.x, sc.x, sh.x); o.y = fmaf(o.y, sc.y, sh.y);
-                  o.z = fmaf(o.z, sc.z, sh.z); o.w = fmaf(o.w, sc.w, sh.w);
-                  if (p.epilogue == GVQA_EPI_AFFINE_RELU) {
-                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                  }
-                }
-                *reinterpret_cast<float4*>(p.h_out + grow * p.C + col) = o;
-              }
+          for (int v = 0; v < 2 * H; ++v) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              u64 w0, w1;
+              lds_2x64(vb + (uint32_t)(v * kMaxNB + 4 * c) * 4u, w0, w1);                          // 0 past C
+              ffma2(part2[v], x[c][0], w0);
+              ffma2(part2[v], x[c][1], w1);
             }
-            __syncwarp();
           }
+          __syncwarp();                                    // the staging block may be overwritten by the next pass
         }
+        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 5);
+      }
+      if (p.v_next && r < nrows) {
+        float part[2 * H];
+#pragma unroll
+        for (int v = 0; v < 2 * H; ++v) {
+          float lo, hi;
+          unpack2(part2[v], lo, hi);
+          part[v] = lo + hi;
+        }
+        float* dst = p.a_part + ((int64_t)ct * p.N + row0 + r) * (2 * H);
+#pragma unroll
+        for (int v4 = 0; v4 < 2 * H / 4; ++v4)
+          *reinterpret_cast<float4*>(dst + 4 * v4) = make_float4(part[4 * v4], part[4 * v4 + 1], part[4 * v4 + 2], part[4 * v4 + 3]);
       }
       if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 4);
     }
@@ -588,7 +752,8 @@ __global__ void fused_plan_kernel(const int32_t* __restrict__ graph_ptr, int B, 
 template <int H>
 __global__ void __launch_bounds__(256) gat_alpha_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col_src,
                                                         const int32_t* __restrict__ perm, const int32_t* __restrict__ node_graph,
-                                                        const float* __restrict__ a_node, int64_t lda,
+                                                        const float* __restrict__ a_node, int64_t lda, int parts,
+                                                        int64_t part_stride,
                                                         const float* __restrict__ a_edge, int64_t lde,
                                                         const float* __restrict__ a_graph, int64_t ldag, float slope, int N,
                                                         float* __restrict__ alpha, float* __restrict__ alpha_out) {
@@ -599,11 +764,16 @@ __global__ void __launch_bounds__(256) gat_alpha_kernel(const int32_t* __restric
   if (i >= N) return;
   const int e0 = rowptr[i], e1 = rowptr[i + 1];
   if (e1 <= e0) return;
+  auto node_term = [&](int64_t node, int col) {           // a_node may arrive as partial sums (fixed order)
+    float t = a_node[node * lda + col];
+    for (int pt = 1; pt < parts; ++pt) t += a_node[pt * part_stride + node * lda + col];
+    return t;
+  };
   float tg = a_graph ? a_graph[(int64_t)node_graph[i] * ldag + h] : 0.f;
-  tg += a_node[(int64_t)i * lda + H + h];
+  tg += node_term(i, H + h);
   auto logit = [&](int k) {
     const int64_t e = perm ? perm[k] : k;
-    const float v = (a_edge[e * lde + h] + a_node[(int64_t)col_src[k] * lda + h]) + tg;
+    const float v = (a_edge[e * lde + h] + node_term(col_src[k], h)) + tg;
     return leaky_relu(v, slope);
   };
   float mx = -INFINITY;
@@ -618,22 +788,56 @@ __global__ void __launch_bounds__(256) gat_alpha_kernel(const int32_t* __restric
   }
 }
 
-// ---- weight prepack: W [H*C, >= F] fp32 (row h*C + c) -> [C, H * Fp * 2] fp16, per 32 input channels 32 hi | 32 lo' ----
-__global__ void fused_pack_kernel(const float* __restrict__ w, int64_t ldw, int H, int C, int F, int Fp,
+// ---- hop-invariant logit terms of all hops in CSR order (once per batch):
+//   terms[hop][k][h] = a_edge[perm[k]][hop*H + h] + a_graph[hop][graph of the edge's destination][h]
+template <int H>
+__global__ void __launch_bounds__(256) logit_terms_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                                                          const int32_t* __restrict__ node_graph,
+                                                          const float* __restrict__ a_edge, int64_t lde,
+                                                          const float* __restrict__ a_graph, int64_t ldag, int64_t hop_stride,
+                                                          int hops, int N, int64_t terms_hop_stride, float* __restrict__ terms) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t / H, h = t - i * H;
+  if (i >= N) return;
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  if (e1 <= e0) return;
+  const int g = a_graph ? node_graph[i] : 0;
+  for (int hop = 0; hop < hops; ++hop) {
+    const float tg = a_graph ? a_graph[hop * hop_stride + (int64_t)g * ldag + h] : 0.f;
+    for (int k = e0; k < e1; ++k) {
+      const int64_t e = perm ? perm[k] : k;
+      terms[hop * terms_hop_stride + (int64_t)k * H + h] = a_edge[e * lde + hop * H + h] + tg;
+    }
+  }
+}
+
+// ---- weight prepack: W [H*C, >= F] fp32 (row h*C + c) scaled by `scale` (a power of two that brings the low parts into
+// fp16's normal range) -> [C, Fp/16, H, (16 hi | 16 lo)] fp16, Fp = F rounded up to 16 ------------------------------
+__global__ void fused_pack_kernel(const float* __restrict__ w, int64_t ldw, int H, int C, int F, int Fp, float scale,
                                   __half* __restrict__ out) {
   const int64_t total = (int64_t)C * H * Fp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i / ((int64_t)H * Fp);
     const int rem = (int)(i - c * H * Fp), h = rem / Fp, k = rem - h * Fp;
-    const float x = k < F ? w[((int64_t)h * C + c) * ldw + k] : 0.f;
+    const float x = k < F ? w[((int64_t)h * C + c) * ldw + k] * scale : 0.f;
     const __half hi = __float2half_rn(x);
-    const int64_t o = c * ((int64_t)H * Fp * 2) + (int64_t)((h * Fp + k) >> 5) * 64 + (k & 31);
+    const int64_t o = c * ((int64_t)H * Fp * 2) + (int64_t)((k >> 4) * H + h) * 32 + (k & 15);
     out[o] = hi;
-    out[o + 32] = __float2half_rn((x - __half2float(hi)) * kLoScale);
+    out[o + 16] = __float2half_rn(x - __half2float(hi));
   }
 }
 
 unsigned long long* g_fused_trace = nullptr;
+
+// column blocks of a launch: as few as fit the 256-column accumulator, equal widths (multiples of 32: each CTA of a
+// pair stages half a block); one more split when the batch would otherwise leave more than half of the pairs idle
+inline void column_blocks(int64_t num_nodes, int channels, int* n_ct, int* nb) {
+  int n = (channels + kMaxNB - 1) / kMaxNB;
+  const int64_t pair_tiles = (num_nodes + 2 * kBM - 1) / (2 * kBM);
+  if (pair_tiles * n * 2 <= kNumSMs / 2 && channels / (2 * n) >= 64) n *= 2;
+  *nb = (((channels + n - 1) / n) + 31) & ~31;
+  *n_ct = (channels + *nb - 1) / *nb;
+}
 
 }  // namespace fused
 }  // namespace gvqa
@@ -644,6 +848,12 @@ extern "C" GVQA_API void gvqa_debug_set_fused_trace(unsigned long long* buf) { f
 
 extern "C" GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t num_graphs) {
   return num_graphs + (num_nodes + fused::kBM - 1) / fused::kBM + 2;
+}
+
+extern "C" GVQA_API int32_t gvqa_gat_fused_part_blocks(int64_t num_nodes, int32_t channels) {
+  int n_ct, nb;
+  fused::column_blocks(num_nodes, channels, &n_ct, &nb);
+  return n_ct;
 }
 
 extern "C" GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph) {
@@ -683,10 +893,10 @@ extern "C" GVQA_API int gvqa_gat_fused_plan_host(const int32_t* graph_ptr_host, 
 
 extern "C" GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
                                            const int32_t* node_graph, const float* a_node, int64_t ld_a_node,
-                                           const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
+                                           int32_t a_node_parts, int64_t a_node_part_stride, const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
                                            float negative_slope, int64_t num_nodes, int32_t heads, float* alpha,
                                            float* alpha_out, void* stream_) {
-  if (num_nodes < 0 || num_nodes >= (1ll << 28)) return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes < 0 || num_nodes >= (1ll << 28) || a_node_parts < 1) return GVQA_ERR_BAD_SHAPE;
   if (num_nodes == 0) return GVQA_OK;
   if (!rowptr || !col_src || !a_node || !a_edge || !alpha || (a_graph && !node_graph)) return GVQA_ERR_NULL_POINTER;
   const int64_t threads = num_nodes * heads;
@@ -694,7 +904,7 @@ extern "C" GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t*
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
 #define GVQA_ALPHA(HH)                                                                                                  \
   if (launch_pdl(2, fused::gat_alpha_kernel<HH>, grid, block, 0, st, rowptr, col_src, perm, node_graph, a_node, ld_a_node, \
-                 a_edge, lde, a_graph, ld_a_graph, negative_slope, (int)num_nodes, alpha, alpha_out) != cudaSuccess) {  \
+                 (int)a_node_parts, a_node_part_stride, a_edge, lde, a_graph, ld_a_graph, negative_slope, (int)num_nodes, alpha, alpha_out) != cudaSuccess) {  \
     (void)cudaGetLastError();                                                                                           \
     return GVQA_ERR_CUDA;                                                                                               \
   }
@@ -710,26 +920,49 @@ extern "C" GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t*
   return GVQA_OK;
 }
 
+extern "C" GVQA_API int gvqa_gat_fused_logit_terms_f32(const int32_t* rowptr, const int32_t* perm, const int32_t* node_graph,
+                                                       const float* a_edge, int64_t lde, const float* a_graph,
+                                                       int64_t ld_a_graph, int64_t hop_stride_a_graph, int32_t hops,
+                                                       int64_t num_nodes, int64_t num_edges, int32_t heads, float* terms,
+                                                       int64_t terms_hop_stride, void* stream_) {
+  if (num_nodes < 0 || num_nodes >= (1ll << 28) || num_edges < 0 || hops < 1 || terms_hop_stride < num_edges * heads)
+    return GVQA_ERR_BAD_SHAPE;
+  if (num_nodes == 0 || num_edges == 0) return GVQA_OK;
+  if (!rowptr || !a_edge || !terms || (a_graph && !node_graph)) return GVQA_ERR_NULL_POINTER;
+  const dim3 grid((unsigned)((num_nodes * heads + 255) / 256)), block(256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (heads == 4)
+    fused::logit_terms_kernel<4><<<grid, block, 0, st>>>(rowptr, perm, node_graph, a_edge, lde, a_graph, ld_a_graph,
+                                                         hop_stride_a_graph, hops, (int)num_nodes, terms_hop_stride, terms);
+  else if (heads == 2)
+    fused::logit_terms_kernel<2><<<grid, block, 0, st>>>(rowptr, perm, node_graph, a_edge, lde, a_graph, ld_a_graph,
+                                                         hop_stride_a_graph, hops, (int)num_nodes, terms_hop_stride, terms);
+  else
+    return GVQA_ERR_UNSUPPORTED;
+  GVQA_LAUNCH_CHECK();
+  return GVQA_OK;
+}
+
 extern "C" GVQA_API int64_t gvqa_gat_fused_pack_halves(int32_t heads, int32_t channels, int32_t in_channels) {
-  const int64_t fp = (in_channels + 31) & ~31;
+  const int64_t fp = (in_channels + 15) & ~15;
   return (int64_t)channels * heads * fp * 2;
 }
 
 extern "C" GVQA_API int gvqa_gat_fused_pack_f16(const float* w, int64_t ldw, int32_t heads, int32_t channels,
-                                                int32_t in_channels, void* packed, void* stream_) {
-  if (heads <= 0 || channels <= 0 || in_channels <= 0 || ldw < in_channels) return GVQA_ERR_BAD_SHAPE;
+                                                int32_t in_channels, float scale, void* packed, void* stream_) {
+  if (heads <= 0 || channels <= 0 || in_channels <= 0 || ldw < in_channels || !(scale > 0.f)) return GVQA_ERR_BAD_SHAPE;
   if (!w || !packed) return GVQA_ERR_NULL_POINTER;
-  const int fp = (in_channels + 31) & ~31;
+  const int fp = (in_channels + 15) & ~15;
   const int64_t total = (int64_t)channels * heads * fp;
   const int64_t blocks = (total + 255) / 256;
   fused::fused_pack_kernel<<<(unsigned)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      w, ldw, heads, channels, in_channels, fp, static_cast<__half*>(packed));
+      w, ldw, heads, channels, in_channels, fp, scale, static_cast<__half*>(packed));
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
 }
 
 extern "C" GVQA_API int gvqa_gat_fused_supported(int32_t heads, int32_t in_channels, int32_t channels) {
-  return (heads == 4 || heads == 2 || heads == 1) && in_channels > 0 && (in_channels & 3) == 0 && channels > 0 &&
+  return (heads == 4 || heads == 2) && in_channels > 0 && (in_channels & 3) == 0 && channels > 0 &&
          (channels & 3) == 0;
 }
 
@@ -742,8 +975,11 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
     return GVQA_ERR_UNSUPPORTED;
   if (a->num_nodes == 0) return GVQA_OK;
   if (!a->h_in || !a->w_pack || !a->tiles || !a->tile_count || !a->rowptr || !a->col_src || !a->alpha || !a->node_graph ||
-      !a->h_out)
+      !a->h_out || (a->logit_terms && !a->a_node))
     return GVQA_ERR_NULL_POINTER;
+  if (a->logit_terms && (a->a_node_parts < 1 || !aligned16(a->logit_terms) || !aligned16(a->a_node) ||
+                         (a->a_node_part_stride & 3)))
+    return GVQA_ERR_MISALIGNED;
   if ((a->epilogue == GVQA_EPI_AFFINE || a->epilogue == GVQA_EPI_AFFINE_RELU) && (!a->ep_scale || !a->ep_shift))
     return GVQA_ERR_NULL_POINTER;
   if (a->epilogue == GVQA_EPI_GRAPH_LN) return GVQA_ERR_UNSUPPORTED;
@@ -754,26 +990,36 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
       (a->skip && !aligned16(a->skip)) || (a->graph_bias && !aligned16(a->graph_bias)) || (a->bias && !aligned16(a->bias)) ||
       (a->ep_scale && !aligned16(a->ep_scale)) || (a->ep_shift && !aligned16(a->ep_shift)))
     return GVQA_ERR_MISALIGNED;
+  if (!(a->w_scale > 0.f)) return GVQA_ERR_BAD_SHAPE;
   Params p;
   memset(&p, 0, sizeof(p));
-  const int fp = (a->in_channels + 31) & ~31;
-  if (!make_map(&p.map_a, a->h_in, a->num_nodes, a->in_channels, ld_h, a->window, 32) ||
-      !make_map_f16(&p.map_b, a->w_pack, a->channels, (int64_t)a->heads * fp * 2, (int64_t)a->heads * fp * 2, 64))
+  const int fp = (a->in_channels + 15) & ~15;
+  int n_ct, nb;
+  column_blocks(a->num_nodes, a->channels, &n_ct, &nb);
+  if (!make_map(&p.map_a, a->h_in, a->num_nodes, a->in_channels, ld_h, a->window, kKB, CU_TENSOR_MAP_SWIZZLE_64B) ||
+      !make_map_f16(&p.map_b, a->w_pack, a->channels, (int64_t)a->heads * fp * 2, (int64_t)a->heads * fp * 2, nb / 2))
     return GVQA_ERR_CUDA;
   p.tiles = reinterpret_cast<const int4*>(a->tiles);
   p.tile_count = a->tile_count;
   p.rowptr = a->rowptr; p.col_src = a->col_src; p.alpha = a->alpha; p.node_graph = a->node_graph;
+  p.logit_terms = a->logit_terms; p.a_node = a->a_node; p.a_node_parts = a->a_node_parts;
+  p.a_node_part_stride = a->a_node_part_stride; p.slope = a->negative_slope;
   p.h_in = a->h_in; p.ld_h = ld_h;
   p.skip = a->skip; p.ld_skip = ld_skip;
   p.graph_bias = a->graph_bias; p.ldgb = ldgb;
   p.bias = a->bias; p.ep_scale = a->ep_scale; p.ep_shift = a->ep_shift;
   p.h_out = a->h_out;
   p.overflow = a->overflow;
-  p.N = (int)a->num_nodes; p.F = a->in_channels; p.C = a->channels; p.Fp = fp;
-  p.n_ct = (a->channels + kBN - 1) / kBN;
-  p.ks = fp / kKS;
+  p.N = (int)a->num_nodes; p.F = a->in_channels; p.C = a->channels;
+  p.n_ct = n_ct;
+  p.nb = nb;
+  p.ks = fp / kKB;
   p.epilogue = a->epilogue;
-  p.inv_heads = 1.0f / (float)a->heads;
+  p.out_scale = 1.0f / ((float)a->heads * a->w_scale);
+  p.v_next = a->v_next;
+  p.a_part = a->a_part;
+  if (a->v_next && (!a->a_part || !aligned16(a->v_next) || !aligned16(a->a_part))) return GVQA_ERR_MISALIGNED;
+  if (a->v_next && a->a_part_blocks != n_ct) return GVQA_ERR_BAD_SHAPE;
   p.trace = g_fused_trace;
 
   void (*kernel)(const Params) = nullptr;
@@ -781,9 +1027,9 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
   int slot = 0;
 #define GVQA_PICK(W, HH, S) { kernel = gat_fused_hop_kernel<W, HH>; smem = Cfg<W, HH>::kSmem; slot = S; }
   if (a->window == 128) {
-    if (a->heads == 4) GVQA_PICK(128, 4, 0) else if (a->heads == 2) GVQA_PICK(128, 2, 1) else GVQA_PICK(128, 1, 2)
+    if (a->heads == 4) GVQA_PICK(128, 4, 0) else GVQA_PICK(128, 2, 1)
   } else {
-    if (a->heads == 4) GVQA_PICK(256, 4, 3) else if (a->heads == 2) GVQA_PICK(256, 2, 4) else GVQA_PICK(256, 1, 5)
+    if (a->heads == 4) GVQA_PICK(256, 4, 3) else GVQA_PICK(256, 2, 4)
   }
 #undef GVQA_PICK
   static bool attr_done[6] = {false, false, false, false, false, false};

@@ -173,7 +173,7 @@ inline EncodeTiledFn encode_fn() {
 
 // [rows, K] fp32 row-major (row stride ld floats) -> 2-D map with a [box_rows x 32] 128B-swizzled box
 inline bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows,
-                     int box_cols = 32) {
+                     int box_cols = 32, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
@@ -181,7 +181,7 @@ inline bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -477,16 +477,20 @@ class gat_seq(nn.Module):
         csr_d = csr.as_dict()
         alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)
         a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        # hops >= 1 get their node logits from the previous hop's epilogue (partial sums per 128-column block)
+        # (two buffers: a hop reads the previous hop's block while it writes its own)
+        a_part = torch.empty(2, _cabi.fused_part_blocks(n, c), n, 2 * heads, dtype=torch.float32, device=x.device)
         h, hops = x, []
+        terms = None
         for i in range(num_hops):
-            _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
             if i == 0:
+                _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
                 if csr_ready is not None:
                     cur.wait_event(csr_ready)
                 if plan_ready is not None:
                     cur.wait_event(plan_ready)
-            _cabi.gat_alpha(a_node, a_edge_all[:, i * heads:], csr_d, heads, lde=a_edge_all.stride(0),
-                            a_graph=g_all[i, :, c:c + heads], negative_slope=self.convs[i].negative_slope, out=alpha)
+                # hop-invariant logit terms of all hops, CSR order (the kernels run the softmax in their tile prologues)
+                terms = _cabi.fused_logit_terms(csr_d, a_edge_all, g_all[:, :, c:c + heads], num_hops, heads, n)
             last = i == num_hops - 1
             epi = dict(epilogue=_cabi.EPI_NONE) if last else \
                 dict(epilogue=_cabi.EPI_AFFINE_RELU, ep_scale=pk["scale"][i], ep_shift=pk["shift"][i])
@@ -496,7 +500,10 @@ class gat_seq(nn.Module):
                 ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
                 ev[0].record()
             _cabi.gat_fused_hop(h, pk["w_fused"][i], plan, csr_d, alpha, heads, c, h_out, window=window, skip=h,
-                                graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag, **epi)
+                                graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag,
+                                v_next=None if last else pk["v_node"][i + 1], a_part=None if last else a_part[i & 1],
+                                logit_terms=terms[i], a_node=a_node if i == 0 else a_part[(i - 1) & 1],
+                                negative_slope=self.convs[i].negative_slope, **epi)
             if self.hop_events is not None:
                 ev[1].record()
                 self.hop_events.append(ev)

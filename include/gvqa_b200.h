@@ -220,9 +220,11 @@ GVQA_API int gvqa_gat_hop_build_slabs_f32(const int32_t* rowptr, const int32_t* 
  * (never stored), runs  Z[N, H*F] @ W'[C, H*F]^T  on tcgen05 with the fp16 split of gvqa_proj_gemm_3xf16, and
  * applies the hop epilogue (head mean, graph_bias for rows with in-edges, bias, skip, affine / ReLU) to the
  * accumulators.  x_l[N, H*C] is never materialised.  Pieces:
- *   gvqa_gat_fused_pack_f16   once per checkpoint: lin_l.weight[:, :F] ([H*C, ldw] fp32, row h*C + c) -> packed fp16
- *                             [C, H * Fp * 2] (Fp = F rounded up to 32; per 32 input channels 32 hi then 32 lo');
- *                             gvqa_gat_fused_pack_halves gives the element count;
+ *   gvqa_gat_fused_pack_f16   once per checkpoint: scale * lin_l.weight[:, :F] ([H*C, ldw] fp32, row h*C + c) -> packed
+ *                             fp16 [C, Fp/16, H, (16 hi | 16 lo)] (Fp = F rounded up to 16; lo = x - hi, unscaled);
+ *                             `scale`: a power of two that lifts the low parts into fp16's normal range (2^9 / max|W|
+ *                             rounded down to a power of two is what gat_seq uses), passed again as w_scale to the
+ *                             hop, which divides it out; gvqa_gat_fused_pack_halves gives the element count;
  *   gvqa_gat_fused_plan       once per batch: row tiles {first row, rows, first window row, 0} (int32 x 4 each) from
  *                             graph_ptr: whole graphs packed greedily into <= 128 rows; larger graphs are cut into
  *                             128-row chunks.  `window` = gvqa_gat_fused_window(max nodes per graph) (128 or 256 rows
@@ -230,9 +232,11 @@ GVQA_API int gvqa_gat_hop_build_slabs_f32(const int32_t* rowptr, const int32_t* 
  *                             correctness input).  tiles: 16-byte aligned, gvqa_gat_fused_max_tiles entries; count: one
  *                             int32 on the device.  _host: the same plan built by the loader (wire format);
  *   gvqa_gat_alpha_f32        per hop: softmax weights of all in-edges in CSR order, alpha[k, h] (PyG semantics,
- *                             gat_skip.py:183-192); a_node [N, >= 2H] = (a_l | a_r), a_edge gathered through perm,
- *                             a_graph per graph or NULL; alpha_out (optional): the same in original edge order;
- *   gvqa_gat_fused_hop_f32    per hop.  heads in {1, 2, 4}, in_channels and channels multiples of 4
+ *                             gat_skip.py:183-192); a_node [N, >= 2H] = (a_l | a_r) -- or a_node_parts partial sums
+ *                             a_node_part_stride floats apart (the fused hop's a_part), added in order --, a_edge
+ *                             gathered through perm, a_graph per graph or NULL; alpha_out (optional): the same in
+ *                             original edge order;
+ *   gvqa_gat_fused_hop_f32    per hop.  heads in {2, 4}, in_channels and channels multiples of 4
  *                             (gvqa_gat_fused_supported), epilogue NONE / AFFINE / AFFINE_RELU.  `overflow` as in
  *                             gvqa_proj_gemm_3xf16 (OR-ed with 1 when an aggregated input does not fit fp16). */
 typedef struct gvqa_gat_fused_args {
@@ -244,7 +248,16 @@ typedef struct gvqa_gat_fused_args {
   const int32_t* rowptr;    /* destination-CSR (gvqa_build_csr)                                           */
   const int32_t* col_src;
   const int32_t* node_graph;
-  const float* alpha;       /* [E, heads] from gvqa_gat_alpha_f32                                         */
+  float* alpha;             /* [E, heads]: softmax weights from gvqa_gat_alpha_f32 (read only) -- or, with
+                               logit_terms, scratch for tiles that do not fit the kernel's staging          */
+  const float* logit_terms; /* optional: THIS hop's [E, heads] block of gvqa_gat_fused_logit_terms_f32.  The kernel
+                               then computes the softmax weights itself in each tile's prologue (no
+                               gvqa_gat_alpha_f32 launch) from these and a_node                            */
+  const float* a_node;      /* with logit_terms: [a_node_parts][N][2*heads] node logits a_l | a_r as partial
+                               sums a_node_part_stride floats apart (the previous hop's a_part, or one block) */
+  int64_t a_node_part_stride;
+  int32_t a_node_parts;
+  float negative_slope;
   const float* skip;        /* [N, channels] added to every row (gat_skip.py:270), row stride ld_skip; or NULL */
   int64_t ld_skip;
   const float* graph_bias;  /* [B, channels] per-graph instruction term (rows with in-edges only) or NULL */
@@ -256,11 +269,19 @@ typedef struct gvqa_gat_fused_args {
   int32_t* overflow;        /* device int32 or NULL                                                       */
   int64_t num_nodes;
   int32_t in_channels, channels, heads, epilogue, window;
+  float w_scale;            /* the scale given to gvqa_gat_fused_pack_f16                                 */
+  const float* v_next;      /* optional: [2*heads, channels] collapsed logit vectors (V_l ; V_r) of the NEXT hop:
+                               the epilogue also emits that hop's node logits a_l | a_r = h_out . V
+                               (gat_skip.py:134-135) as partial sums over 128-column blocks,
+                               a_part[block][node][2*heads]; gvqa_gat_alpha_f32 adds the blocks in fixed order */
+  float* a_part;
+  int32_t a_part_blocks;    /* gvqa_gat_fused_part_blocks(channels) when v_next is given                  */
 } gvqa_gat_fused_args;
+GVQA_API int32_t gvqa_gat_fused_part_blocks(int64_t num_nodes, int32_t channels);
 GVQA_API int gvqa_gat_fused_supported(int32_t heads, int32_t in_channels, int32_t channels);
 GVQA_API int64_t gvqa_gat_fused_pack_halves(int32_t heads, int32_t channels, int32_t in_channels);
 GVQA_API int gvqa_gat_fused_pack_f16(const float* w, int64_t ldw, int32_t heads, int32_t channels,
-                                     int32_t in_channels, void* packed, void* stream);
+                                     int32_t in_channels, float scale, void* packed, void* stream);
 GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t num_graphs);
 GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph);
 GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t num_graphs, int32_t window, int32_t* tiles,
@@ -269,9 +290,18 @@ GVQA_API int gvqa_gat_fused_plan_host(const int32_t* graph_ptr_host, int64_t num
                                       int32_t* tiles_host, int32_t* count_host, int64_t max_tiles);
 GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,
                                 const int32_t* node_graph, const float* a_node, int64_t ld_a_node,
-                                const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
+                                int32_t a_node_parts, int64_t a_node_part_stride, const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
                                 float negative_slope, int64_t num_nodes, int32_t heads, float* alpha,
                                 float* alpha_out, void* stream);
+/* Hop-invariant logit terms of all hops in CSR order, once per batch:
+ *   terms[hop][k][h] = a_edge[perm[k]][hop*heads + h] + a_graph[hop][graph of the destination][h]
+ * a_edge [E, lde], a_graph at a_graph + hop*hop_stride_a_graph + g*ld_a_graph + h (or NULL); hop j's block starts at
+ * terms + j*terms_hop_stride (floats; >= E*heads, a multiple of 4 so that every block is 16-byte aligned). */
+GVQA_API int gvqa_gat_fused_logit_terms_f32(const int32_t* rowptr, const int32_t* perm, const int32_t* node_graph,
+                                            const float* a_edge, int64_t lde, const float* a_graph, int64_t ld_a_graph,
+                                            int64_t hop_stride_a_graph, int32_t hops, int64_t num_nodes,
+                                            int64_t num_edges, int32_t heads, float* terms,
+                                            int64_t terms_hop_stride, void* stream);
 GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------

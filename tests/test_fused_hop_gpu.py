@@ -56,19 +56,20 @@ def test_plan_device_host_and_reference_agree(sizes, win):
     assert not covered or covered[-1][1] == n
 
 
-@pytest.mark.parametrize("heads,c,f", [(4, 64, 64), (2, 36, 20), (1, 128, 300)])
+@pytest.mark.parametrize("heads,c,f", [(4, 64, 64), (2, 36, 20), (4, 128, 300)])
 def test_pack_layout(heads, c, f):
     g = torch.Generator().manual_seed(c)
-    w = torch.randn(heads * c, f + 12, generator=g)
-    packed = _cabi.fused_pack(w.to(DEV), heads, c, f).cpu()
-    fp = (f + 31) // 32 * 32
+    w = torch.randn(heads * c, f + 12, generator=g) * 0.03
+    packed, scale = _cabi.fused_pack(w.to(DEV), heads, c, f)
+    assert 256.0 <= float(w[:, :f].abs().max()) * scale < 512.0
+    fp = (f + 15) // 16 * 16
     wp = torch.zeros(heads, c, fp)
-    wp[:, :, :f] = w[:, :f].view(heads, c, -1)
+    wp[:, :, :f] = w[:, :f].view(heads, c, -1) * scale
     hi = wp.half()
-    lo = ((wp - hi.float()) * 2048.0).half()
-    # [C, H, Fp/32, (32 hi | 32 lo')]
-    want = torch.stack([hi.view(heads, c, fp // 32, 32), lo.view(heads, c, fp // 32, 32)], 3).permute(1, 0, 2, 3, 4)
-    assert torch.equal(packed.view(c, heads, fp // 32, 2, 32), want.contiguous())
+    lo = (wp - hi.float()).half()
+    # [C, Fp/16, H, (16 hi | 16 lo)]
+    want = torch.stack([hi.view(heads, c, fp // 16, 16), lo.view(heads, c, fp // 16, 16)], 3).permute(1, 2, 0, 3, 4)
+    assert torch.equal(packed.cpu().view(c, fp // 16, heads, 2, 16), want.contiguous())
 
 
 def _alpha_reference(a_node, a_edge, a_graph, ei, batch, heads, slope):
@@ -117,7 +118,8 @@ def _hop_reference(t, heads, c, epilogue):
     (40, 5, 40, 2.0, 4, 300, 300, 128, 2),       # reference dims: ragged k-slice (300 = 9 x 32 + 12) and column tile
     (3, 150, 220, 3.0, 4, 128, 128, 256, 0),     # graphs larger than a tile: chunks with the whole graph as window
     (2, 290, 300, 2.0, 2, 64, 96, 256, 1),       # graphs larger than the window: sources read from global memory
-    (3, 150, 220, 3.0, 1, 36, 20, 128, 2),       # window hint too small for the graphs (generic path), tiny widths
+    (3, 150, 220, 3.0, 2, 36, 20, 128, 2),       # window hint too small for the graphs (generic path), tiny widths
+    (70, 20, 40, 2.0, 4, 512, 512, 128, 2),      # two column blocks of 256, several items per pair
     (300, 1, 3, 1.0, 4, 32, 32, 128, 2),         # many tiny graphs
 ])
 def test_fused_hop_matches_float64_reference(graphs, n_lo, n_hi, extra, heads, f, c, win, epilogue):
@@ -131,12 +133,30 @@ def test_fused_hop_matches_float64_reference(graphs, n_lo, n_hi, extra, heads, f
     assert (alpha.cpu()[:perm.numel()].double() - want_alpha[perm]).abs().max() <= 1e-5
     out = torch.full((n, c), float("nan"), device=DEV)
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    v_next = torch.randn(2 * heads, c, generator=torch.Generator().manual_seed(1)) / c ** 0.5
+    a_part = torch.full((_cabi.fused_part_blocks(n, c), n, 2 * heads), float("nan"), device=DEV)
     _cabi.gat_fused_hop(d["h"], _cabi.fused_pack(d["w"], heads, c, f), csr.fused_plan(win), csr.as_dict(), alpha, heads, c,
                         out, window=win, skip=d["skip"], graph_bias=d["gb"], bias=d["bias"], ep_scale=d["scale"],
-                        ep_shift=d["shift"], epilogue=epilogue, overflow=flag)
+                        ep_shift=d["shift"], epilogue=epilogue, overflow=flag, v_next=v_next.to(DEV), a_part=a_part)
     err = (out.cpu().double() - want).abs().max()
     assert err <= 2e-5 * max(1.0, float(want.abs().max())), "max|d| = %g" % err
     assert int(flag) == 0
+    # the next hop's node logits, emitted by the epilogue as partial sums per 128-column block
+    a_next = a_part.cpu().double().sum(0)
+    assert (a_next - want @ v_next.double().t()).abs().max() <= 1e-4
+    # ... and consumed in that form by the softmax-weight kernel
+    alpha2 = _cabi.gat_alpha(a_part, d["a_edge"], csr.as_dict(), heads, a_graph=d["a_graph"])
+    alpha2_ref = _cabi.gat_alpha(a_part.sum(0), d["a_edge"], csr.as_dict(), heads, a_graph=d["a_graph"])
+    assert (alpha2 - alpha2_ref).abs().max() <= 1e-6
+    # the same hop with the softmax inside the kernel (logit terms + node logits instead of precomputed weights)
+    terms = _cabi.fused_logit_terms(csr.as_dict(), d["a_edge"], d["a_graph"][None], 1, heads, n)
+    out2 = torch.full((n, c), float("nan"), device=DEV)
+    scratch = torch.zeros_like(alpha)
+    _cabi.gat_fused_hop(d["h"], _cabi.fused_pack(d["w"], heads, c, f), csr.fused_plan(win), csr.as_dict(), scratch, heads, c,
+                        out2, window=win, skip=d["skip"], graph_bias=d["gb"], bias=d["bias"], ep_scale=d["scale"],
+                        ep_shift=d["shift"], epilogue=epilogue, logit_terms=terms[0], a_node=d["a_node"])
+    err2 = (out2.cpu().double() - want).abs().max()
+    assert err2 <= 2e-5 * max(1.0, float(want.abs().max())), "in-kernel softmax: max|d| = %g" % err2
 
 
 def test_fused_hop_hub_exceeds_the_staged_edge_list():
@@ -152,11 +172,13 @@ def test_fused_hop_hub_exceeds_the_staged_edge_list():
     csr = GraphCSR.build(d["ei"], d["batch"], 1)
     alpha = _cabi.gat_alpha(d["a_node"], d["a_edge"], csr.as_dict(), 4, a_graph=d["a_graph"])
     _, want = _hop_reference(t, 4, 64, 2)
-    out = torch.empty(n, 64, device=DEV)
-    _cabi.gat_fused_hop(d["h"], _cabi.fused_pack(d["w"], 4, 64, 64), csr.fused_plan(128), csr.as_dict(), alpha, 4, 64, out,
-                        window=128, skip=d["skip"], graph_bias=d["gb"], bias=d["bias"], ep_scale=d["scale"],
-                        ep_shift=d["shift"], epilogue=2)
-    assert (out.cpu().double() - want).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
+    terms = _cabi.fused_logit_terms(csr.as_dict(), d["a_edge"], d["a_graph"][None], 1, 4, n)
+    for kw in (dict(), dict(logit_terms=terms[0], a_node=d["a_node"])):      # weights given / softmax inside the kernel
+        out = torch.empty(n, 64, device=DEV)
+        _cabi.gat_fused_hop(d["h"], _cabi.fused_pack(d["w"], 4, 64, 64), csr.fused_plan(128), csr.as_dict(),
+                            alpha if not kw else torch.zeros_like(alpha), 4, 64, out, window=128, skip=d["skip"],
+                            graph_bias=d["gb"], bias=d["bias"], ep_scale=d["scale"], ep_shift=d["shift"], epilogue=2, **kw)
+        assert (out.cpu().double() - want).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
 
 
 def test_fused_hop_flags_inputs_outside_fp16_range():
@@ -210,7 +232,7 @@ def _check(o, e, args, hints=True, own_csr=True):
 
 
 @pytest.mark.parametrize("own_csr", [True, False])
-@pytest.mark.parametrize("f,d,heads,hops", [(300, 512, 4, 5), (512, 512, 4, 5), (64, 32, 1, 2), (36, 20, 2, 2)])
+@pytest.mark.parametrize("f,d,heads,hops", [(300, 512, 4, 5), (512, 512, 4, 5), (64, 32, 2, 2), (36, 20, 2, 2)])
 def test_gat_seq_fused_matches_oracle_random_graphs(f, d, heads, hops, own_csr):
     cfg = dict(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d, num_ins=hops, dropout=0.1, gat_heads=heads)
     o, e = _pair(cfg, seed=11)
@@ -231,7 +253,7 @@ def test_gat_seq_fused_cfg2_full_batch_matches_oracle_and_is_deterministic():
         assert torch.equal(got, again)
         e.hop_mode = "split"
         split = e(*dargs)
-    assert (split - got).abs().max() <= 2e-5
+    assert (split - got).abs().max() <= TOL
 
 
 def test_gat_seq_fused_cfg4_shape_large_graphs():
@@ -251,8 +273,9 @@ def test_gat_seq_fused_refdims_jittered_graphs_without_hints():
     _check(o, e, _inputs(ei, batch, 40, 300, 300, 512, 5, seed=52), hints=False)
 
 
-def test_gat_seq_fused_heads8_uses_the_split_path():
-    cfg = dict(in_channels=128, out_channels=128, edge_attr_dim=128, ins_dim=64, num_ins=3, gat_heads=8)
+@pytest.mark.parametrize("heads", [1, 8])
+def test_gat_seq_fused_other_head_counts_use_the_split_path(heads):
+    cfg = dict(in_channels=128, out_channels=128, edge_attr_dim=128, ins_dim=64, num_ins=3, gat_heads=heads)
     o, e = _pair(cfg, seed=61)
     ei, batch = random_graphs(6, 1, 24, 2.0, seed=5, isolated=True)
     _check(o, e, _inputs(ei, batch, 6, 128, 128, 64, 3, seed=62))
