@@ -30,6 +30,9 @@ if ROOT not in sys.path:
 # capture (cold L2; the 15.7 MB output is still dirty in L2 when the kernel ends)
 NCU_TRAFFIC_BYTES = 85176576          # 80.934 MB read + 4.242 MB written (gat_hop_slab_kernel<4,4,0>, first captured launch)
 NCU_TRAFFIC_SOURCE = "profiles/r02/hop_slab_ncu_raw.csv"
+# the same for one gat_fused_hop_kernel launch at cfg2 (ncu --set full, profiles/r02/fused_hop_ncu_raw.csv)
+FUSED_NCU_TRAFFIC_BYTES = None
+FUSED_NCU_TRAFFIC_SOURCE = "profiles/r02/fused_hop_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
 UNIT = "questions/s"
@@ -394,6 +397,7 @@ def cfg4_sharded(args, dev, rank, world, steps):
     randomise_bn(model.gat_seq, 7)
     model = model.to(dev)
     model.gat_seq.kernel_variant = args.variant
+    model.gat_seq.hop_mode = args.hop_mode
     model.strict_range = False
     lo, hi = gdist.graph_range(b, rank, world)
     shard = gdist.shard_scene_graphs(full, rank, world, num_graphs=b).to(device=dev)
@@ -448,6 +452,8 @@ def run_engine(args, rank, local_rank, world):
     randomise_bn(model, 7)
     model = model.to(dev)
     model.kernel_variant = args.variant
+    model.hop_mode = args.hop_mode
+    fused = args.hop_mode == "fused" and args.variant == 0 and args.projection == "3xf16"
     if args.gemm_flags:
         _cabi.lib().gvqa_debug_set_gemm_flags(args.gemm_flags)
     model.projection = args.projection
@@ -521,12 +527,12 @@ def run_engine(args, rank, local_rank, world):
         value = b * world / (ms_per_step / 1e3)
 
         # ---------------- fused-hop kernel time, live, eager launches with events ---------------
-        model.hop_events, model.gemm_events = [], []
+        model.hop_events, model.gemm_events = [], (None if fused else [])
         for i in range(args.steps):
             step(dev_sets[i % R])
         torch.cuda.synchronize()
         hop_ms = [a.elapsed_time(z) for a, z in model.hop_events]
-        gemm_ms = [a.elapsed_time(z) for a, z in model.gemm_events]
+        gemm_ms = [a.elapsed_time(z) for a, z in (model.gemm_events or [])]
         model.hop_events = model.gemm_events = None
         gemm_us = 1e3 * sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
         hop_us = 1e3 * sum(hop_ms) / len(hop_ms)
@@ -634,7 +640,7 @@ def run_engine(args, rank, local_rank, world):
         pm = PipelineModel(VocabSpec(text_vocab_size=64, sg_vocab_size=SG_VOCAB), sg_emb_dim=cfg["feat"]).eval()
         pm.gat_seq.load_state_dict(model.state_dict())           # the SAME hop stack as the resident measurement
         pm = pm.to(dev)
-        pm.gat_seq.kernel_variant, pm.gat_seq.projection = args.variant, args.projection
+        pm.gat_seq.kernel_variant, pm.gat_seq.projection, pm.gat_seq.hop_mode = args.variant, args.projection, args.hop_mode
         collator = WireCollator(depth=R + 1)
         wires, text = [], []
         for r in range(R):
@@ -672,14 +678,19 @@ def run_engine(args, rank, local_rank, world):
     else:
         primary_us, primary_method = hop_us, "event_bracket"
     primary_achieved = algo / (primary_us * 1e-6) / 1e9
+    peaks_all = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     base = cpu_baseline(cfg, steps=3, warmup=1) if (not args.skip_cpu and world == 1) else None   # N=1 only
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "step": "gat_seq.forward = CSR build + edge-logit pre-pass + 5 x (fp32-accurate tcgen05 projection + "
-                           "fused hop)",
+                   "step": ("gat_seq.forward = CSR build + row-tile plan + pre-pass (edge / instruction terms, hop 0 node "
+                            "logits) + 5 x ONE tcgen05 kernel per hop (aggregate the input rows per head, project the "
+                            "aggregate, hop epilogue)") if fused else
+                           ("gat_seq.forward = CSR build + edge-logit pre-pass + 5 x (fp32-accurate tcgen05 projection + "
+                            "fused hop)"),
+                   "hop_mode": "fused" if fused else "split",
                    "hop_kernel_variant": args.variant,
                    "graphs_per_gpu": b, "parallelism": "graph-sharded x%d, no data-path collective" % world,
                    "l2_hygiene": "4 distinct input sets (~200 MB > 126 MB L2) rotated step to step",
@@ -698,9 +709,12 @@ def run_engine(args, rank, local_rank, world):
                                      "(pre-encoded fp32 features) up, node states down; PCIe-bound"},
         # per step: 5 CSR kernels + hops x (projection GEMM + fused hop); the edge-logit and instruction pre-pass
         # products ride in hop 0's projection launch (grouped) or cost two launches of their own
-        "gpu_launches": args.steps * (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
-                                      + (1 if model.use_slabs and args.variant in (0, 5) else 0)),
-        "roofline": {"bound": "hbm",
+        "gpu_launches": args.steps * ((5 + 1 + 1 + 1 + 1 + hops) if fused else     # CSR, plan, pre-pass GEMM, hop-0 logits, logit terms, hops
+                                      (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
+                                       + (1 if model.use_slabs and args.variant in (0, 5) else 0))),
+        "roofline": None,
+    }
+    hbm_roofline = {"bound": "hbm",
                      "kernel": ("gat_hop_slab_kernel (gvqa_gat_hop_f32; hops 1-4; hop 0 runs gat_hop_block_kernel while the "
                                 "slabs are built)" if (model.use_slabs and args.variant in (0, 5)) else
                                 "gvqa_gat_hop_f32, variant %d" % args.variant),
@@ -716,8 +730,32 @@ def run_engine(args, rank, local_rank, world):
                              "runs in the timed region); in_graph_us_min_max = "
                              "smallest and largest round.  bracketed_*: eager launches with an event pair around every hop "
                              "launch of K steps; an event pair around an empty stream position already reads ~2.7 us "
-                             "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"},
-    }
+                             "and around a 32-element kernel ~6 us (profiles/r01/event_overhead.txt)"}
+    if fused:
+        # the dominant kernel is tensor-bound: per launch 3 fp16 products (hi*hi, hi*lo, lo*hi) of
+        # Z[N, H*F] x W'[C, H*F]^T on tcgen05 -- against the measured dense bf16/fp16 matmul peak
+        tpeak = peaks_all.get("bf16_tflops", 2250.0)
+        flops = 3 * 2.0 * n * (heads * cfg["feat"]) * c
+        tf = flops / (primary_us * 1e-6) / 1e12
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "gat_fused_hop_kernel<128,4> (gvqa_gat_fused_hop_f32): aggregate + project + hop epilogue",
+            "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+            "traffic": FUSED_NCU_TRAFFIC_BYTES, "traffic_source": FUSED_NCU_TRAFFIC_SOURCE,
+            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks_all else "nominal dense bf16",
+            "peak_sustained": peaks_all.get("bf16_tflops_sustained"),
+            "frac_of_sustained": (tf / peaks_all["bf16_tflops_sustained"]) if peaks_all.get("bf16_tflops_sustained") else None,
+            "tensor_flops_per_launch": flops, "useful_fp32_flops_per_launch": flops / 3,
+            "avg_launch_us": primary_us, "method": primary_method,
+            "bracketed_us": hop_us, "bracketed_frac": flops / (hop_us * 1e-6) / 1e12 / tpeak, "launches_bracketed": len(hop_ms),
+            "in_graph_us": hop_in_graph_us, "in_graph_us_min_max": hop_in_graph_spread,
+            "in_graph_bracketed_us": hop_graph_bracket_us,
+            "hbm_bytes_per_launch_algorithmic": 4 * (2 * n * c) + 4 * heads * c * cfg["feat"],
+            "note": "algorithmic work of one hop = the three split-precision tensor-core products (16.1 GFLOP of useful fp32 "
+                    "work); HBM traffic is h in + h out + the packed weights, x_l[N, H*C] is never materialised.  "
+                    "in_graph_differential: median over 15 interleaved rounds of (K replays of the step graph minus K "
+                    "replays of the same graph captured without the 5 hop launches), per hop"}
+    else:
+        line["roofline"] = hbm_roofline
     if gemm_us:
         # the other big kernel of the step, tensor-bound: 3 fp16 products (hi*hi, hi*lo', lo'*hi) of [N x F] x
         # [H*C+16 x F]^T per launch against the measured dense bf16/fp16 matmul peak
@@ -786,6 +824,9 @@ def main():
     ap.add_argument("--variant", type=int, default=0,
                     help="fused-hop kernel: 0 auto (slab), 1 gather, 2 staged, 3 block, 4 persistent warp-specialised, "
                          "5 block with the one-round-trip slab prologue")
+    ap.add_argument("--hop-mode", default="fused", choices=["fused", "split"],
+                    help="fused: one tensor-core kernel per hop that aggregates the input rows and projects the aggregate "
+                         "(gvqa_gat_fused_hop_f32; needs --variant 0 and --projection 3xf16); split: projection GEMM + hop kernel")
     ap.add_argument("--projection", default="3xf16", choices=["3xf16", "3xtf32", "cublas"])
     ap.add_argument("--gemm-flags", type=int, default=0, help="debug flags of the projection GEMM (experiments)")
     ap.add_argument("--l2-persist", type=int, default=0, help="MiB of L2 set aside to keep x_l resident (0 = off)")

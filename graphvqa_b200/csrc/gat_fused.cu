@@ -99,7 +99,7 @@ struct Params {
   int32_t N, F, C, n_ct, nb, ks, epilogue;
   float out_scale;                 // 1 / (heads * weight scale)
   const float* v_next;             // [2H, C] collapsed logit vectors of the NEXT hop, or NULL
-  float* a_part;                   // [n_ct][N][2H] partial node logits of the next hop (one block per column block)
+  float* a_part;                   // [2 * n_ct][N][2H] partial node logits of the next hop (two blocks per column block)
   unsigned long long* trace;       // debug only
 };
 
@@ -244,6 +244,156 @@ __device__ __forceinline__ void aggregate_any(u64 (&acc)[H][8], int eb, int ee, 
 #define GVQA_FUSED_TRACE(slot, col) \
   do { if (p.trace && blockIdx.x == 0 && (slot) < 1100) p.trace[(slot) * 8 + (col)] = clock64(); } while (0)
 
+// One warp's share of an item's epilogue: accumulator rows [32 * quarter, +32), column passes [pass_begin, pass_end)
+// of 32 columns each.  tcgen05.ld (thread = row) -> transpose through shared memory -> lane = (row sub-index, float4
+// column): every global access of a warp covers four full 128-byte row segments.  The skip rows of pass n+1 travel
+// global -> shared by cp.async while pass n is finished; per-column constants come from cst_s (staged once per item:
+// the L1 left beside ~220 KB of shared memory does not hold them).  With v_next the final values go back through the
+// staging block and thread = row accumulates the NEXT hop's collapsed node logits a_l | a_r = h_out . V
+// (gat_skip.py:134-135) into a_part[blk][row][2H]; zero_other: the sibling block blk + 1 gets zeros (nobody else
+// covers it).
+template <int H>
+__device__ __forceinline__ void run_epilogue(const Params& p, uint32_t accbuf, const float* cst_s, uint32_t tmem_base,
+                                             int quarter, int lane, int row0, int nrows, int ct, int pass_begin,
+                                             int pass_end, int blk, uint64_t* acc_full, uint32_t full_parity,
+                                             uint64_t* acc_empty, bool zero_other, bool own_buffers, bool trace_on) {
+  const uint32_t skipbuf = accbuf + 4096u;
+  const int rsub = lane >> 3, f4 = lane & 7;
+  const float* __restrict__ skip = p.skip;
+  const float* __restrict__ gbias = p.graph_bias;
+  float* __restrict__ h_out = p.h_out;
+  const bool relu = p.epilogue == GVQA_EPI_AFFINE_RELU;
+  const int colb = ct * p.nb;                              // first column of the item
+  const int col_end = min(p.C, colb + p.nb);
+  const int nr_w = nrows - quarter * 32;                   // rows of the tile in this warp's quarter
+  const float* skip_base = skip ? skip + (int64_t)(row0 + quarter * 32 + rsub) * p.ld_skip + colb + 4 * f4 : p.h_in;
+  auto issue_skip = [&](int pass) {                        // skip rows of `pass` -> skipbuf (zero-filled where there is none)
+    const bool cok = skip != nullptr && colb + pass * 32 + 4 * f4 < col_end;
+    const float* src0 = skip_base + pass * 32;
+#pragma unroll
+    for (int it8 = 0; it8 < 8; ++it8) {
+      const int row = it8 * 4 + rsub;
+      const bool ok = cok && row < nr_w;
+      const float* src = ok ? src0 + (int64_t)it8 * 4 * p.ld_skip : p.h_in;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(skipbuf + (uint32_t)row * 128u +
+                                                                        (uint32_t)((f4 ^ (row & 7)) << 4)),
+                   "l"(src), "r"(ok ? 16 : 0)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // (a helper warp stages through the operand ring: nothing may be written there before every MMA has completed)
+  if (own_buffers && pass_begin < pass_end) issue_skip(pass_begin);
+  int gid = -1;                                            // graph of the thread's own row when it takes a graph_bias
+  const int r = quarter * 32 + lane;
+  if (r < nrows && gbias && __ldg(p.rowptr + row0 + r + 1) > __ldg(p.rowptr + row0 + r)) gid = __ldg(p.node_graph + row0 + r);
+  int grow8[8];                                            // graph (or -1) of the eight rows this lane finishes per pass
+#pragma unroll
+  for (int it8 = 0; it8 < 8; ++it8) grow8[it8] = __shfl_sync(kFull, gid, it8 * 4 + rsub);
+  float4 gbv[8];
+  auto request_gb = [&](int pass) {                        // graph_bias segments of `pass` (rows with in-edges only)
+    const int col = colb + pass * 32 + 4 * f4;
+#pragma unroll
+    for (int it8 = 0; it8 < 8; ++it8) {
+      gbv[it8] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow8[it8] >= 0 && col < col_end) gbv[it8] = __ldg(reinterpret_cast<const float4*>(gbias + (int64_t)grow8[it8] * p.ldgb + col));
+    }
+  };
+  if (pass_begin < pass_end) request_gb(pass_begin);
+  u64 part2[2 * H];                                        // (sum over even, over odd columns) of the logit dot products
+#pragma unroll
+  for (int v = 0; v < 2 * H; ++v) part2[v] = 0ull;
+  mbar_wait(acc_full, full_parity);
+  if (trace_on && lane == 0) GVQA_FUSED_TRACE(1024, 2);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!own_buffers && pass_begin < pass_end) issue_skip(pass_begin);
+  const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+  for (int pass = pass_begin; pass < pass_end; ++pass) {
+    if (trace_on && lane == 0) GVQA_FUSED_TRACE(1040 + pass, 0);
+    {
+      uint32_t v32[32];
+      GVQA_TMEM_LD32(v32, tcol + (uint32_t)(pass * 32));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (pass == pass_end - 1 && acc_empty != nullptr) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive_cta(acc_empty, 0);                     // TMEM is free: the next item's MMAs may start
+        if (trace_on && lane == 0) GVQA_FUSED_TRACE(1024, 3);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        sts128(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), __uint_as_float(v32[4 * c]),
+               __uint_as_float(v32[4 * c + 1]), __uint_as_float(v32[4 * c + 2]), __uint_as_float(v32[4 * c + 3]));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const int cl = pass * 32 + 4 * f4;                     // column inside the item
+    const int col = colb + cl;
+    const bool cvalid = col < col_end;
+    const float4 bi = *reinterpret_cast<const float4*>(cst_s + cl);
+    const float4 sc = *reinterpret_cast<const float4*>(cst_s + kMaxNB + cl);
+    const float4 sh = *reinterpret_cast<const float4*>(cst_s + 2 * kMaxNB + cl);
+    float* outp = h_out + (int64_t)(row0 + quarter * 32 + rsub) * p.C + col;
+#pragma unroll
+    for (int it8 = 0; it8 < 8; ++it8) {
+      const int row = it8 * 4 + rsub;
+      const uint32_t off = (uint32_t)row * 128u + (uint32_t)((f4 ^ (row & 7)) << 4);
+      float4 t = lds128(accbuf + off);
+      const float4 sk = lds128(skipbuf + off);
+      t.x = fmaf(t.x, p.out_scale, gbv[it8].x) + bi.x + sk.x;
+      t.y = fmaf(t.y, p.out_scale, gbv[it8].y) + bi.y + sk.y;
+      t.z = fmaf(t.z, p.out_scale, gbv[it8].z) + bi.z + sk.z;
+      t.w = fmaf(t.w, p.out_scale, gbv[it8].w) + bi.w + sk.w;
+      t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);          // (scale 1, shift 0 without an affine epilogue)
+      t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+      if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      if (row < nr_w && cvalid) *reinterpret_cast<float4*>(outp + (int64_t)it8 * 4 * p.C) = t;
+      if (p.v_next) sts128(accbuf + off, t.x, t.y, t.z, t.w);            // final values for the logit dot products
+    }
+    __syncwarp();
+    if (trace_on && lane == 0) GVQA_FUSED_TRACE(1040 + pass, 3);
+    if (pass + 1 < pass_end) {                             // skipbuf is free; both land while the logits are accumulated
+      issue_skip(pass + 1);
+      request_gb(pass + 1);
+    }
+    if (trace_on && lane == 0) GVQA_FUSED_TRACE(1040 + pass, 4);
+    if (p.v_next) {
+      u64 x[8][2];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) lds_2x64(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), x[c][0], x[c][1]);
+      const uint32_t vb = smem_u32(cst_s) + (uint32_t)(3 * kMaxNB + pass * 32) * 4u;
+#pragma unroll
+      for (int v = 0; v < 2 * H; ++v) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          u64 w0, w1;
+          lds_2x64(vb + (uint32_t)(v * kMaxNB + 4 * c) * 4u, w0, w1);                              // 0 past C
+          ffma2(part2[v], x[c][0], w0);
+          ffma2(part2[v], x[c][1], w1);
+        }
+      }
+      __syncwarp();                                        // the staging block may be overwritten by the next pass
+    }
+    if (trace_on && lane == 0) GVQA_FUSED_TRACE(1040 + pass, 5);
+  }
+  if (p.v_next && r < nrows) {
+    float part[2 * H];
+#pragma unroll
+    for (int v = 0; v < 2 * H; ++v) {
+      float lo, hi;
+      unpack2(part2[v], lo, hi);
+      part[v] = lo + hi;
+    }
+    float* dst = p.a_part + ((int64_t)blk * p.N + row0 + r) * (2 * H);
+#pragma unroll
+    for (int v4 = 0; v4 < 2 * H / 4; ++v4) {
+      *reinterpret_cast<float4*>(dst + 4 * v4) = make_float4(part[4 * v4], part[4 * v4 + 1], part[4 * v4 + 2], part[4 * v4 + 3]);
+      if (zero_other) *reinterpret_cast<float4*>(dst + (int64_t)p.N * (2 * H) + 4 * v4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (trace_on && lane == 0) GVQA_FUSED_TRACE(1024, 4);
+}
+
 template <int WIN, int H>
 __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid_constant__ Params p) {
   using C_ = Cfg<WIN, H>;
@@ -265,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   uint64_t* a_empty = a_ready + kASlots;        // [kASlots]
   uint64_t* acc_full = a_empty + kASlots;
   uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* cst_full = acc_empty + 1;           // the item's epilogue constants are staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cst_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -282,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, kEpiThreads * 2);
+    mbar_init(cst_full, kEpiThreads);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -530,52 +682,36 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       }
     }
     if (p.overflow != nullptr && !(amax <= 65000.0f)) atomicOr(p.overflow, 1);   // also catches NaN / inf
+    if (grp == 1 && items > pair_id) {
+      // helper epilogue of the CTA's last item: the upper half of the column passes, staged through the first bytes of
+      // the operand ring (no load is in flight or will be issued any more, and acc_full says every MMA has read it)
+      int last_item = pair_id, n_it = 0;
+      while (last_item + npairs < items) {
+        last_item += npairs;
+        ++n_it;
+      }
+      const int prt = last_item / n_ct, ct = last_item - prt * n_ct;
+      const int te = 2 * prt + rank;
+      int4 tile = make_int4(0, 0, 0, 0);
+      if (te < T) tile = __ldg(&p.tiles[te]);
+      const int npass = (min(p.C, ct * p.nb + p.nb) - ct * p.nb + 31) >> 5;
+      mbar_wait(cst_full, n_it & 1);
+      run_epilogue<H>(p, smem_u32(smem) + (uint32_t)quarter * kEpiStageBytes, cst_s, tmem_base, quarter, lane, tile.x, tile.y, ct,
+                      (npass + 1) >> 1, npass, 2 * ct + 1, acc_full, n_it & 1, nullptr, false, false, false);
+    }
   } else {
-    // ===================== epilogue: warp = 32 accumulator rows x all columns of the item =====================
-    // 32 accumulator columns per pass: tcgen05.ld (thread = row) -> transpose through shared memory -> lane = (row
-    // sub-index, float4 column): every global access of a warp covers four full 128-byte row segments.  The skip
-    // rows of pass n+1 travel global -> shared by cp.async while pass n is finished; per-column constants are staged
-    // once per item (the L1 left beside ~220 KB of shared memory does not hold them).  With v_next the final values
-    // go back through the staging block and thread = row accumulates the NEXT hop's collapsed node logits
-    // a_l | a_r = h_out . V  (gat_skip.py:134-135): a_part[column block][row][2H].
+    // ===================== epilogue: warp = 32 accumulator rows x the columns of the item =====================
     const int quarter = warp & 3;
     const int etid = threadIdx.x - kFirstEpiWarp * 32;
     const uint32_t accbuf = smem_u32(epi_stage + (size_t)(warp - kFirstEpiWarp) * kEpiStageBytes);
-    const uint32_t skipbuf = accbuf + 4096u;
-    const int rsub = lane >> 3, f4 = lane & 7;
-    const float* __restrict__ skip = p.skip;
-    const float* __restrict__ gbias = p.graph_bias;
-    float* __restrict__ h_out = p.h_out;
     const bool affine = p.epilogue == GVQA_EPI_AFFINE || p.epilogue == GVQA_EPI_AFFINE_RELU;
-    const bool relu = p.epilogue == GVQA_EPI_AFFINE_RELU;
     uint32_t item_it = 0;
     for (int item = pair_id; item < items; item += npairs, ++item_it) {
       const int prt = item / n_ct, ct = item - prt * n_ct;
       const int te = 2 * prt + rank;
       int4 tile = make_int4(0, 0, 0, 0);
       if (te < T) tile = __ldg(&p.tiles[te]);
-      const int row0 = tile.x, nrows = tile.y;
-      const int colb = ct * p.nb;                          // first column of the item
-      const int col_end = min(p.C, colb + p.nb);
-      const int npass = (col_end - colb + 31) >> 5;
-      const int nr_w0 = nrows - quarter * 32;
-      const float* skip_base = skip ? skip + (int64_t)(row0 + quarter * 32 + rsub) * p.ld_skip + colb + 4 * f4 : p.h_in;
-      auto issue_skip = [&](int pass) {                    // skip rows of `pass` -> skipbuf (zero-filled where there is none)
-        const bool cok = skip != nullptr && colb + pass * 32 + 4 * f4 < col_end;
-        const float* src0 = skip_base + pass * 32;
-#pragma unroll
-        for (int it8 = 0; it8 < 8; ++it8) {
-          const int row = it8 * 4 + rsub;
-          const bool ok = cok && row < nr_w0;
-          const float* src = ok ? src0 + (int64_t)it8 * 4 * p.ld_skip : p.h_in;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(skipbuf + (uint32_t)row * 128u +
-                                                                            (uint32_t)((f4 ^ (row & 7)) << 4)),
-                       "l"(src), "r"(ok ? 16 : 0)
-                       : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      if (npass > 0) issue_skip(0);
+      const int colb = ct * p.nb;
       epi_bar_sync();                                      // the previous item's constants are no longer read
       for (int c = etid; c < p.nb; c += kEpiThreads) {
         const int col = colb + c;
@@ -586,115 +722,14 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
 #pragma unroll
         for (int v = 0; v < 2 * H; ++v) cst_s[(3 + v) * kMaxNB + c] = (ok && p.v_next) ? __ldg(p.v_next + (int64_t)v * p.C + col) : 0.f;
       }
-      int gid = -1;                                        // graph of the thread's own row when it takes a graph_bias
-      const int r = quarter * 32 + lane;
-      if (r < nrows && gbias && __ldg(p.rowptr + row0 + r + 1) > __ldg(p.rowptr + row0 + r)) gid = __ldg(p.node_graph + row0 + r);
       epi_bar_sync();
-      const int nr_w = nrows - quarter * 32;               // rows of the tile in this warp's quarter
-      int grow8[8];                                        // graph (or -1) of the eight rows this lane finishes per pass
-#pragma unroll
-      for (int it8 = 0; it8 < 8; ++it8) grow8[it8] = __shfl_sync(kFull, gid, it8 * 4 + rsub);
-      float4 gbv[8];
-      auto request_gb = [&](int pass) {                    // graph_bias segments of `pass` (rows with in-edges only)
-        const int col = colb + pass * 32 + 4 * f4;
-#pragma unroll
-        for (int it8 = 0; it8 < 8; ++it8) {
-          gbv[it8] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow8[it8] >= 0 && col < col_end) gbv[it8] = __ldg(reinterpret_cast<const float4*>(gbias + (int64_t)grow8[it8] * p.ldgb + col));
-        }
-      };
-      if (npass > 0) request_gb(0);
-      u64 part2[2 * H];                                    // (sum over even, over odd columns) of the logit dot products
-#pragma unroll
-      for (int v = 0; v < 2 * H; ++v) part2[v] = 0ull;
-      mbar_wait(acc_full, item_it & 1);
-      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 2);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int pass = 0; pass < npass; ++pass) {
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 0);
-        {
-          uint32_t v32[32];
-          GVQA_TMEM_LD32(v32, tcol + (uint32_t)(pass * 32));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (pass == npass - 1) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cta(acc_empty, 0);                 // TMEM is free: the next item's MMAs may start
-            if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 3);
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts128(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), __uint_as_float(v32[4 * c]),
-                   __uint_as_float(v32[4 * c + 1]), __uint_as_float(v32[4 * c + 2]), __uint_as_float(v32[4 * c + 3]));
-        }
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 2);
-        const int cl = pass * 32 + 4 * f4;                 // column inside the item
-        const int col = colb + cl;
-        const bool cvalid = col < col_end;
-        const float4 bi = *reinterpret_cast<const float4*>(cst_s + cl);
-        const float4 sc = *reinterpret_cast<const float4*>(cst_s + kMaxNB + cl);
-        const float4 sh = *reinterpret_cast<const float4*>(cst_s + 2 * kMaxNB + cl);
-        float* outp = h_out + (int64_t)(row0 + quarter * 32 + rsub) * p.C + col;
-#pragma unroll
-        for (int it8 = 0; it8 < 8; ++it8) {
-          const int row = it8 * 4 + rsub;
-          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((f4 ^ (row & 7)) << 4);
-          float4 t = lds128(accbuf + off);
-          const float4 sk = lds128(skipbuf + off);
-          t.x = fmaf(t.x, p.out_scale, gbv[it8].x) + bi.x + sk.x;
-          t.y = fmaf(t.y, p.out_scale, gbv[it8].y) + bi.y + sk.y;
-          t.z = fmaf(t.z, p.out_scale, gbv[it8].z) + bi.z + sk.z;
-          t.w = fmaf(t.w, p.out_scale, gbv[it8].w) + bi.w + sk.w;
-          t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y);      // (scale 1, shift 0 without an affine epilogue)
-          t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
-          if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-          if (row < nr_w && cvalid) *reinterpret_cast<float4*>(outp + (int64_t)it8 * 4 * p.C) = t;
-          if (p.v_next) sts128(accbuf + off, t.x, t.y, t.z, t.w);        // final values for the logit dot products
-        }
-        __syncwarp();
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 3);
-        if (pass + 1 < npass) {                            // skipbuf is free; both land while the logits are accumulated
-          issue_skip(pass + 1);
-          request_gb(pass + 1);
-        }
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 4);
-        if (p.v_next) {
-          u64 x[8][2];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) lds_2x64(accbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), x[c][0], x[c][1]);
-          const uint32_t vb = smem_u32(cst_s) + (uint32_t)(3 * kMaxNB + pass * 32) * 4u;
-#pragma unroll
-          for (int v = 0; v < 2 * H; ++v) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              u64 w0, w1;
-              lds_2x64(vb + (uint32_t)(v * kMaxNB + 4 * c) * 4u, w0, w1);                          // 0 past C
-              ffma2(part2[v], x[c][0], w0);
-              ffma2(part2[v], x[c][1], w1);
-            }
-          }
-          __syncwarp();                                    // the staging block may be overwritten by the next pass
-        }
-        if (threadIdx.x == kFirstEpiWarp * 32 && item_it == 0) GVQA_FUSED_TRACE(1040 + pass, 5);
-      }
-      if (p.v_next && r < nrows) {
-        float part[2 * H];
-#pragma unroll
-        for (int v = 0; v < 2 * H; ++v) {
-          float lo, hi;
-          unpack2(part2[v], lo, hi);
-          part[v] = lo + hi;
-        }
-        float* dst = p.a_part + ((int64_t)ct * p.N + row0 + r) * (2 * H);
-#pragma unroll
-        for (int v4 = 0; v4 < 2 * H / 4; ++v4)
-          *reinterpret_cast<float4*>(dst + 4 * v4) = make_float4(part[4 * v4], part[4 * v4 + 1], part[4 * v4 + 2], part[4 * v4 + 3]);
-      }
-      if (threadIdx.x == kFirstEpiWarp * 32) GVQA_FUSED_TRACE(1024 + item_it, 4);
+      mbar_arrive(cst_full);                               // (the helper warps of the last item wait for this)
+      // on the CTA's last item the second converter group, idle by then, takes the upper half of the column passes
+      const bool last = item + npairs >= items;
+      const int npass = (min(p.C, colb + p.nb) - colb + 31) >> 5;
+      const int split = last ? (npass + 1) >> 1 : npass;
+      run_epilogue<H>(p, accbuf, cst_s, tmem_base, quarter, lane, tile.x, tile.y, ct, 0, split, 2 * ct, acc_full, item_it & 1,
+                      acc_empty, !last, true, item_it == 0 && warp == kFirstEpiWarp);
     }
   }
 
@@ -740,12 +775,70 @@ __host__ __device__ inline int plan_tiles(const int32_t* graph_ptr, int B, int w
   return t < max_tiles ? t : max_tiles;
 }
 
-__global__ void fused_plan_kernel(const int32_t* __restrict__ graph_ptr, int B, int win, int4* tiles, int32_t* count,
-                                  int max_tiles) {
-  extern __shared__ int32_t gp_s[];
+// One CTA.  The greedy packing is sequential only in WHICH graphs start a tile: every graph computes in parallel where
+// a tile starting at it would end (binary search in graph_ptr) and how many tiles it would emit, one thread then walks
+// the chain of starts (two shared-memory loads per tile), and the tiles are written in parallel.  Same result as
+// plan_tiles() on the host.
+__global__ void __launch_bounds__(256) fused_plan_kernel(const int32_t* __restrict__ graph_ptr, int B, int win, int4* tiles,
+                                                         int32_t* count, int max_tiles) {
+  extern __shared__ int32_t plan_s[];
+  int32_t* gp_s = plan_s;                 // [B + 1]
+  int32_t* nxt_s = gp_s + (B + 1);        // [B] first graph after a tile that starts at g
+  int32_t* cnt_s = nxt_s + B;             // [B] tiles such a start emits
+  int32_t* off_s = cnt_s + B;             // [B] index of its first tile, -1 when g does not start a tile
   for (int i = threadIdx.x; i <= B; i += blockDim.x) gp_s[i] = graph_ptr[i];
   __syncthreads();
-  if (threadIdx.x == 0) *count = plan_tiles(gp_s, B, win, tiles, max_tiles);
+  for (int g = threadIdx.x; g < B; g += blockDim.x) {
+    const int r0 = gp_s[g], n_g = gp_s[g + 1] - r0;
+    int nxt = g + 1, cnt = 0;
+    if (n_g > kBM) {
+      cnt = (n_g + kBM - 1) / kBM;
+    } else if (n_g > 0) {
+      int lo = g + 1, hi = B;             // largest e in [g + 1, B] with graph_ptr[e] <= r0 + 128
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (gp_s[mid] - r0 <= kBM) lo = mid;
+        else hi = mid - 1;
+      }
+      nxt = lo;
+      cnt = 1;
+    }
+    nxt_s[g] = nxt;
+    cnt_s[g] = cnt;
+    off_s[g] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int g = 0, t = 0;
+    while (g < B) {
+      const int c = cnt_s[g];
+      if (c > 0) off_s[g] = t;
+      t += c;
+      g = nxt_s[g];
+    }
+    *count = t < max_tiles ? t : max_tiles;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < B; g += blockDim.x) {
+    const int t0 = off_s[g];
+    if (t0 < 0) continue;
+    const int r0 = gp_s[g], n_g = gp_s[g + 1] - r0;
+    if (n_g > kBM) {
+      int t = t0;
+      for (int s = r0; s < r0 + n_g; s += kBM, ++t) {
+        const int nr = (r0 + n_g - s) < kBM ? (r0 + n_g - s) : kBM;
+        int w0 = r0;
+        if (n_g > win) {
+          w0 = s - (win - kBM) / 2;
+          if (w0 > r0 + n_g - win) w0 = r0 + n_g - win;
+          if (w0 < r0) w0 = r0;
+        }
+        if (t < max_tiles) tiles[t] = make_int4(s, nr, w0, 0);
+      }
+    } else if (t0 < max_tiles) {
+      tiles[t0] = make_int4(r0, gp_s[nxt_s[g]] - r0, r0, 0);
+    }
+  }
 }
 
 // ---- softmax weights of all in-edges (gat_skip.py:183-192 + PyG utils.softmax), CSR order ---------------------------
@@ -853,7 +946,7 @@ extern "C" GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t 
 extern "C" GVQA_API int32_t gvqa_gat_fused_part_blocks(int64_t num_nodes, int32_t channels) {
   int n_ct, nb;
   fused::column_blocks(num_nodes, channels, &n_ct, &nb);
-  return n_ct;
+  return 2 * n_ct;
 }
 
 extern "C" GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph) {
@@ -865,8 +958,8 @@ extern "C" GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t nu
   if (num_graphs < 0 || max_tiles < 0 || (window != 128 && window != 256)) return GVQA_ERR_BAD_SHAPE;
   if (!graph_ptr || !tiles || !count) return GVQA_ERR_NULL_POINTER;
   if (!aligned16(tiles)) return GVQA_ERR_MISALIGNED;
-  if ((num_graphs + 1) * 4 > 200 * 1024) return GVQA_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)(num_graphs + 1) * 4;
+  if ((4 * num_graphs + 1) * 4 > 200 * 1024) return GVQA_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(4 * num_graphs + 1) * 4;
   if (smem > 48 * 1024) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -1019,7 +1112,7 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
   p.v_next = a->v_next;
   p.a_part = a->a_part;
   if (a->v_next && (!a->a_part || !aligned16(a->v_next) || !aligned16(a->a_part))) return GVQA_ERR_MISALIGNED;
-  if (a->v_next && a->a_part_blocks != n_ct) return GVQA_ERR_BAD_SHAPE;
+  if (a->v_next && a->a_part_blocks != 2 * n_ct) return GVQA_ERR_BAD_SHAPE;
   p.trace = g_fused_trace;
 
   void (*kernel)(const Params) = nullptr;

@@ -189,7 +189,8 @@ class gat_seq(nn.Module):
         # "fused": one tensor-core kernel per hop that aggregates the INPUT rows per head and projects the aggregate
         # (gvqa_gat_fused_hop_f32; x_l [N, H*C] is never materialised); "split": projection GEMM + hop kernel.
         # Shapes the fused kernel does not take (heads 8, ...) and the other projection kinds use "split".
-        self.hop_mode = os.environ.get("GVQA_HOP_MODE", "split")
+        # An explicit kernel_variant (a hop kernel of the split path) also selects "split".
+        self.hop_mode = os.environ.get("GVQA_HOP_MODE", "fused")
         self._overflow, self._overflow_pending = None, []
         self.overflow_external = False   # True: the caller reads / clears the fp16 range flag itself (host runner)
         self._side = None
@@ -316,7 +317,7 @@ class gat_seq(nn.Module):
             def gemm(a, split, out=None):
                 return _cabi.proj_gemm_3xtf32(a, split[0], split[1], out=out)
         if self.hop_mode == "fused" and pk.get("w_fused") is not None and self._interleaved_ln is None and n > 0 \
-                and self.gemm_events is None and not self.skip_hop_launch:
+                and self.gemm_events is None and self.kernel_variant == _cabi.VARIANT_AUTO:
             return self._forward_fused(x, edge_attr, ins, csr, side, csr_ready if side is not None else None, pk, flag,
                                        return_hops)
         hc = heads * c
@@ -475,7 +476,7 @@ class gat_seq(nn.Module):
         g_all = outs[0]
         a_edge_all = outs[1] if e > 0 else x.new_zeros(1, num_hops * heads)
         csr_d = csr.as_dict()
-        alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)
+        alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)    # scratch of the kernels' generic path
         a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
         # hops >= 1 get their node logits from the previous hop's epilogue (partial sums per 128-column block)
         # (two buffers: a hop reads the previous hop's block while it writes its own)
@@ -499,11 +500,12 @@ class gat_seq(nn.Module):
                 ext = torch.cuda.is_current_stream_capturing()
                 ev = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
                 ev[0].record()
-            _cabi.gat_fused_hop(h, pk["w_fused"][i], plan, csr_d, alpha, heads, c, h_out, window=window, skip=h,
-                                graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag,
-                                v_next=None if last else pk["v_node"][i + 1], a_part=None if last else a_part[i & 1],
-                                logit_terms=terms[i], a_node=a_node if i == 0 else a_part[(i - 1) & 1],
-                                negative_slope=self.convs[i].negative_slope, **epi)
+            if not self.skip_hop_launch:
+                _cabi.gat_fused_hop(h, pk["w_fused"][i], plan, csr_d, alpha, heads, c, h_out, window=window, skip=h,
+                                    graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag,
+                                    v_next=None if last else pk["v_node"][i + 1], a_part=None if last else a_part[i & 1],
+                                    logit_terms=terms[i], a_node=a_node if i == 0 else a_part[(i - 1) & 1],
+                                    negative_slope=self.convs[i].negative_slope, **epi)
             if self.hop_events is not None:
                 ev[1].record()
                 self.hop_events.append(ev)

@@ -292,7 +292,9 @@ def test_gat_seq_cfg4_shape_large_graphs():
 
 
 def test_gat_seq_projection_paths_agree():
-    """tcgen05 3xTF32 / 3xF16 projections vs cuBLAS fp32 projection inside gat_seq: same result to 2e-5."""
+    """tcgen05 3xTF32 / 3xF16 projections vs cuBLAS fp32 projection inside gat_seq: same result to 2e-5 on the split
+    path; the default fused hop (hop_mode "fused", one accumulator chain over K = H*F per output) to 4e-5 -- both far
+    inside the 1e-4 bar of BASELINE.json."""
     cfg = dict(in_channels=300, out_channels=300, edge_attr_dim=300, ins_dim=512, num_ins=5, gat_heads=4)
     _, e = _pair(cfg, seed=51)
     ei, batch = random_graphs(20, 5, 40, 2.0, seed=6)
@@ -301,9 +303,11 @@ def test_gat_seq_projection_paths_agree():
         e.projection = "3xtf32"; a = e(*args)
         e.projection = "cublas"; b = e(*args)
         e.projection = "3xf16"; c = e(*args)
+        e.hop_mode = "split"; d = e(*args)
     e.check_overflow()
     assert (a - b).abs().max() <= 2e-5
-    assert (c - b).abs().max() <= 2e-5
+    assert (d - b).abs().max() <= 2e-5
+    assert (c - b).abs().max() <= 4e-5
 
 
 @pytest.mark.parametrize("edges", [True, False])
