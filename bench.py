@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 NCU_TRAFFIC_BYTES = 85176576          # 80.934 MB read + 4.242 MB written (gat_hop_slab_kernel<4,4,0>, first captured launch)
 NCU_TRAFFIC_SOURCE = "profiles/r02/hop_slab_ncu_raw.csv"
 # the same for one gat_fused_hop_kernel launch at cfg2 (ncu --set full, profiles/r02/fused_hop_ncu_raw.csv)
-FUSED_NCU_TRAFFIC_BYTES = None
+FUSED_NCU_TRAFFIC_BYTES = 21990144         # 21.938 MB read + 0.052 MB written (the output is still dirty in L2)
 FUSED_NCU_TRAFFIC_SOURCE = "profiles/r02/fused_hop_ncu_raw.csv"
 CFG2 = dict(name="cfg2", graphs=256, nodes=30, edges=60, feat=512, ins=512, heads=4, hops=5)
 METRIC = "questions/sec (batched scene-graph inference, 5-hop GAT-skip stack)"
@@ -709,7 +709,7 @@ def run_engine(args, rank, local_rank, world):
                                      "(pre-encoded fp32 features) up, node states down; PCIe-bound"},
         # per step: 5 CSR kernels + hops x (projection GEMM + fused hop); the edge-logit and instruction pre-pass
         # products ride in hop 0's projection launch (grouped) or cost two launches of their own
-        "gpu_launches": args.steps * ((5 + 1 + 1 + 1 + 1 + hops) if fused else     # CSR, plan, pre-pass GEMM, hop-0 logits, logit terms, hops
+        "gpu_launches": args.steps * ((5 + 1 + 1 + 1 + hops) if fused else         # CSR, plan, pre-pass GEMM, logit terms, hops
                                       (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
                                        + (1 if model.use_slabs and args.variant in (0, 5) else 0))),
         "roofline": None,

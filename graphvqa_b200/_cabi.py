@@ -44,7 +44,7 @@ class GatFusedArgs(ctypes.Structure):
         ("h_in", _c_vp), ("ld_h", _c_i64), ("w_pack", _c_vp), ("tiles", _c_vp), ("tile_count", _c_vp),
         ("rowptr", _c_vp), ("col_src", _c_vp), ("node_graph", _c_vp), ("alpha", _c_vp),
         ("logit_terms", _c_vp), ("a_node", _c_vp), ("a_node_part_stride", _c_i64), ("a_node_parts", _c_i32),
-        ("negative_slope", _c_f32),
+        ("negative_slope", _c_f32), ("ld_a_node", _c_i64), ("flags", _c_i32),
         ("skip", _c_vp), ("ld_skip", _c_i64), ("graph_bias", _c_vp), ("ld_graph_bias", _c_i64),
         ("bias", _c_vp), ("ep_scale", _c_vp), ("ep_shift", _c_vp), ("h_out", _c_vp), ("overflow", _c_vp),
         ("num_nodes", _c_i64), ("in_channels", _c_i32), ("channels", _c_i32), ("heads", _c_i32),
@@ -371,14 +371,14 @@ def fused_logit_terms(csr, a_edge_all, a_graph_all, hops, heads, num_nodes):
 
 def gat_fused_hop(h_in, w_pack, plan, csr, alpha, heads, channels, h_out, *, window, skip=None, graph_bias=None,
                   bias=None, ep_scale=None, ep_shift=None, epilogue=EPI_NONE, overflow=None, v_next=None, a_part=None,
-                  logit_terms=None, a_node=None, negative_slope=0.2):
+                  logit_terms=None, a_node=None, negative_slope=0.2, inputs_older_than_predecessor=False):
     """``alpha`` [E, heads]: the softmax weights (gat_alpha) -- or, with ``logit_terms`` ([E, heads], this hop's block of
     fused_logit_terms) and ``a_node`` ([N, 2*heads] or [parts, N, 2*heads] partial sums), scratch: the kernel computes
     the weights in its tile prologues.  ``v_next`` [2*heads, channels] + ``a_part`` [fused_part_blocks, N, 2*heads]: the
     epilogue also emits the next hop's node logits as partial sums."""
     require_cuda(h_in, w_pack[0], alpha, h_out, skip, graph_bias, bias, ep_scale, ep_shift, overflow, v_next, a_part,
                  logit_terms, a_node)
-    require_f32c(v_next=v_next, a_part=a_part, logit_terms=logit_terms, a_node=a_node, alpha=alpha)
+    require_f32c(v_next=v_next, a_part=a_part, logit_terms=logit_terms, alpha=alpha)
     require_f32c(h_out=h_out, bias=bias, ep_scale=ep_scale, ep_shift=ep_shift)
     for name, t in (("h_in", h_in), ("skip", skip), ("graph_bias", graph_bias)):
         if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
@@ -397,9 +397,12 @@ def gat_fused_hop(h_in, w_pack, plan, csr, alpha, heads, channels, h_out, *, win
     a.v_next, a.a_part, a.a_part_blocks = ptr(v_next), ptr(a_part), (a_part.size(0) if a_part is not None else 0)
     a.logit_terms, a.a_node, a.negative_slope = ptr(logit_terms), ptr(a_node), negative_slope
     a.a_node_parts, a.a_node_part_stride = 1, 0
+    a.ld_a_node = 0
+    a.flags = HOP_INPUTS_OLDER_THAN_PREDECESSOR if inputs_older_than_predecessor else 0
     if a_node is not None:
-        if a_node.size(-1) != 2 * heads:
-            raise ValueError("gat_fused_hop: a_node must be [N, 2*heads] or [parts, N, 2*heads]")
+        if a_node.size(-1) < 2 * heads or a_node.stride(-1) != 1:
+            raise ValueError("gat_fused_hop: a_node must be [N, >= 2*heads] or [parts, N, 2*heads]")
+        a.ld_a_node = a_node.stride(-2)
         if a_node.dim() == 3:
             a.a_node_parts, a.a_node_part_stride = a_node.size(0), a_node.stride(0)
     with torch.cuda.device(h_out.device):

@@ -80,8 +80,11 @@ struct Params {
   const int32_t* col_src;
   float* alpha;                    // [E, H] softmax weights, CSR order: input (logit_terms == NULL) or scratch
   const float* logit_terms;        // [E, H] hop-invariant logit terms, CSR order: softmax in the tile prologue
-  const float* a_node;             // [parts][N][2H] node logits a_l | a_r (partial sums)
+  const float* a_node;             // [parts][N][ld_an >= 2H] node logits a_l | a_r (partial sums)
   int64_t a_node_part_stride;
+  int32_t ld_an;
+  int32_t early;                   // per-batch inputs (plan, topology, logit terms, constants, weights) are older than the
+                                   // predecessor kernel: they may be read before griddepcontrol.wait
   int32_t a_node_parts;
   float slope;
   const int32_t* node_graph;
@@ -446,7 +449,11 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  pdl_wait();
+  // Programmatic dependent launch: with `early` everything up to the first read of the predecessor's outputs (h_in,
+  // a_node) -- set-up, the plan, the tile's topology and logit terms, the epilogue constants -- overlaps the
+  // predecessor's tail; each role waits right before its first dependent read.
+  const bool early = p.early != 0;
+  if (!early) pdl_wait();
   pdl_launch_dependents();
 
   const int T = __ldg(p.tile_count);
@@ -459,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       if (elect_one()) {
         uint32_t it = 0;
         const uint32_t stage_tx = kABytes + (uint32_t)(H / 2) * (uint32_t)(p.nb >> 1) * 128u;
+        if (early) pdl_wait();
         for (int item = pair_id; item < items; item += npairs) {
           const int prt = item / n_ct, ct = item - prt * n_ct;
           const int te = 2 * prt + rank;
@@ -557,13 +565,14 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
         }
         if (far) *far_s = 1;                               // (benign race: every writer stores 1)
       }
+      if (early && item == pair_id) pdl_wait();            // a_node is the predecessor's output
       if (softmax_here && nrows > 0) {
         // node logits of the window rows, partial sums added in fixed order
         for (int t = ctid; t < WIN * 2 * H / 4; t += kConvThreads) {
           const int L = t / (2 * H / 4), part4 = t - L * (2 * H / 4);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (win0 + L < p.N) {
-            const float* src = p.a_node + (int64_t)(win0 + L) * (2 * H) + 4 * part4;
+            const float* src = p.a_node + (int64_t)(win0 + L) * p.ld_an + 4 * part4;
             v = __ldg(reinterpret_cast<const float4*>(src));
             for (int pt = 1; pt < p.a_node_parts; ++pt) {
               const float4 w = __ldg(reinterpret_cast<const float4*>(src + pt * p.a_node_part_stride));
@@ -616,8 +625,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
         } else if (ctid < nrows) {
           // generic path: one thread per row, everything from global memory, weights to the scratch array
           auto node_term = [&](int64_t node, int col) {
-            float t = __ldg(p.a_node + node * (2 * H) + col);
-            for (int pt = 1; pt < p.a_node_parts; ++pt) t += __ldg(p.a_node + pt * p.a_node_part_stride + node * (2 * H) + col);
+            float t = __ldg(p.a_node + node * p.ld_an + col);
+            for (int pt = 1; pt < p.a_node_parts; ++pt) t += __ldg(p.a_node + pt * p.a_node_part_stride + node * p.ld_an + col);
             return t;
           };
           const int kb = e0 + rp_s[ctid], ke = e0 + rp_s[ctid + 1];
@@ -724,6 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       }
       epi_bar_sync();
       mbar_arrive(cst_full);                               // (the helper warps of the last item wait for this)
+      if (early && item_it == 0) pdl_wait();               // the skip rows are the predecessor's output
       // on the CTA's last item the second converter group, idle by then, takes the upper half of the column passes
       const bool last = item + npairs >= items;
       const int npass = (min(p.C, colb + p.nb) - colb + 31) >> 5;
@@ -883,24 +893,33 @@ __global__ void __launch_bounds__(256) gat_alpha_kernel(const int32_t* __restric
 
 // ---- hop-invariant logit terms of all hops in CSR order (once per batch):
 //   terms[hop][k][h] = a_edge[perm[k]][hop*H + h] + a_graph[hop][graph of the edge's destination][h]
+// One thread per in-edge (CSR position k): the destination row by binary search in rowptr, then per hop one H-wide
+// vector load / store (coalesced stores, 16-byte gathers through perm).
 template <int H>
 __global__ void __launch_bounds__(256) logit_terms_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
                                                           const int32_t* __restrict__ node_graph,
                                                           const float* __restrict__ a_edge, int64_t lde,
                                                           const float* __restrict__ a_graph, int64_t ldag, int64_t hop_stride,
-                                                          int hops, int N, int64_t terms_hop_stride, float* __restrict__ terms) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = t / H, h = t - i * H;
-  if (i >= N) return;
-  const int e0 = rowptr[i], e1 = rowptr[i + 1];
-  if (e1 <= e0) return;
-  const int g = a_graph ? node_graph[i] : 0;
+                                                          int hops, int N, int64_t E, int64_t terms_hop_stride,
+                                                          float* __restrict__ terms) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= E) return;
+  int lo = 0, hi = N - 1;                      // largest row i with rowptr[i] <= k
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(rowptr + mid) <= k) lo = mid;
+    else hi = mid - 1;
+  }
+  const int g = a_graph ? __ldg(node_graph + lo) : 0;
+  const int64_t e = perm ? __ldg(perm + k) : k;
+  const float* ae = a_edge + e * lde;
   for (int hop = 0; hop < hops; ++hop) {
-    const float tg = a_graph ? a_graph[hop * hop_stride + (int64_t)g * ldag + h] : 0.f;
-    for (int k = e0; k < e1; ++k) {
-      const int64_t e = perm ? perm[k] : k;
-      terms[hop * terms_hop_stride + (int64_t)k * H + h] = a_edge[e * lde + hop * H + h] + tg;
-    }
+    float v[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) v[h] = __ldg(ae + hop * H + h) + (a_graph ? __ldg(a_graph + hop * hop_stride + (int64_t)g * ldag + h) : 0.f);
+    float* dst = terms + hop * terms_hop_stride + k * H;
+    if constexpr (H == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
   }
 }
 
@@ -1022,14 +1041,17 @@ extern "C" GVQA_API int gvqa_gat_fused_logit_terms_f32(const int32_t* rowptr, co
     return GVQA_ERR_BAD_SHAPE;
   if (num_nodes == 0 || num_edges == 0) return GVQA_OK;
   if (!rowptr || !a_edge || !terms || (a_graph && !node_graph)) return GVQA_ERR_NULL_POINTER;
-  const dim3 grid((unsigned)((num_nodes * heads + 255) / 256)), block(256);
+  if (!aligned16(terms) || (terms_hop_stride & 3)) return GVQA_ERR_MISALIGNED;
+  const dim3 grid((unsigned)((num_edges + 255) / 256)), block(256);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (heads == 4)
     fused::logit_terms_kernel<4><<<grid, block, 0, st>>>(rowptr, perm, node_graph, a_edge, lde, a_graph, ld_a_graph,
-                                                         hop_stride_a_graph, hops, (int)num_nodes, terms_hop_stride, terms);
+                                                         hop_stride_a_graph, hops, (int)num_nodes, num_edges,
+                                                         terms_hop_stride, terms);
   else if (heads == 2)
     fused::logit_terms_kernel<2><<<grid, block, 0, st>>>(rowptr, perm, node_graph, a_edge, lde, a_graph, ld_a_graph,
-                                                         hop_stride_a_graph, hops, (int)num_nodes, terms_hop_stride, terms);
+                                                         hop_stride_a_graph, hops, (int)num_nodes, num_edges,
+                                                         terms_hop_stride, terms);
   else
     return GVQA_ERR_UNSUPPORTED;
   GVQA_LAUNCH_CHECK();
@@ -1097,6 +1119,9 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
   p.rowptr = a->rowptr; p.col_src = a->col_src; p.alpha = a->alpha; p.node_graph = a->node_graph;
   p.logit_terms = a->logit_terms; p.a_node = a->a_node; p.a_node_parts = a->a_node_parts;
   p.a_node_part_stride = a->a_node_part_stride; p.slope = a->negative_slope;
+  p.early = (a->flags & GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR) && a->logit_terms != nullptr;
+  p.ld_an = a->ld_a_node ? (int)a->ld_a_node : 2 * a->heads;
+  if (a->logit_terms && (p.ld_an < 2 * a->heads || (p.ld_an & 3))) return GVQA_ERR_UNSUPPORTED;
   p.h_in = a->h_in; p.ld_h = ld_h;
   p.skip = a->skip; p.ld_skip = ld_skip;
   p.graph_bias = a->graph_bias; p.ldgb = ldgb;

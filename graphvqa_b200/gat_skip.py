@@ -262,10 +262,11 @@ class gat_seq(nn.Module):
             ins_rows = [pad16(torch.cat([wi.t(), vg.t()])) for wi, vg in zip(w_ins, v_graph)]
             ins_split = split(torch.cat(ins_rows).contiguous())
             ins_ld = ins_rows[0].size(0)
-        w_fused = None
+        w_fused = v0_split = None
         if w_h[0].is_cuda and self.projection == "3xf16" and _cabi.fused_supported(heads, f, c):
             w_fused = [_cabi.fused_pack(w, heads, c, f) for w in w_h]
-        pack = dict(w_h=w_h, w_split=w_split, w_fused=w_fused, w_ins=torch.stack(w_ins), v_node=v_node,
+            v0_split = _cabi.split_f16(pad16(v_node[0]))      # hop 0's node logits ride in the pre-pass GEMM launch
+        pack = dict(w_h=w_h, w_split=w_split, w_fused=w_fused, v0_split=v0_split, w_ins=torch.stack(w_ins), v_node=v_node,
                     v_graph=torch.stack(v_graph), v_edge=v_edge_all, edge_split=edge_split,
                     ins_split=ins_split, ins_ld=ins_ld if ins_split is not None else 0,
                     scale=scale, shift=shift)
@@ -469,15 +470,16 @@ class gat_seq(nn.Module):
             plan, plan_ready = csr.fused_plan(window), None
         ld = pk["ins_ld"]
         bh, bl = (t.unflatten(0, (num_hops, ld)) for t in pk["ins_split"])
-        problems = [(ins, bh, bl, None)]
+        # ONE pre-pass launch: hop 0's node logits x @ [V_l ; V_r]^T, the per-graph instruction terms of all hops and
+        # (with edges) all hops' edge logits in one sweep over edge_attr
+        problems = [(x, pk["v0_split"][0], pk["v0_split"][1], None), (ins, bh, bl, None)]
         if e > 0:
             problems.append((edge_attr, pk["edge_split"][0], pk["edge_split"][1], None))
         outs = _cabi.proj_gemm_3xf16_grouped(problems, overflow=flag)
-        g_all = outs[0]
-        a_edge_all = outs[1] if e > 0 else x.new_zeros(1, num_hops * heads)
+        a_node, g_all = outs[0], outs[1]
+        a_edge_all = outs[2] if e > 0 else x.new_zeros(1, num_hops * heads)
         csr_d = csr.as_dict()
         alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)    # scratch of the kernels' generic path
-        a_node = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
         # hops >= 1 get their node logits from the previous hop's epilogue (partial sums per 128-column block)
         # (two buffers: a hop reads the previous hop's block while it writes its own)
         a_part = torch.empty(2, _cabi.fused_part_blocks(n, c), n, 2 * heads, dtype=torch.float32, device=x.device)
@@ -485,7 +487,6 @@ class gat_seq(nn.Module):
         terms = None
         for i in range(num_hops):
             if i == 0:
-                _cabi.skinny_matmul(h, pk["v_node"][i], out=a_node)
                 if csr_ready is not None:
                     cur.wait_event(csr_ready)
                 if plan_ready is not None:
@@ -505,7 +506,9 @@ class gat_seq(nn.Module):
                                     graph_bias=g_all[i, :, :c], bias=self.convs[i].bias, overflow=flag,
                                     v_next=None if last else pk["v_node"][i + 1], a_part=None if last else a_part[i & 1],
                                     logit_terms=terms[i], a_node=a_node if i == 0 else a_part[(i - 1) & 1],
-                                    negative_slope=self.convs[i].negative_slope, **epi)
+                                    negative_slope=self.convs[i].negative_slope,
+                                    # (the predecessor of hop i >= 1 is hop i - 1: it writes h and the node logits only)
+                                    inputs_older_than_predecessor=i > 0, **epi)
             if self.hop_events is not None:
                 ev[1].record()
                 self.hop_events.append(ev)

@@ -258,6 +258,12 @@ typedef struct gvqa_gat_fused_args {
   int64_t a_node_part_stride;
   int32_t a_node_parts;
   float negative_slope;
+  int64_t ld_a_node;        /* row stride of a_node in floats (0 = dense 2*heads; a multiple of 4): the logits may be
+                               the leading columns of a wider GEMM output                                   */
+  int32_t flags;            /* GVQA_HOP_INPUTS_OLDER_THAN_PREDECESSOR (with logit_terms): tiles, topology, logit_terms,
+                               graph_bias, bias, ep_*, v_next and w_pack were NOT written by the kernel launched
+                               right before this one (in gat_seq that is the previous hop, which writes h_in, a_node):
+                               the kernel reads them while its predecessor drains                          */
   const float* skip;        /* [N, channels] added to every row (gat_skip.py:270), row stride ld_skip; or NULL */
   int64_t ld_skip;
   const float* graph_bias;  /* [B, channels] per-graph instruction term (rows with in-edges only) or NULL */

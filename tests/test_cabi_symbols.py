@@ -90,8 +90,9 @@ def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("gcc not available")
-    fields = {"gvqa_gat_hop_args": [n for n, _ in _cabi.GatHopArgs._fields_],
-              "gvqa_gemm_problem": [n for n, _ in _cabi.GemmProblem._fields_]}
+    classes = (("gvqa_gat_hop_args", _cabi.GatHopArgs), ("gvqa_gemm_problem", _cabi.GemmProblem),
+               ("gvqa_gat_fused_args", _cabi.GatFusedArgs))
+    fields = {struct: [n for n, _ in cls._fields_] for struct, cls in classes}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "gvqa_b200.h"', 'int main(void) {']
     for struct, names in fields.items():
         src.append('  printf("%s %%zu", sizeof(struct %s));' % (struct, struct))
@@ -105,11 +106,44 @@ def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c_file), "-o", str(exe)],
                    check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
-    for line, (struct, cls) in zip(out, (("gvqa_gat_hop_args", _cabi.GatHopArgs), ("gvqa_gemm_problem", _cabi.GemmProblem))):
+    for line, (struct, cls) in zip(out, classes):
         got = line.split()
         assert got[0] == struct
         want = [ctypes.sizeof(cls)] + [getattr(cls, n).offset for n, _ in cls._fields_]
         assert [int(v) for v in got[1:]] == want, struct
+
+
+def test_fused_hop_argument_errors_are_reported_before_any_launch():
+    lib = _cabi.lib()
+    assert lib.gvqa_gat_fused_hop_f32(None, None) == -1
+    assert lib.gvqa_gat_fused_supported(4, 512, 512) == 1 and lib.gvqa_gat_fused_supported(8, 512, 512) == 0
+    assert lib.gvqa_gat_fused_supported(4, 30, 32) == 0                        # widths must be multiples of 4
+    assert lib.gvqa_gat_fused_window(30) == 128 and lib.gvqa_gat_fused_window(200) == 256
+    assert lib.gvqa_gat_fused_part_blocks(7680, 512) == 4 and lib.gvqa_gat_fused_pack_halves(4, 512, 300) == 512 * 4 * 304 * 2
+    a = _cabi.GatFusedArgs()
+    a.num_nodes, a.in_channels, a.channels, a.heads, a.window, a.w_scale = 8, 64, 64, 8, 128, 1.0
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -3           # heads 8: the split path's job
+    a.heads, a.window = 4, 100
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -3           # window must be 128 or 256
+    a.window = 128
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -1           # NULL operands
+    a.h_in = a.w_pack = a.tiles = a.tile_count = a.rowptr = a.col_src = a.node_graph = a.alpha = a.h_out = 256
+    a.epilogue = 2
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -1           # affine epilogue without scale / shift
+    a.epilogue, a.h_out = 0, 260
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -4           # not 16-byte aligned
+    a.h_out, a.num_nodes = 256, 0
+    assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == 0            # nothing to do
+    assert lib.gvqa_gat_fused_plan(None, 4, 128, None, None, 8, None) == -1
+    assert lib.gvqa_gat_fused_plan(256, 4, 100, 256, 256, 8, None) == -2
+
+
+def test_fused_plan_on_the_host():
+    import torch
+    gp = torch.tensor([0, 30, 60, 90, 120, 150, 400, 401], dtype=torch.int32)
+    tiles, count = _cabi.fused_plan_host(gp, 401, 7, 256)
+    assert int(count) == 5          # four graphs of 30 | one of 30 | a 250-node graph in two chunks (window = the graph) | 1
+    assert tiles[:5].tolist() == [[0, 120, 0, 0], [120, 30, 120, 0], [150, 128, 150, 0], [278, 122, 150, 0], [400, 1, 400, 0]]
 
 
 def test_grouped_gemm_argument_errors_are_reported_before_any_launch():
