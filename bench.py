@@ -374,7 +374,7 @@ def collate_throughput(cfg, reps=10):
             "what": "collate.WireCollator: concatenation + int32 narrowing + gvqa_build_csr_host into a pinned arena "
                     "(per-graph tensors in, as a dataset __getitem__ yields them)",
             "wire_bytes": sum(t.numel() * t.element_size() for t in (w.x, w.edge_index, w.edge_attr, w.edge_sign))
-            + sum(t.numel() * t.element_size() for t in w.csr_host.values())}
+            + sum(t.numel() * t.element_size() for t in w.csr_host.values() if torch.is_tensor(t))}
 
 
 def cfg4_sharded(args, dev, rank, world, steps):

@@ -215,6 +215,15 @@ class WireCollator:
             ei.data_ptr(), 4, e, batch.data_ptr(), 4, n, b, parts["rowptr"].data_ptr(), parts["col_src"].data_ptr(),
             parts["perm"].data_ptr(), parts["graph_ptr"].data_ptr(), parts["node_graph"].data_ptr(),
             parts["stats"].data_ptr()), "gvqa_build_csr_host")
+        # the row tiles of the fused hop (gvqa_gat_fused_plan_host): with them the GPU runs no plan kernel either
+        window = _cabi.fused_window(int(parts["stats"][0]))
+        max_tiles = _cabi.lib().gvqa_gat_fused_max_tiles(n, b)
+        parts["tiles"] = arena.get("tiles", 4 * max_tiles, i32).view(max_tiles, 4)
+        parts["tile_count"] = arena.get("tile_count", 1, i32)
+        _cabi.check(_cabi.lib().gvqa_gat_fused_plan_host(parts["graph_ptr"].data_ptr(), b, window, parts["tiles"].data_ptr(),
+                                                          parts["tile_count"].data_ptr(), max_tiles),
+                    "gvqa_gat_fused_plan_host")
+        parts["tile_window"] = window
         return SceneGraphBatch(x=x, edge_index=ei, edge_attr=ea, batch=batch, added_sym_edge=sym.to(i32), edge_sign=sign,
                                num_graphs=b, max_nodes_per_graph=int(parts["stats"][0]),
                                max_in_edges_per_graph=int(parts["stats"][1]), csr_host=parts)

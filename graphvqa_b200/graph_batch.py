@@ -56,7 +56,11 @@ class GraphCSR:
                for k in ("rowptr", "col_src", "perm", "graph_ptr", "node_graph", "stats")}
         n, b = parts["rowptr"].numel() - 1, parts["graph_ptr"].numel() - 1
         e = int(parts["rowptr"][n]) if n >= 0 else 0
-        return GraphCSR(dev, n, e, b, int(st[0]), int(st[1]))
+        csr = GraphCSR(dev, n, e, b, int(st[0]), int(st[1]))
+        if "tiles" in parts:            # the loader also built the fused hop's row tiles (collate.WireCollator)
+            csr._fused_plans[int(parts["tile_window"])] = tuple(
+                parts[k].to(device=device, non_blocking=non_blocking) for k in ("tiles", "tile_count"))
+        return csr
 
     def check(self):
         """Synchronising sanity check (debug / first batch of a new data source): raises when the build counted

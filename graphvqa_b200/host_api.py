@@ -187,7 +187,8 @@ class GraphSideHostRunner(_PipelinedRunner):
     in its final int32 form."""
 
     _csr_keys = ("rowptr", "col_src", "perm", "graph_ptr", "node_graph", "stats")
-    _keys = ("x", "edge_index", "edge_attr", "edge_sign") + _csr_keys + ("instr_vectors", "q0")
+    _plan_keys = ("tiles", "tile_count")         # row tiles of the fused hop, built by the loader as well
+    _keys = ("x", "edge_index", "edge_attr", "edge_sign") + _csr_keys + _plan_keys + ("instr_vectors", "q0")
 
     def __init__(self, model, device, depth=3, use_cuda_graph=True):
         self.model = model
@@ -207,6 +208,7 @@ class GraphSideHostRunner(_PipelinedRunner):
         e = d["edge_index"].size(1)
         hints = self._hints
         csr = GraphCSR({k: d[k] for k in self._csr_keys}, n, e, b, hints[0], hints[1])
+        csr._fused_plans[self._tile_window] = (d["tiles"], d["tile_count"])
         g = SceneGraphBatch(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], batch=d["node_graph"],
                             edge_sign=d["edge_sign"], num_graphs=b, max_nodes_per_graph=hints[0],
                             max_in_edges_per_graph=hints[1])
@@ -227,9 +229,11 @@ class GraphSideHostRunner(_PipelinedRunner):
             host = dict(x=graphs.x, edge_index=graphs.edge_index, edge_attr=graphs.edge_attr,
                         edge_sign=graphs.edge_sign, instr_vectors=instr_vectors, q0=q0, **graphs.csr_host)
             self._hints = (graphs.max_nodes_per_graph, graphs.max_in_edges_per_graph)
+            self._tile_window = int(graphs.csr_host["tile_window"])
         return super().submit(host)
 
     _hints = (0, 0)
+    _tile_window = 128
 
     def __call__(self, graphs, instr_vectors, q0):
         return self.result(self.submit(graphs, instr_vectors, q0))
@@ -237,5 +241,5 @@ class GraphSideHostRunner(_PipelinedRunner):
     @staticmethod
     def bytes_per_batch(graphs, instr_vectors, q0):
         host = [graphs.x, graphs.edge_index, graphs.edge_attr, graphs.edge_sign, instr_vectors, q0] + \
-               [graphs.csr_host[k] for k in GraphSideHostRunner._csr_keys]
+               [graphs.csr_host[k] for k in GraphSideHostRunner._csr_keys + GraphSideHostRunner._plan_keys]
         return sum(t.numel() * t.element_size() for t in host)
