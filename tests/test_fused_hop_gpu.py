@@ -121,6 +121,9 @@ def _hop_reference(t, heads, c, epilogue):
     (3, 150, 220, 3.0, 2, 36, 20, 128, 2),       # window hint too small for the graphs (generic path), tiny widths
     (70, 20, 40, 2.0, 4, 512, 512, 128, 2),      # two column blocks of 256, several items per pair
     (300, 1, 3, 1.0, 4, 32, 32, 128, 2),         # many tiny graphs
+    (190, 90, 128, 1.5, 4, 64, 64, 128, 2),      # ~95 pair tiles on 74 pairs: several items per pair (accumulator
+                                                 # hand-over between items, helper warps on the last item only)
+    (100, 129, 200, 2.0, 2, 32, 160, 256, 1),    # two rounds of two-tile graphs, window 256, ragged column block
 ])
 def test_fused_hop_matches_float64_reference(graphs, n_lo, n_hi, extra, heads, f, c, win, epilogue):
     t = _hop_case(graphs, n_lo, n_hi, extra, heads, f, c, seed=graphs)
