@@ -268,7 +268,7 @@ def _back_to_back(fns, reps=20):
     return e0.elapsed_time(e1) * 1e3 / (2 * reps * len(fns))
 
 
-def variant_rooflines(dev, peak, variant):
+def variant_rooflines(dev, peak, variant, tensor_peak=1675.8):
     """The other HBM-bound kernels of SURVEY.md section 8 at their BASELINE shapes (cfg3 GINE, cfg5 LCGN per GPU,
     graph LayerNorm, GCN) and the fused hop at the reference width F=300 and at cfg4 per GPU, measured in this
     process: algorithmic bytes / duration.  Two durations: `avg_launch_us` = event bracket
@@ -322,6 +322,40 @@ def variant_rooflines(dev, peak, variant):
     hop("gat_hop_cfg2", 256, 30, 60, 512)
     hop("gat_hop_f300", 256, 30, 60, 300)
     hop("gat_hop_cfg4_per_gpu", 128, 200, 800, 512)
+
+    def fused_hop(name, b, n_, e_, f, h=4):
+        """the default one-kernel hop (gvqa_gat_fused_hop_f32) at another shape: tensor-bound, against the bf16 peak"""
+        e, n, _, csr = graphs(b, n_, e_)
+        window = _cabi.fused_window(csr.max_nodes_per_graph)
+        plan = csr.fused_plan(window)
+        w = rnd(h * f, f) * (1.0 / f ** 0.5)
+        pack = _cabi.fused_pack(w, h, f, f)
+        flops = 3 * 2.0 * n * (h * f) * f
+
+        def make():
+            x, o = rnd(n, f), torch.empty(n, f, device=dev)
+            a_node, a_edge, ag = rnd(n, 2 * h), rnd(e, h), rnd(1, b, h)
+            gb, bias, sc, sh, vn = rnd(b, f), rnd(f), rnd(f), rnd(f), rnd(2 * h, f)
+            terms = _cabi.fused_logit_terms(csr.as_dict(), a_edge, ag, 1, h, n)
+            scratch = torch.empty(e, h, device=dev)
+            a_part = torch.empty(_cabi.fused_part_blocks(n, f), n, 2 * h, device=dev)
+            return lambda: _cabi.gat_fused_hop(x, pack, plan, csr.as_dict(), scratch, h, f, o, window=window, skip=x,
+                                               graph_bias=gb, bias=bias, ep_scale=sc, ep_shift=sh,
+                                               epilogue=_cabi.EPI_AFFINE_RELU, v_next=vn, a_part=a_part,
+                                               logit_terms=terms[0], a_node=a_node)
+        nbytes = 4 * (2 * n * f) + 4 * h * f * f
+        sets = max(2, min(12, int(1.5 * (130 << 20) / max(nbytes, 1)) + 1))
+        fns = [make() for _ in range(sets)]
+        us = _bracketed(fns[0], flush)
+        b2b = _back_to_back(fns)
+        out[name] = {"kernel": "gvqa_gat_fused_hop_f32", "bound": "tensor", "achieved": flops / b2b / 1e6, "peak": tensor_peak,
+                     "unit": "TFLOP/s", "frac": flops / b2b / 1e6 / tensor_peak, "avg_launch_us": b2b,
+                     "method": "back to back: %d rotating buffer sets, 20 rounds captured in one CUDA graph, 2 replays" % sets,
+                     "bracketed_us": us, "bracketed_frac": flops / us / 1e6 / tensor_peak,
+                     "tensor_flops_per_launch": flops, "shape": "B=%d, %d nodes/%d edges, F=%d, H=%d" % (b, n_, e_, f, h)}
+    fused_hop("gat_fused_hop_cfg2", 256, 30, 60, 512)
+    fused_hop("gat_fused_hop_f300", 256, 30, 60, 300)
+    fused_hop("gat_fused_hop_cfg4_per_gpu", 128, 200, 800, 512)
     e, n, batch, csr = graphs(256, 30, 60)
     ln = LayerNorm(512).to(dev).eval()
 
@@ -666,7 +700,8 @@ def run_engine(args, rank, local_rank, world):
         del gs_runner
 
         # ---------------- the other kernels of the path, the loader side, the sharded large-graph config --------
-        variants = variant_rooflines(dev, peak, args.variant) if (rank == 0 and not args.skip_variants) else None
+        tensor_peak = (json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}).get("bf16_tflops", 2250.0)
+        variants = variant_rooflines(dev, peak, args.variant, tensor_peak) if (rank == 0 and not args.skip_variants) else None
         sharded = cfg4_sharded(args, dev, rank, world, steps=max(3, min(args.steps, 10))) if (world > 1 and not args.skip_cfg4) else None
         collate = collate_throughput(cfg) if rank == 0 else None
 
@@ -709,8 +744,8 @@ def run_engine(args, rank, local_rank, world):
                                      "(pre-encoded fp32 features) up, node states down; PCIe-bound"},
         # per step: 5 CSR kernels + hops x (projection GEMM + fused hop); the edge-logit and instruction pre-pass
         # products ride in hop 0's projection launch (grouped) or cost two launches of their own
-        "gpu_launches": args.steps * ((5 + 1 + 1 + 1 + hops) if fused else         # CSR, plan, pre-pass GEMM, logit terms, hops
-                                      (5 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
+        "gpu_launches": args.steps * ((4 + 1 + 1 + 1 + hops) if fused else         # CSR (4 kernels), plan, pre-pass GEMM, logit terms, hops
+                                      (4 + (0 if model.group_prepass and model.projection == "3xf16" else 2) + 2 * hops
                                        + (1 if model.use_slabs and args.variant in (0, 5) else 0))),
         "roofline": None,
     }

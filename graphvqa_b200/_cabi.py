@@ -92,6 +92,7 @@ SIGNATURES = {
     "gvqa_gat_fused_part_blocks": (_c_i32, [_c_i64, _c_i32]),
     "gvqa_gat_fused_window": (_c_i32, [_c_i32]),
     "gvqa_gat_fused_plan": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "gvqa_gat_fused_plan_from_batch": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
     "gvqa_gat_fused_plan_host": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64]),
     "gvqa_gat_alpha_f32": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
                                           _c_f32, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp]),
@@ -311,6 +312,21 @@ def fused_plan(graph_ptr, num_nodes, num_graphs, window):
     with torch.cuda.device(graph_ptr.device):
         check(lib().gvqa_gat_fused_plan(ptr(graph_ptr), num_graphs, window, ptr(tiles), ptr(count), max_tiles,
                                         stream_handle(graph_ptr.device)), "gvqa_gat_fused_plan")
+    return tiles, count
+
+
+def fused_plan_from_batch(batch, num_graphs, window):
+    """The same plan from the int64 ``batch`` vector (device): independent of the CSR build."""
+    require_cuda(batch)
+    if batch.dtype != torch.int64 or not batch.is_contiguous():
+        raise ValueError("fused_plan_from_batch: batch must be a contiguous int64 tensor")
+    n = batch.numel()
+    max_tiles = lib().gvqa_gat_fused_max_tiles(n, num_graphs)
+    tiles = torch.empty(max_tiles, 4, dtype=torch.int32, device=batch.device)
+    count = torch.empty(1, dtype=torch.int32, device=batch.device)
+    with torch.cuda.device(batch.device):
+        check(lib().gvqa_gat_fused_plan_from_batch(ptr(batch), n, num_graphs, window, ptr(tiles), ptr(count), max_tiles,
+                                                   stream_handle(batch.device)), "gvqa_gat_fused_plan_from_batch")
     return tiles, count
 
 

@@ -60,12 +60,27 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* __restrict__ de
     int32_t v[kScanItems];
     int32_t tsum = 0;
     // all loads first, then the zero stores: interleaving them serialises 16 dependent global round trips
-    // (the compiler must assume the store may alias the next load) -- measured 12.8 us for N = 7680
+    // (the compiler must assume the store may alias the next load) -- measured 12.8 us for N = 7680.  128-bit
+    // accesses: a thread's 16 consecutive entries are 64 contiguous bytes, and one warp instruction touches 32
+    // different sectors whatever its width, so four wide accesses cost a quarter of sixteen narrow ones
+    const bool full = i0 + kScanItems <= N;
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) v[j] = (i0 + j < N) ? __ldcg(deg + i0 + j) : 0;
+      for (int j = 0; j < kScanItems; j += 4) {
+        const int4 q = __ldcg(reinterpret_cast<const int4*>(deg + i0 + j));
+        v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+      }
+#pragma unroll
+      for (int j = 0; j < kScanItems; j += 4) *reinterpret_cast<int4*>(deg + i0 + j) = make_int4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j) v[j] = (i0 + j < N) ? __ldcg(deg + i0 + j) : 0;
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j)
+        if (i0 + j < N) deg[i0 + j] = 0;
+    }
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-      if (i0 + j < N) deg[i0 + j] = 0;
       local_max = max(local_max, v[j]);
       tsum += v[j];
     }
@@ -90,10 +105,22 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(int32_t* __restrict__ de
     const int32_t carry = carry_s;
     const int32_t warp_off = wid > 0 ? warp_tot[wid - 1] : 0;
     int32_t run = carry + warp_off + incl - tsum;
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
-      if (i0 + j < N) rowptr[i0 + j] = run;
-      run += v[j];
+      for (int j = 0; j < kScanItems; j += 4) {
+        int4 q;
+        q.x = run; run += v[j];
+        q.y = run; run += v[j + 1];
+        q.z = run; run += v[j + 2];
+        q.w = run; run += v[j + 3];
+        *reinterpret_cast<int4*>(rowptr + i0 + j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j) {
+        if (i0 + j < N) rowptr[i0 + j] = run;
+        run += v[j];
+      }
     }
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = run;
@@ -120,9 +147,28 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ edge_index, int64_t 
 // the caller's edge order, then emit perm / col_src.  Also per-graph maxima for the stats.
 __global__ void csr_sort_kernel(const int64_t* __restrict__ edge_index, int64_t N,
                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slots,
-                                int32_t* __restrict__ perm, int32_t* __restrict__ col_src) {
-  const int64_t node = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+                                int32_t* __restrict__ perm, int32_t* __restrict__ col_src,
+                                const int32_t* __restrict__ graph_ptr, int64_t B, int32_t* __restrict__ stats) {
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t node = gtid >> 5;
   const int lane = threadIdx.x & 31;
+  if (gtid < ((B + 31) & ~(int64_t)31)) {       // (whole warps) per-graph maxima for the stats: thread = graph
+    int32_t nn = 0, ne = 0;
+    if (gtid < B) {
+      const int32_t n0 = graph_ptr[gtid], n1 = graph_ptr[gtid + 1];
+      nn = n1 - n0;
+      ne = rowptr[n1] - rowptr[n0];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nn = max(nn, __shfl_xor_sync(kFull, nn, o));
+      ne = max(ne, __shfl_xor_sync(kFull, ne, o));
+    }
+    if (lane == 0) {
+      atomicMax(&stats[0], nn);
+      atomicMax(&stats[1], ne);
+    }
+  }
   if (node >= N) return;
   const int32_t e0 = rowptr[node], e1 = rowptr[node + 1];
   for (int32_t t = e0 + lane; t < e1; t += 32) {
@@ -191,11 +237,11 @@ extern "C" GVQA_API int gvqa_build_csr(const int64_t* edge_index, int64_t E, con
     csr_fill_kernel<<<(unsigned)((E + threads - 1) / threads), threads, 0, stream>>>(edge_index, E, N, rowptr,
                                                                                       cursor, slots);
     GVQA_LAUNCH_CHECK();
-    csr_sort_kernel<<<(unsigned)((N * 32 + threads - 1) / threads), threads, 0, stream>>>(edge_index, N, rowptr,
-                                                                                           slots, perm, col_src);
+    const int64_t sort_threads = (N * 32 > ((B + 31) & ~(int64_t)31)) ? N * 32 : ((B + 31) & ~(int64_t)31);
+    csr_sort_kernel<<<(unsigned)((sort_threads + threads - 1) / threads), threads, 0, stream>>>(
+        edge_index, N, rowptr, slots, perm, col_src, graph_ptr, B, stats);
     GVQA_LAUNCH_CHECK();
-  }
-  if (B > 0) {
+  } else if (B > 0) {
     csr_graph_stats_kernel<<<(unsigned)((B + threads - 1) / threads), threads, 0, stream>>>(graph_ptr, rowptr, B,
                                                                                             stats);
     GVQA_LAUNCH_CHECK();

@@ -789,14 +789,29 @@ __host__ __device__ inline int plan_tiles(const int32_t* graph_ptr, int B, int w
 // a tile starting at it would end (binary search in graph_ptr) and how many tiles it would emit, one thread then walks
 // the chain of starts (two shared-memory loads per tile), and the tiles are written in parallel.  Same result as
 // plan_tiles() on the host.
-__global__ void __launch_bounds__(256) fused_plan_kernel(const int32_t* __restrict__ graph_ptr, int B, int win, int4* tiles,
-                                                         int32_t* count, int max_tiles) {
+__global__ void __launch_bounds__(256) fused_plan_kernel(const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+                                                         int N, int B, int win, int4* tiles, int32_t* count, int max_tiles) {
   extern __shared__ int32_t plan_s[];
   int32_t* gp_s = plan_s;                 // [B + 1]
   int32_t* nxt_s = gp_s + (B + 1);        // [B] first graph after a tile that starts at g
   int32_t* cnt_s = nxt_s + B;             // [B] tiles such a start emits
   int32_t* off_s = cnt_s + B;             // [B] index of its first tile, -1 when g does not start a tile
-  for (int i = threadIdx.x; i <= B; i += blockDim.x) gp_s[i] = graph_ptr[i];
+  if (graph_ptr != nullptr) {
+    for (int i = threadIdx.x; i <= B; i += blockDim.x) gp_s[i] = graph_ptr[i];
+  } else {
+    // graph boundaries straight from the non-decreasing batch vector (what gvqa_build_csr derives as well, ids clamped
+    // the same way): the plan then does not wait for the CSR build
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+      int64_t b = batch[t], prev = t > 0 ? batch[t - 1] : -1;
+      b = b < 0 ? 0 : (b >= B ? (B > 0 ? B - 1 : 0) : b);
+      prev = prev < -1 ? -1 : (prev >= B ? B - 1 : prev);
+      for (int64_t g = prev + 1; g <= b && g <= B; ++g) gp_s[g] = t;
+      if (t == N - 1)
+        for (int64_t g = b + 1; g <= B; ++g) gp_s[g] = N;
+    }
+    if (N == 0)
+      for (int i = threadIdx.x; i <= B; i += blockDim.x) gp_s[i] = 0;
+  }
   __syncthreads();
   for (int g = threadIdx.x; g < B; g += blockDim.x) {
     const int r0 = gp_s[g], n_g = gp_s[g + 1] - r0;
@@ -972,10 +987,11 @@ extern "C" GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph) {
   return max_nodes_per_graph > fused::kBM ? 256 : 128;
 }
 
-extern "C" GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t num_graphs, int32_t window, int32_t* tiles,
-                                            int32_t* count, int64_t max_tiles, void* stream_) {
-  if (num_graphs < 0 || max_tiles < 0 || (window != 128 && window != 256)) return GVQA_ERR_BAD_SHAPE;
-  if (!graph_ptr || !tiles || !count) return GVQA_ERR_NULL_POINTER;
+static int launch_plan(const int32_t* graph_ptr, const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t window,
+                       int32_t* tiles, int32_t* count, int64_t max_tiles, void* stream_) {
+  if (num_graphs < 0 || max_tiles < 0 || num_nodes < 0 || num_nodes >= (1ll << 31) || (window != 128 && window != 256))
+    return GVQA_ERR_BAD_SHAPE;
+  if ((!graph_ptr && !batch && num_nodes > 0) || !tiles || !count) return GVQA_ERR_NULL_POINTER;
   if (!aligned16(tiles)) return GVQA_ERR_MISALIGNED;
   if ((4 * num_graphs + 1) * 4 > 200 * 1024) return GVQA_ERR_UNSUPPORTED;
   const size_t smem = (size_t)(4 * num_graphs + 1) * 4;
@@ -990,9 +1006,22 @@ extern "C" GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t nu
     }
   }
   fused::fused_plan_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream_)>>>(
-      graph_ptr, (int)num_graphs, window, reinterpret_cast<int4*>(tiles), count, (int)max_tiles);
+      graph_ptr, batch, (int)num_nodes, (int)num_graphs, window, reinterpret_cast<int4*>(tiles), count, (int)max_tiles);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
+}
+
+extern "C" GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t num_graphs, int32_t window, int32_t* tiles,
+                                            int32_t* count, int64_t max_tiles, void* stream_) {
+  if (!graph_ptr) return GVQA_ERR_NULL_POINTER;
+  return launch_plan(graph_ptr, nullptr, 0, num_graphs, window, tiles, count, max_tiles, stream_);
+}
+
+extern "C" GVQA_API int gvqa_gat_fused_plan_from_batch(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                                                       int32_t window, int32_t* tiles, int32_t* count, int64_t max_tiles,
+                                                       void* stream_) {
+  if (!batch && num_nodes > 0) return GVQA_ERR_NULL_POINTER;
+  return launch_plan(nullptr, batch, num_nodes, num_graphs, window, tiles, count, max_tiles, stream_);
 }
 
 extern "C" GVQA_API int gvqa_gat_fused_plan_host(const int32_t* graph_ptr_host, int64_t num_graphs, int32_t window,

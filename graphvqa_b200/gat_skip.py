@@ -320,7 +320,7 @@ class gat_seq(nn.Module):
         if self.hop_mode == "fused" and pk.get("w_fused") is not None and self._interleaved_ln is None and n > 0 \
                 and self.gemm_events is None and self.kernel_variant == _cabi.VARIANT_AUTO:
             return self._forward_fused(x, edge_attr, ins, csr, side, csr_ready if side is not None else None, pk, flag,
-                                       return_hops)
+                                       return_hops, batch=batch)
         hc = heads * c
         fused_logits = tensor_core
         ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
@@ -450,7 +450,7 @@ class gat_seq(nn.Module):
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
 
-    def _forward_fused(self, x, edge_attr, ins, csr, side, csr_ready, pk, flag, return_hops):
+    def _forward_fused(self, x, edge_attr, ins, csr, side, csr_ready, pk, flag, return_hops, batch=None):
         """Hops as ONE kernel each (hop_mode "fused"): per hop the collapsed node logits (skinny matvec), the softmax
         weights of all in-edges (gvqa_gat_alpha_f32) and gvqa_gat_fused_hop_f32."""
         num_hops = len(self.convs)
@@ -459,7 +459,18 @@ class gat_seq(nn.Module):
         cur = torch.cuda.current_stream(x.device)
         # per-batch: row tiles (beside the CSR build when that runs on the side stream), pre-pass products
         window = _cabi.fused_window(csr.max_nodes_per_graph or 256)
-        if side is not None:
+        if side is not None and batch is not None and batch.dtype == torch.int64 and window not in csr._fused_plans:
+            # the CSR is being built on the side stream: plan straight from `batch` on a second side stream, beside it
+            side2 = self._side_stream2(x.device)
+            side2.wait_stream(cur)
+            with torch.cuda.stream(side2):
+                plan = _cabi.fused_plan_from_batch(batch.contiguous(), b, window)
+                plan_ready = torch.cuda.Event()
+                plan_ready.record(side2)
+            csr._fused_plans[window] = plan
+            for t in plan:
+                t.record_stream(cur)
+        elif side is not None:
             with torch.cuda.stream(side):
                 plan = csr.fused_plan(window)
                 plan_ready = torch.cuda.Event()
@@ -530,6 +541,12 @@ class gat_seq(nn.Module):
         if self._side is None or self._side.device != device:
             self._side = torch.cuda.Stream(device)
         return self._side
+
+    def _side_stream2(self, device):
+        side2 = self.__dict__.get("_side2")
+        if side2 is None or side2.device != device:
+            side2 = self.__dict__["_side2"] = torch.cuda.Stream(device)
+        return side2
 
     # ---- fp16 range guard of the "3xf16" projection -----------------------------------------------
     # The kernels OR a device flag when an input element does not fit fp16 (|x| >= 65504 or not finite).

@@ -292,6 +292,9 @@ GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t num_graphs)
 GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph);
 GVQA_API int gvqa_gat_fused_plan(const int32_t* graph_ptr, int64_t num_graphs, int32_t window, int32_t* tiles,
                                  int32_t* count, int64_t max_tiles, void* stream);
+/* the same plan straight from the reference's non-decreasing int64 `batch` vector (device): does not wait for the CSR */
+GVQA_API int gvqa_gat_fused_plan_from_batch(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t window,
+                                            int32_t* tiles, int32_t* count, int64_t max_tiles, void* stream);
 GVQA_API int gvqa_gat_fused_plan_host(const int32_t* graph_ptr_host, int64_t num_graphs, int32_t window,
                                       int32_t* tiles_host, int32_t* count_host, int64_t max_tiles);
 GVQA_API int gvqa_gat_alpha_f32(const int32_t* rowptr, const int32_t* col_src, const int32_t* perm,

@@ -48,9 +48,12 @@ def test_plan_device_host_and_reference_agree(sizes, win):
     want = _plan_reference(gp.tolist(), win)
     tiles_h, count_h = _cabi.fused_plan_host(gp, n, b, win)
     tiles_d, count_d = _cabi.fused_plan(gp.to(DEV), n, b, win)
-    assert int(count_h) == int(count_d) == len(want)
+    batch = torch.repeat_interleave(torch.arange(b), torch.tensor(sizes, dtype=torch.long)) if sizes else torch.zeros(0, dtype=torch.long)
+    tiles_b, count_b = _cabi.fused_plan_from_batch(batch.to(DEV), b, win)       # straight from the batch vector
+    assert int(count_h) == int(count_d) == int(count_b) == len(want)
     assert tiles_h[:len(want)].tolist() == want
     assert tiles_d.cpu()[:len(want)].tolist() == want
+    assert tiles_b.cpu()[:len(want)].tolist() == want
     covered = sorted((t[0], t[0] + t[1]) for t in want)       # the tiles partition [0, N)
     assert [c[0] for c in covered] == [0] + [c[1] for c in covered[:-1]] if covered else n == 0
     assert not covered or covered[-1][1] == n
