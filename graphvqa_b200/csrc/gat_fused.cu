@@ -244,6 +244,10 @@ __device__ __forceinline__ void aggregate_any(u64 (&acc)[H][8], int eb, int ee, 
   }
 }
 
+// per-CTA start / end (globaltimer, ns) in rows 100 + blockIdx.x / 4 of the same buffer
+#define GVQA_FUSED_SPAN(which) \
+  do { if (p.trace && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+       p.trace[(100 + (blockIdx.x >> 2)) * 8 + (blockIdx.x & 3) * 2 + (which)] = t_; } } while (0)
 #define GVQA_FUSED_TRACE(slot, col) \
   do { if (p.trace && blockIdx.x == 0 && (slot) < 1100) p.trace[(slot) * 8 + (col)] = clock64(); } while (0)
 
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int pair_id = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  GVQA_FUSED_SPAN(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -745,6 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();         // neither CTA leaves (or frees tensor memory) while its peer may still signal or read it
+  GVQA_FUSED_SPAN(1);
   if (warp == 1)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }

@@ -111,4 +111,13 @@ with torch.no_grad():
         print("epilogue passes: start, acc staged, skip landed, stored, next skip issued, logits done")
         for i in range(1040, 1048):
             print("pass", i - 1040, [int(v) - t0 if v else 0 for v in t[i].tolist()][:6])
+        spans = t[100:137].reshape(-1, 2)[:148]
+        st, en = spans[:, 0], spans[:, 1]
+        base = int(st[st > 0].min())
+        busy = [(i, int(st[i]) - base, int(en[i]) - base) for i in range(148) if int(st[i]) > 0]
+        durs = sorted(e - s_ for _, s_, e in busy)
+        print("per-CTA span (ns): start %d..%d, end %d..%d, duration min/median/max %d/%d/%d" % (
+            min(s_ for _, s_, _ in busy), max(s_ for _, s_, _ in busy), min(e for _, _, e in busy), max(e for _, _, e in busy),
+            durs[0], durs[len(durs) // 2], durs[-1]))
+        print("ends (us) of CTAs 0,2,..: " + " ".join("%.1f" % (e / 1e3) for i, _, e in busy if i % 2 == 0))
         print("prologue: start, lists staged, softmax done", [int(v) - t0 if v else 0 for v in t[1060].tolist()][:3])
