@@ -795,7 +795,7 @@ __host__ __device__ inline int plan_tiles(const int32_t* graph_ptr, int B, int w
 // a tile starting at it would end (binary search in graph_ptr) and how many tiles it would emit, one thread then walks
 // the chain of starts (two shared-memory loads per tile), and the tiles are written in parallel.  Same result as
 // plan_tiles() on the host.
-__global__ void __launch_bounds__(256) fused_plan_kernel(const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
+__global__ void __launch_bounds__(1024) fused_plan_kernel(const int32_t* __restrict__ graph_ptr, const int64_t* __restrict__ batch,
                                                          int N, int B, int win, int4* tiles, int32_t* count, int max_tiles) {
   extern __shared__ int32_t plan_s[];
   int32_t* gp_s = plan_s;                 // [B + 1]
@@ -807,13 +807,25 @@ __global__ void __launch_bounds__(256) fused_plan_kernel(const int32_t* __restri
   } else {
     // graph boundaries straight from the non-decreasing batch vector (what gvqa_build_csr derives as well, ids clamped
     // the same way): the plan then does not wait for the CSR build
-    for (int t = threadIdx.x; t < N; t += blockDim.x) {
-      int64_t b = batch[t], prev = t > 0 ? batch[t - 1] : -1;
-      b = b < 0 ? 0 : (b >= B ? (B > 0 ? B - 1 : 0) : b);
-      prev = prev < -1 ? -1 : (prev >= B ? B - 1 : prev);
-      for (int64_t g = prev + 1; g <= b && g <= B; ++g) gp_s[g] = t;
-      if (t == N - 1)
-        for (int64_t g = b + 1; g <= B; ++g) gp_s[g] = N;
+    for (int base = 0; base < N; base += 4 * (int)blockDim.x) {      // eight independent loads in flight per thread
+      int64_t bv[4], pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = base + i * (int)blockDim.x + (int)threadIdx.x;
+        bv[i] = t < N ? batch[t] : 0;
+        pv[i] = (t < N && t > 0) ? batch[t - 1] : -1;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = base + i * (int)blockDim.x + (int)threadIdx.x;
+        if (t >= N) continue;
+        int64_t b = bv[i], prev = pv[i];
+        b = b < 0 ? 0 : (b >= B ? (B > 0 ? B - 1 : 0) : b);
+        prev = prev < -1 ? -1 : (prev >= B ? B - 1 : prev);
+        for (int64_t g = prev + 1; g <= b && g <= B; ++g) gp_s[g] = t;
+        if (t == N - 1)
+          for (int64_t g = b + 1; g <= B; ++g) gp_s[g] = N;
+      }
     }
     if (N == 0)
       for (int i = threadIdx.x; i <= B; i += blockDim.x) gp_s[i] = 0;
@@ -1011,7 +1023,7 @@ static int launch_plan(const int32_t* graph_ptr, const int64_t* batch, int64_t n
       attr_done = true;
     }
   }
-  fused::fused_plan_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream_)>>>(
+  fused::fused_plan_kernel<<<1, batch ? 1024 : 256, smem, static_cast<cudaStream_t>(stream_)>>>(
       graph_ptr, batch, (int)num_nodes, (int)num_graphs, window, reinterpret_cast<int4*>(tiles), count, (int)max_tiles);
   GVQA_LAUNCH_CHECK();
   return GVQA_OK;
