@@ -12,15 +12,17 @@
 // and hand it to the tensor core through tensor memory.  x_l[N, H*C] -- 63 MB written and 63 MB read back per hop at
 // BASELINE cfg2 -- does not exist, the output of the GEMM is h_out[N, C] itself, and the hop's epilogue (head mean,
 // per-graph instruction term, bias, skip, BatchNorm(eval) affine, ReLU; gat_skip.py:270-275) runs on the accumulators.
-// HBM traffic per hop: read h (15.7 MB) once per column tile from L2, write h_out (15.7 MB).
+// HBM traffic per hop: read h (15.7 MB) once per column block (the second read hits L2), write h_out (15.7 MB).
 //
-// Split-precision product as in proj_gemm_f16.cu: x = hi + 2^-11 lo', three fp16 MMAs with fp32 accumulation in
-// tensor memory (hi*hi alternating between two accumulators per k-slice, both lo terms in a third).
+// Split-precision product: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) UNSCALED (fp16 subnormals keep 2^-24 absolute
+// resolution; the weights are pre-scaled by a power of two so that their low parts stay normal), three fp16 MMAs
+// (lo*hi, hi*lo, hi*hi) accumulated in fp32 in ONE tensor-memory accumulator -- proj_gemm_f16.cu scales lo by 2^11 and
+// needs a separate accumulator for it; here the accumulator budget goes into 256-column items instead.
 //
-// Kernel structure (two-CTA pairs, tcgen05.mma.cta_group::2, M = 256: 128 rows per CTA; N = 128 columns per item):
-//   warp 0       TMA producer: per k-slice of 32 input channels one stage = the [WIN x 32] fp32 window of h rows
-//                (128B swizzle) + for each head the CTA's half of the [128 x (32 hi | 32 lo')] fp16 weight tile
-//   warp 1       MMA issuer (leader CTA, one elected lane): per 16-channel sub-block 3 x H MMAs
+// Kernel structure (two-CTA pairs, tcgen05.mma.cta_group::2, M = 256: 128 rows per CTA; N <= 256 columns per item):
+//   warp 0       TMA producer: per slice of 16 input channels one stage = the [WIN x 16] fp32 window of h rows
+//                (64B swizzle) + for each head pair the CTA's half of the [N x 2 x (16 hi | 16 lo)] fp16 weight tile
+//   warp 1       MMA issuer (leader CTA, one elected lane): per stage 3 x H MMAs of M256 x N x K16
 //   warps 4-11   converters, thread = one destination row: sum of alpha[k,h] * (16 channels of source row k) over
 //                the in-edges for all H heads at once (packed FFMA2 from shared memory), fp16 split, tcgen05.st into
 //                a four-slot tensor-memory ring; two groups of four warps alternate stages.  At the start of an item
