@@ -104,7 +104,7 @@ struct Params {
   int32_t N, F, C, n_ct, nb, ks, epilogue;
   float out_scale;                 // 1 / (heads * weight scale)
   const float* v_next;             // [2H, C] collapsed logit vectors of the NEXT hop, or NULL
-  float* a_part;                   // [2 * n_ct][N][2H] partial node logits of the next hop (two blocks per column block)
+  float* a_part;                   // [3 * n_ct][N][2H] partial node logits of the next hop (three blocks per column block)
   unsigned long long* trace;       // debug only
 };
 
@@ -259,8 +259,8 @@ __device__ __forceinline__ void aggregate_any(u64 (&acc)[H][8], int eb, int ee, 
 // global -> shared by cp.async while pass n is finished; per-column constants come from cst_s (staged once per item:
 // the L1 left beside ~220 KB of shared memory does not hold them).  With v_next the final values go back through the
 // staging block and thread = row accumulates the NEXT hop's collapsed node logits a_l | a_r = h_out . V
-// (gat_skip.py:134-135) into a_part[blk][row][2H]; zero_other: the sibling block blk + 1 gets zeros (nobody else
-// covers it).
+// (gat_skip.py:134-135) into a_part[blk][row][2H]; zero_other: the sibling blocks blk + 1, blk + 2 get zeros (nobody
+// else covers them).
 template <int H>
 __device__ __forceinline__ void run_epilogue(const Params& p, uint32_t accbuf, const float* cst_s, uint32_t tmem_base,
                                              int quarter, int lane, int row0, int nrows, int ct, int pass_begin,
@@ -397,7 +397,10 @@ __device__ __forceinline__ void run_epilogue(const Params& p, uint32_t accbuf, c
 #pragma unroll
     for (int v4 = 0; v4 < 2 * H / 4; ++v4) {
       *reinterpret_cast<float4*>(dst + 4 * v4) = make_float4(part[4 * v4], part[4 * v4 + 1], part[4 * v4 + 2], part[4 * v4 + 3]);
-      if (zero_other) *reinterpret_cast<float4*>(dst + (int64_t)p.N * (2 * H) + 4 * v4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_other) {
+        *reinterpret_cast<float4*>(dst + (int64_t)p.N * (2 * H) + 4 * v4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dst + (int64_t)2 * p.N * (2 * H) + 4 * v4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   if (trace_on && lane == 0) GVQA_FUSED_TRACE(1024, 4);
@@ -698,9 +701,10 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       }
     }
     if (p.overflow != nullptr && !(amax <= 65000.0f)) atomicOr(p.overflow, 1);   // also catches NaN / inf
-    if (grp == 1 && items > pair_id) {
-      // helper epilogue of the CTA's last item: the upper half of the column passes, staged through the first bytes of
-      // the operand ring (no load is in flight or will be issued any more, and acc_full says every MMA has read it)
+    if (items > pair_id) {
+      // helper epilogue of the CTA's last item: group 1 takes the middle third of the column passes, group 0 the last
+      // third, staged through the first bytes of the operand ring (no load is in flight or will be issued any more,
+      // and acc_full says every MMA has read it)
       int last_item = pair_id, n_it = 0;
       while (last_item + npairs < items) {
         last_item += npairs;
@@ -711,9 +715,11 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       int4 tile = make_int4(0, 0, 0, 0);
       if (te < T) tile = __ldg(&p.tiles[te]);
       const int npass = (min(p.C, ct * p.nb + p.nb) - ct * p.nb + 31) >> 5;
+      const int third = (npass + 2) / 3;
+      const int pb = grp == 1 ? third : min(2 * third, npass), pe = grp == 1 ? min(2 * third, npass) : npass;
       mbar_wait(cst_full, n_it & 1);
-      run_epilogue<H>(p, smem_u32(smem) + (uint32_t)quarter * kEpiStageBytes, cst_s, tmem_base, quarter, lane, tile.x, tile.y, ct,
-                      (npass + 1) >> 1, npass, 2 * ct + 1, acc_full, n_it & 1, nullptr, false, false, false);
+      run_epilogue<H>(p, smem_u32(smem) + (uint32_t)((1 - grp) * 4 + quarter) * kEpiStageBytes, cst_s, tmem_base, quarter, lane, tile.x,
+                      tile.y, ct, pb, pe, 3 * ct + 2 - grp, acc_full, n_it & 1, nullptr, false, false, false);
     }
   } else {
     // ===================== epilogue: warp = 32 accumulator rows x the columns of the item =====================
@@ -741,11 +747,11 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       epi_bar_sync();
       mbar_arrive(cst_full);                               // (the helper warps of the last item wait for this)
       if (early && item_it == 0) pdl_wait();               // the skip rows are the predecessor's output
-      // on the CTA's last item the second converter group, idle by then, takes the upper half of the column passes
+      // on the CTA's last item the two converter groups, idle by then, take the upper two thirds of the column passes
       const bool last = item + npairs >= items;
       const int npass = (min(p.C, colb + p.nb) - colb + 31) >> 5;
-      const int split = last ? (npass + 1) >> 1 : npass;
-      run_epilogue<H>(p, accbuf, cst_s, tmem_base, quarter, lane, tile.x, tile.y, ct, 0, split, 2 * ct, acc_full, item_it & 1,
+      const int split = last ? (npass + 2) / 3 : npass;
+      run_epilogue<H>(p, accbuf, cst_s, tmem_base, quarter, lane, tile.x, tile.y, ct, 0, split, 3 * ct, acc_full, item_it & 1,
                       acc_empty, !last, true, item_it == 0 && warp == kFirstEpiWarp);
     }
   }
@@ -1000,7 +1006,7 @@ extern "C" GVQA_API int64_t gvqa_gat_fused_max_tiles(int64_t num_nodes, int64_t 
 extern "C" GVQA_API int32_t gvqa_gat_fused_part_blocks(int64_t num_nodes, int32_t channels) {
   int n_ct, nb;
   fused::column_blocks(num_nodes, channels, &n_ct, &nb);
-  return 2 * n_ct;
+  return 3 * n_ct;
 }
 
 extern "C" GVQA_API int32_t gvqa_gat_fused_window(int32_t max_nodes_per_graph) {
@@ -1186,7 +1192,7 @@ extern "C" GVQA_API int gvqa_gat_fused_hop_f32(const gvqa_gat_fused_args* a, voi
   p.v_next = a->v_next;
   p.a_part = a->a_part;
   if (a->v_next && (!a->a_part || !aligned16(a->v_next) || !aligned16(a->a_part))) return GVQA_ERR_MISALIGNED;
-  if (a->v_next && a->a_part_blocks != 2 * n_ct) return GVQA_ERR_BAD_SHAPE;
+  if (a->v_next && a->a_part_blocks != 3 * n_ct) return GVQA_ERR_BAD_SHAPE;
   p.trace = g_fused_trace;
 
   void (*kernel)(const Params) = nullptr;

@@ -119,7 +119,7 @@ def test_fused_hop_argument_errors_are_reported_before_any_launch():
     assert lib.gvqa_gat_fused_supported(4, 512, 512) == 1 and lib.gvqa_gat_fused_supported(8, 512, 512) == 0
     assert lib.gvqa_gat_fused_supported(4, 30, 32) == 0                        # widths must be multiples of 4
     assert lib.gvqa_gat_fused_window(30) == 128 and lib.gvqa_gat_fused_window(200) == 256
-    assert lib.gvqa_gat_fused_part_blocks(7680, 512) == 4 and lib.gvqa_gat_fused_pack_halves(4, 512, 300) == 512 * 4 * 304 * 2
+    assert lib.gvqa_gat_fused_part_blocks(7680, 512) == 6 and lib.gvqa_gat_fused_pack_halves(4, 512, 300) == 512 * 4 * 304 * 2
     a = _cabi.GatFusedArgs()
     a.num_nodes, a.in_channels, a.channels, a.heads, a.window, a.w_scale = 8, 64, 64, 8, 128, 1.0
     assert lib.gvqa_gat_fused_hop_f32(ctypes.byref(a), None) == -3           # heads 8: the split path's job
