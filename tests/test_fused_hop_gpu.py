@@ -299,3 +299,42 @@ def test_gat_seq_fused_golden_refdims(golden):
     with torch.no_grad():
         out = e(*[fx[k].to(DEV) for k in ("x", "edge_index", "edge_attr", "instr_vectors", "batch")]).cpu()
     assert (out - fx["out"]).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_gat_seq_fused_equals_split_on_random_shapes(seed):
+    """Fuzz: random widths (multiples of 4), head counts, graph-size mixes (empty, single-node, > 128 and > 256 nodes),
+    edge densities and hop counts -- the one-kernel hop against the projection GEMM + hop kernel pair."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    f = 4 * ri(3, 80)
+    d = 4 * ri(2, 40)
+    heads, hops = (2, 4)[ri(0, 1)], ri(1, 4)
+    cfg = dict(in_channels=f, out_channels=f, edge_attr_dim=f, ins_dim=d, num_ins=hops, gat_heads=heads)
+    _, e = _pair(cfg, seed=seed)
+    sizes = [ri(0, 3) for _ in range(ri(0, 6))] + [ri(1, 60) for _ in range(ri(1, 30))]
+    if seed % 3 == 0:
+        sizes += [ri(129, 300)]
+    if seed % 4 == 1:
+        sizes += [ri(257, 400)]
+    order = torch.randperm(len(sizes), generator=g).tolist()
+    sizes = [sizes[i] for i in order]
+    src, dst, batch, off = [], [], [], 0
+    for b, n in enumerate(sizes):
+        m = int(n * (0.5 + 3 * float(torch.rand(1, generator=g))))
+        if n:
+            src += (torch.randint(0, n, (m,), generator=g) + off).tolist() + list(range(off, off + n))[: n // 2]
+            dst += (torch.randint(0, n, (m,), generator=g) + off).tolist() + list(range(off, off + n))[: n // 2]
+        batch += [b] * n
+        off += n
+    ei = torch.tensor([src, dst], dtype=torch.long).reshape(2, -1)
+    batch = torch.tensor(batch, dtype=torch.long)
+    args = [a.to(DEV) for a in _inputs(ei, batch, len(sizes), f, f, d, hops, seed=seed + 7)]
+    with torch.no_grad():
+        e.hop_mode = "fused"
+        got = e(*args)
+        e.hop_mode = "split"
+        want = e(*args)
+    e.check_overflow()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max() <= TOL, "seed %d: max|d| = %g" % (seed, (got - want).abs().max())
