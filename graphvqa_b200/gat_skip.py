@@ -273,7 +273,15 @@ class gat_seq(nn.Module):
         self._packed[self.projection] = pack
         return pack
 
-    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, csr=None, return_hops=False, csr_hints=None):
+    def fused_path_ready(self):
+        """True when forward() will run the one-kernel hops (and therefore accepts ``a_edge_all`` in place of
+        ``edge_attr``)."""
+        return (self.hop_mode == "fused" and self.projection == "3xf16" and self.kernel_variant == _cabi.VARIANT_AUTO
+                and self._interleaved_ln is None and self.gemm_events is None and not self.training
+                and self.convs[0].lin_l.weight.is_cuda and self.packed().get("w_fused") is not None)
+
+    def forward(self, x, edge_index, edge_attr, instr_vectors, batch, csr=None, return_hops=False, csr_hints=None,
+                a_edge_all=None):
         """x [N,F], edge_index [2,E] i64, edge_attr [E,Fe], instr_vectors [num_ins,B,D], batch [N] i64
         -> h [N,F].  ``csr`` (a GraphCSR) may be passed to reuse the per-batch pre-pass; otherwise it is built
         here, on a side stream, concurrently with the pre-pass GEMMs and the first projection (none of which
@@ -298,7 +306,8 @@ class gat_seq(nn.Module):
         csr_d = csr.as_dict()
         pk = self.packed()
         x = x.contiguous().float()
-        edge_attr = edge_attr.contiguous().float()
+        if edge_attr is not None:
+            edge_attr = edge_attr.contiguous().float()
         ins = instr_vectors[:num_hops].contiguous().float()
 
         # hop-invariant pre-pass: all hops' edge logits in one sweep over edge_attr, and the
@@ -320,7 +329,7 @@ class gat_seq(nn.Module):
         if self.hop_mode == "fused" and pk.get("w_fused") is not None and self._interleaved_ln is None and n > 0 \
                 and self.gemm_events is None and self.kernel_variant == _cabi.VARIANT_AUTO:
             return self._forward_fused(x, edge_attr, ins, csr, side, csr_ready if side is not None else None, pk, flag,
-                                       return_hops, batch=batch)
+                                       return_hops, batch=batch, a_edge_all=a_edge_all)
         hc = heads * c
         fused_logits = tensor_core
         ldx = hc + (-(-2 * heads // 16) * 16 if fused_logits else 0)
@@ -450,7 +459,7 @@ class gat_seq(nn.Module):
             self._queue_overflow_check()
         return (h, hops) if return_hops else h
 
-    def _forward_fused(self, x, edge_attr, ins, csr, side, csr_ready, pk, flag, return_hops, batch=None):
+    def _forward_fused(self, x, edge_attr, ins, csr, side, csr_ready, pk, flag, return_hops, batch=None, a_edge_all=None):
         """Hops as ONE kernel each (hop_mode "fused"): per hop the collapsed node logits (skinny matvec), the softmax
         weights of all in-edges (gvqa_gat_alpha_f32) and gvqa_gat_fused_hop_f32."""
         num_hops = len(self.convs)
@@ -484,11 +493,15 @@ class gat_seq(nn.Module):
         # ONE pre-pass launch: hop 0's node logits x @ [V_l ; V_r]^T, the per-graph instruction terms of all hops and
         # (with edges) all hops' edge logits in one sweep over edge_attr
         problems = [(x, pk["v0_split"][0], pk["v0_split"][1], None), (ins, bh, bl, None)]
-        if e > 0:
+        if e > 0 and a_edge_all is None:
             problems.append((edge_attr, pk["edge_split"][0], pk["edge_split"][1], None))
         outs = _cabi.proj_gemm_3xf16_grouped(problems, overflow=flag)
         a_node, g_all = outs[0], outs[1]
-        a_edge_all = outs[2] if e > 0 else x.new_zeros(1, num_hops * heads)
+        if a_edge_all is None:
+            a_edge_all = outs[2] if e > 0 else x.new_zeros(1, num_hops * heads)
+        elif a_edge_all.dtype != torch.float32 or a_edge_all.dim() != 2 or a_edge_all.stride(1) != 1 \
+                or a_edge_all.size(0) != e or a_edge_all.size(1) < num_hops * heads:
+            raise ValueError("gat_seq: a_edge_all must be float32 [E, >= hops*heads] with unit column stride")
         csr_d = csr.as_dict()
         alpha = torch.empty(max(e, 1), heads, dtype=torch.float32, device=x.device)    # scratch of the kernels' generic path
         # hops >= 1 get their node logits from the previous hop's epilogue (partial sums per 128-column block)

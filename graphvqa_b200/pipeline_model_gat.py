@@ -234,10 +234,30 @@ class _MetaLayer(nn.Module):
         self.node_model = _NodeModel(nf, ef)
         self._lin = _TensorCoreLinear()
 
-    def forward(self, x, edge_index, edge_attr, csr):
+    def _folded_edge_weights(self, v_edge):
+        """The edge model's last Linear feeds two LINEAR consumers only when the hop stack takes the fused path: the node
+        model's first layer (edge half) and gat_seq's collapsed edge-logit vectors.  [W1n_e ; V] @ W2e and the matching
+        bias, in float64, cached per parameter version."""
+        em, nm = self.edge_model.edge_mlp, self.node_model
+        nf = em[2].weight.size(0)
+        w1n = nm.node_mlp_1[0].weight
+        key = ("fold",) + tuple((t.data_ptr(), t._version) for t in (em[2].weight, em[2].bias, w1n, v_edge))
+        hit = self._lin._cache.get(key)
+        if hit is None:
+            w2, b2 = em[2].weight.detach().double(), em[2].bias.detach().double()
+            stack = torch.cat([w1n[:, nf:].detach().double(), v_edge.detach().double()])      # [c1 + R, F]
+            hit = self._lin._cache[key] = ((stack @ w2).float().contiguous(), (stack @ b2).float().contiguous())
+        return hit
+
+    def forward(self, x, edge_index, edge_attr, csr, edge_logit_weight=None):
         """The first Linear of every MLP acts on a concatenation of gathered rows; it is evaluated as a
         sum of per-part projections (node-level GEMMs) followed by one fused gather+add+bias+ReLU kernel,
-        so [E,900] / [E,600] are never materialised; scatter_mean runs over the destination-CSR."""
+        so [E,900] / [E,600] are never materialised; scatter_mean runs over the destination-CSR.
+
+        ``edge_logit_weight`` [R, F] (gat_seq's collapsed edge-logit vectors of all hops): the updated edge features
+        e' are then NOT materialised -- both of their consumers are linear, so the edge model's last Linear is folded
+        into them (one GEMM of width c + R instead of two of width F and c plus the hop stack's edge-logit sweep) --
+        and the second return value is ``a_edge_all`` [E, R] instead of e'."""
         nf = x.size(1)
         d = csr.as_dict()
         em, nm = self.edge_model.edge_mlp, self.node_model
@@ -252,9 +272,17 @@ class _MetaLayer(nn.Module):
         px, ec = lin.group([(x, wx, bx, False), (edge_attr, w1e[:, 2 * nf:], None, False)])
         xa, xb, x1, x2 = px[:, :c], px[:, c:2 * c], px[:, 2 * c:2 * c + nf], px[:, 2 * c + nf:]
         # edge model: e' = W2 relu(W1 [x_src | x_dst | e] + b1) + b2
-        e_new = lin(_cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index), em[2].weight, em[2].bias)
+        e_hid = _cabi.gather_add_relu(xa, xb, ec, em[0].bias, edge_index)
+        if edge_logit_weight is None:
+            e_new = lin(e_hid, em[2].weight, em[2].bias)
+            t1 = lin(e_new, w1n[:, nf:])
+        else:
+            wf, bf = self._folded_edge_weights(edge_logit_weight)
+            both = lin(e_hid, wf, bf)                        # [E, c1 + R]: node model term | edge logits of all hops
+            c1 = w1n.size(0)
+            t1, e_new = both[:, :c1], both[:, c1:]
         # node model 1 on the UPDATED edges, mean over in-edges, node model 2 on [x | agg]
-        msg = lin(_cabi.gather_add_relu(x1, None, lin(e_new, w1n[:, nf:]), nm.node_mlp_1[0].bias, edge_index),
+        msg = lin(_cabi.gather_add_relu(x1, None, t1, nm.node_mlp_1[0].bias, edge_index),
                   nm.node_mlp_1[2].weight, nm.node_mlp_1[2].bias)
         agg = _cabi.segment_mean_rows(msg, d, mean=True)
         # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns (x2 carries b1)
@@ -272,7 +300,8 @@ class GroundTruth_SceneGraph_Encoder(nn.Module):
         self.scene_graph_encoding_layer = _MetaLayer(self.sg_emb_dim, self.sg_emb_dim)
         self.graph_layer_norm = LayerNorm(self.sg_emb_dim)
 
-    def forward(self, gt_scene_graphs, csr=None):
+    def forward(self, gt_scene_graphs, csr=None, edge_logit_weight=None):
+        """``edge_logit_weight``: see _MetaLayer.forward (the second return value is then gat_seq's ``a_edge_all``)."""
         g = gt_scene_graphs
         table = self.sg_vocab_embedding.weight.detach()
         # token-embedding sums in one kernel each ([N,12,F] / [E,1,F] are never materialised).  The reference negates
@@ -288,7 +317,7 @@ class GroundTruth_SceneGraph_Encoder(nn.Module):
         e_sum = _cabi.embedding_sum(table, g.edge_attr, sign)
         if csr is None:
             csr = _batch_csr(g, int(g.batch.max()) + 1 if getattr(g, "num_graphs", None) is None else g.num_graphs)
-        x_enc, e_enc = self.scene_graph_encoding_layer(x_sum, g.edge_index, e_sum, csr)
+        x_enc, e_enc = self.scene_graph_encoding_layer(x_sum, g.edge_index, e_sum, csr, edge_logit_weight=edge_logit_weight)
         return self.graph_layer_norm(x_enc, g.batch, csr=csr), e_enc, None
 
 
@@ -438,10 +467,24 @@ class PipelineModel(nn.Module):
             self._range_flag.zero_()
         return bad
 
+    def _edge_logit_shortcut(self, g):
+        """gat_seq's collapsed edge-logit vectors [hops*H, Fe] when the hop stack will take the fused path (which consumes
+        the encoded edge features through them only), else None."""
+        seq = getattr(self, "gat_seq", None)
+        if seq is None or not hasattr(seq, "fused_path_ready") or g.edge_index.size(1) == 0:
+            return None
+        return seq.packed()["v_edge"] if seq.fused_path_ready() else None
+
     def _graph_side_once(self, g, instr_vectors, questions_encoded, num_graphs, csr, encoded):
-        if encoded is None:
-            encoded = self.scene_graph_encoder(g, csr=csr)
-        x_executed = self._execute(encoded[0], encoded[1], g, instr_vectors, questions_encoded, csr)
+        v_edge = self._edge_logit_shortcut(g) if encoded is None else None
+        if v_edge is not None:
+            x_enc, a_edge_all, _ = self.scene_graph_encoder(g, csr=csr, edge_logit_weight=v_edge)
+            x_executed = self.gat_seq(x=x_enc, edge_index=g.edge_index, edge_attr=None, instr_vectors=instr_vectors,
+                                      batch=g.batch, csr=csr, a_edge_all=a_edge_all)
+        else:
+            if encoded is None:
+                encoded = self.scene_graph_encoder(g, csr=csr)
+            x_executed = self._execute(encoded[0], encoded[1], g, instr_vectors, questions_encoded, csr)
         q0 = questions_encoded[0]
         pooled = self.graph_global_attention_pooling(x=x_executed, u=q0, batch=g.batch, size=num_graphs,
                                                      graph_ptr=csr.graph_ptr, node_graph=csr.node_graph)

@@ -142,6 +142,13 @@ def test_encoder_and_graph_side_match_reference_goldens(golden):
         logits = m.graph_side(g, fx["instr_vectors"].to(DEV), q_enc, 4).cpu()
         csr = g.csr()
         enc = m.scene_graph_encoder(g, csr=csr)
+        # graph_side without pre-encoded inputs folds the edge model's last Linear into its two linear consumers (the
+        # node model's edge half and gat_seq's edge-logit vectors: edge_attr_encoded is not materialised); with them it
+        # takes the layer-by-layer route: both must agree, and both must match the reference
+        assert m.gat_seq.fused_path_ready() and m._edge_logit_shortcut(g) is not None
+        logits_unfolded = m.graph_side(g, fx["instr_vectors"].to(DEV), q_enc, 4, csr=csr, encoded=enc).cpu()
+        assert (logits - logits_unfolded).abs().max() <= TOL
+        assert (logits_unfolded - base["short_answer_logits"]).abs().max() <= TOL
         x_exec = m.gat_seq(enc[0], g.edge_index, enc[1], fx["instr_vectors"].to(DEV), g.batch, csr=csr)
         pooled = m.graph_global_attention_pooling(x_exec, fx["q0"].to(DEV), g.batch, size=4, graph_ptr=csr.graph_ptr,
                                                   node_graph=csr.node_graph)
