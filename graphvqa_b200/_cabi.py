@@ -687,20 +687,23 @@ def l2_window(tensor, device, hit_ratio=1.0):
 
 def gather_add_relu(a, b, c, bias, edge_index, relu=True):
     """out[k] = act(a[src_k] + b[dst_k] + c[k] + bias); edge_index [2,E] int64 (reference layout) or int32 (the
-    loader-side wire format); a / b / c float32 [., F] with unit column stride (row-strided views are fine)."""
+    loader-side wire format); a / b / c float32 [., F] with unit column stride (row-strided views are fine).
+    ``edge_index=None``: no gather, out[k] = act(a[k] + b[k] + c[k] + bias) over the rows of ``a``."""
     require_cuda(a, b, c, bias, edge_index)
     require_f32c(bias=bias)
     for name, t in (("a", a), ("b", b), ("c", c)):
         if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
             raise ValueError("gather_add_relu: %s must be float32 [., F] with unit column stride" % name)
-    if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+    if edge_index is not None and (edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2
+                                   or edge_index.size(0) != 2):
         raise TypeError("gather_add_relu: edge_index must be int64 or int32 [2, E]")
-    e, f = edge_index.size(1), a.size(1)
+    e, f = (edge_index.size(1) if edge_index is not None else a.size(0)), a.size(1)
     out = torch.empty(e, f, dtype=torch.float32, device=a.device)
     ld = lambda t: 0 if t is None else (t.stride(0) if t.size(0) > 1 else f)
     with torch.cuda.device(a.device):
         check(lib().gvqa_gather_add_relu_strided_f32(ptr(a), ld(a), ptr(b), ld(b), ptr(c), ld(c), ptr(bias),
-                                                     ptr(edge_index.contiguous()), edge_index.element_size(), ptr(out), e, f,
+                                                     ptr(None if edge_index is None else edge_index.contiguous()),
+                                                     8 if edge_index is None else edge_index.element_size(), ptr(out), e, f,
                                                      1 if relu else 0, stream_handle(a.device)),
               "gvqa_gather_add_relu_strided_f32")
     return out

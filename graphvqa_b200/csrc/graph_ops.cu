@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) gather_add_relu_kernel(
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (k >= E) return;
-  const int64_t src = edge_index[k], dst = edge_index[E + k];
+  const int64_t src = edge_index ? (int64_t)edge_index[k] : k, dst = edge_index ? (int64_t)edge_index[E + k] : k;
   const int F4 = F >> 2;
   for (int c4 = lane; c4 < F4; c4 += 32) {
     float4 v = ldg_cached(a + src * lda + 4 * c4);
@@ -218,7 +218,7 @@ extern "C" GVQA_API int gvqa_gather_add_relu_strided_f32(const float* a, int64_t
                                                          int64_t num_edges, int32_t feat, int32_t relu, void* stream_) {
   if (num_edges < 0 || feat <= 0 || lda < feat || (b && ldb < feat) || (c && ldc < feat)) return GVQA_ERR_BAD_SHAPE;
   if (num_edges == 0) return GVQA_OK;
-  if (!a || !edge_index || !out) return GVQA_ERR_NULL_POINTER;
+  if (!a || !out) return GVQA_ERR_NULL_POINTER;      // edge_index == NULL: no gather, out[k] = act(a[k] + b[k] + c[k] + bias)
   if ((feat & 3) || (index_bytes != 4 && index_bytes != 8)) return GVQA_ERR_UNSUPPORTED;
   if (!aligned16(a) || !aligned16(out) || (b && !aligned16(b)) || (c && !aligned16(c)) || (bias && !aligned16(bias)) ||
       (lda & 3) || (ldb & 3) || (ldc & 3))

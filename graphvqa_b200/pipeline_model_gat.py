@@ -286,7 +286,7 @@ class _MetaLayer(nn.Module):
                   nm.node_mlp_1[2].weight, nm.node_mlp_1[2].bias)
         agg = _cabi.segment_mean_rows(msg, d, mean=True)
         # node model 2: W2 relu(W1 [x | agg] + b1) + b2 with the concatenation split over W1's columns (x2 carries b1)
-        hid = torch.relu_(lin(agg, w1m[:, nf:]).add_(x2))
+        hid = _cabi.gather_add_relu(lin(agg, w1m[:, nf:]), None, x2, None, None)      # relu(. + x2), no gather
         return lin(hid, nm.node_mlp_2[2].weight, nm.node_mlp_2[2].bias), e_new
 
 

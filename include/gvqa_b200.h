@@ -440,7 +440,8 @@ GVQA_API int gvqa_gather_add_relu_i32_f32(const float* a, const float* b, const 
                                           const int32_t* edge_index, float* out, int64_t num_edges,
                                           int32_t feat, int32_t relu, void* stream);
 /* general form: a / b / c are row-strided views (lda, ldb, ldc floats, multiples of 4), e.g. column blocks of one
- * stacked GEMM output; index_bytes 4 or 8 */
+ * stacked GEMM output; index_bytes 4 or 8.  edge_index == NULL: no gather, out[k] = act(a[k] + b[k] + c[k] + bias)
+ * (the node model's  relu(W1 [x | agg] + b1)  with the concatenation split over W1's columns) */
 GVQA_API int gvqa_gather_add_relu_strided_f32(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c,
                                               int64_t ldc, const float* bias, const void* edge_index,
                                               int32_t index_bytes, float* out, int64_t num_edges, int32_t feat,
