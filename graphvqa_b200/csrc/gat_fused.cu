@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
   float* alpha_s = reinterpret_cast<float*>(epi_stage + kEpiWarps * kEpiStageBytes);       // [kEdgeCap][H]
   int32_t* src_s = reinterpret_cast<int32_t*>(alpha_s + kEdgeCap * H);                     // [kEdgeCap] window-local
   int32_t* rp_s = src_s + kEdgeCap;                                                        // [kBM + 1], then a flag word
-  int32_t* far_s = rp_s + kBM + 2;                        // != 0: some source of the tile lies outside the window
+  int32_t* far_s = rp_s + kBM + 2;                        // [2] != 0: some source of the tile lies outside the window
+                                                          // (one word per item parity: cleared an item ahead)
   float* an_s = reinterpret_cast<float*>(rp_s + kBM + 4);                                  // [WIN][2H] a_l | a_r
   float* cst_s = an_s + WIN * 2 * H;                      // [3 + 2H][kMaxNB]: bias, scale, shift, next hop's V rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(cst_s + (3 + 2 * H) * kMaxNB);
@@ -543,7 +544,9 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
     const uint32_t ta0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTmemA;
     uint32_t it = 0;
     float amax = 0.f;
-    for (int item = pair_id; item < items; item += npairs) {
+    if (ctid == 0) far_s[0] = far_s[1] = 0;
+    int item_par = 0;
+    for (int item = pair_id; item < items; item += npairs, item_par ^= 1) {
       const int prt = item / n_ct;
       const int te = 2 * prt + rank;
       int4 tile = make_int4(0, 0, 0, 0);
@@ -551,7 +554,6 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       const int row0 = tile.x, nrows = tile.y, win0 = tile.z;
       if (ctid == 0) GVQA_FUSED_TRACE(1060, 0);
       conv_bar_sync();                                     // the previous item's lists are no longer read
-      if (ctid == 0) *far_s = 0;
       int e0 = 0, ne = 0;
       if (nrows > 0) {
         e0 = __ldg(p.rowptr + row0);
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
             *reinterpret_cast<float2*>(alpha_s + 2 * k) = __ldg(reinterpret_cast<const float2*>(lsrc) + e0 + k);
           }
         }
-        if (far) *far_s = 1;                               // (benign race: every writer stores 1)
+        if (far) far_s[item_par] = 1;                      // (every writer stores 1)
       }
       if (early && item == pair_id) pdl_wait();            // a_node is the predecessor's output
       if (softmax_here && nrows > 0) {
@@ -594,7 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) gat_fused_hop_kernel(const __grid
       }
       conv_bar_sync();
       if (ctid == 0) GVQA_FUSED_TRACE(1060, 1);
-      const bool fast = staged && *far_s == 0;
+      const bool fast = staged && far_s[item_par] == 0;
+      if (ctid == 0) far_s[item_par ^ 1] = 0;              // the other word was last read an item ago, behind two barriers
       if (softmax_here) {
         if (fast) {
           // PyG softmax per (row, head) over the row's in-edges (gat_skip.py:183-192), in place in alpha_s
