@@ -45,3 +45,11 @@ print("max |h| per hop: " + " ".join("%.2f" % float(w.abs().max()) for w in want
 for name, errs in rows.items():
     print("%-28s max abs: %s" % (name, " ".join("%.2e" % float(d.abs().max()) for d in errs)))
     print("%-28s rms    : %s" % ("", " ".join("%.2e" % float(d.pow(2).mean().sqrt()) for d in errs)))
+# signed view: does the truncating accumulate shrink the outputs by a consistent factor?
+for mode in ("fused", "split"):
+    outs = []
+    for d, w in zip(rows[mode], want):
+        big = w.abs() > 0.25 * w.abs().max()
+        rel = (d[big] / w[big])
+        outs.append("%.2e (+-%.1e)" % (float(rel.mean()), float(rel.std())))
+    print("%-8s mean (std) of (got - want) / want over entries with |want| > max/4: %s" % (mode, " ".join(outs)))
